@@ -1,0 +1,1 @@
+// ORACLE ONLY: empty stub (see filtering_streambuf.hpp)
