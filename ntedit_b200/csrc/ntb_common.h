@@ -1,0 +1,117 @@
+// Internal types shared by the CUDA kernels, the device engine and the host-side stitcher.
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define NTB_HD __host__ __device__ __forceinline__
+#define NTB_HD_NOINLINE __host__ __device__ __noinline__
+#else
+#define NTB_HD inline
+#define NTB_HD_NOINLINE
+#endif
+
+namespace ntb {
+
+constexpr unsigned KMAX = 96;        // largest supported k
+constexpr unsigned KMIN = 12;        // k must exceed max_deletions (10) -- see DESIGN.md
+constexpr unsigned HMAX = 8;         // largest supported hash_num
+constexpr uint32_t NONE32 = 0xFFFFFFFFu;
+
+// Read-only view of a filter resident in device (or, for the test-only host simulator, host) memory.
+struct FilterView
+{
+	const uint8_t* data;
+	uint64_t bytes;
+	uint64_t mod;    // bit filter: bytes*8 ; counting filter: bytes    (btllib: hash % array_bits / % array_size)
+	uint64_t recip;  // floor((2^64-1)/mod), for the multiply-high remainder
+	uint64_t mask;   // mod-1 when mod is a power of two, else 0
+	uint32_t hash_num;
+	uint32_t counting;
+};
+
+// Parameters of one polishing run, thresholds pre-reduced to integers on the host with the reference's
+// float arithmetic (ntedit.cpp:1531-1535, 1659-1663, 1865-1873, 1892-1897, 1992-1997).
+struct KParams
+{
+	uint32_t k, h;           // from the primary filter
+	uint32_t h_rep;          // hash_num of the -e filter (0 = absent)
+	uint32_t jump;
+	int32_t mode, snv, mask;
+	uint32_t max_ins_tries;  // num_tries[max_insertions], ntedit.cpp:172
+	uint32_t max_deletions;
+	uint32_t thr_missing;    // smallest count c with float(c) >= missing threshold (NONE32 = never)
+	uint32_t thr_edit;       // ... edit threshold
+	uint32_t thr_edit_del;   // ... tryDeletion's variant, ntedit.cpp:1531-1535
+	uint32_t insertion_cap;
+	uint32_t min_threshold, max_threshold;
+	uint32_t counting;
+	// pre-rotated seeds: srol^(k)(S[c]) and srol^(k-1)(S[c]) for the 4 bases (index: A C G T)
+	uint64_t seed_rot_k[4];
+	uint64_t seed_rot_k1[4];
+};
+
+// One unit of device work: walk contig `contig` from tail position `start` (window known to be clean, i.e.
+// made of unedited consecutive bases) until tail position >= `end` with a clean window again.
+struct Task
+{
+	uint64_t text_off;   // offset of the contig in the batch buffer
+	uint32_t len;        // contig length
+	uint32_t start;      // first tail position this task is responsible for
+	uint32_t end;        // first tail position of the next task (== len for the last one)
+	uint32_t contig;
+	uint32_t flags;      // bit0: contig start (run findFirstAcceptedKmer, ntedit.cpp:1773)
+	uint32_t pad_;
+};
+constexpr uint32_t TASK_CONTIG_START = 1u;
+
+// What a walker reports besides its events.
+struct TaskResult
+{
+	uint32_t end_pos;      // tail position at which the walker stopped with a clean window (>= task.end), or len
+	uint32_t first_touch;  // tail position of the first site it evaluated (NONE32 if none)
+	uint32_t last_event;   // index of its last event in the arena (NONE32 if none); events chain through `prev`
+	uint32_t n_events;
+	uint32_t n_sites;
+	uint32_t status;
+	uint8_t stale[4];      // values of the reference's uninitialised locals after the walker's last site (see STALE_REF)
+};
+constexpr uint32_t ST_DONE = 1u;          // finished normally
+constexpr uint32_t ST_CONTIG_END = 2u;    // the reference's main loop ended (roll failed / guard): nothing after this walker counts
+constexpr uint32_t ST_EV_OVERFLOW = 4u;   // event arena exhausted: re-run with a larger arena
+constexpr uint32_t ST_ROPE_OVERFLOW = 8u; // local rope capacity exceeded (unsupported input)
+
+// makeEdit-level event (ntedit.cpp:1250-1448) in the order the reference would perform them.
+struct Event
+{
+	uint32_t prev;        // previous event of the same walker
+	uint32_t t_pos;       // t_seq_i at the time of the call
+	uint32_t advance;     // tail increments (roll calls, ntedit.cpp:2121) since the previous event; NONE32 = anchored:
+	                      // the walker's window was clean in between, the tail sits on the final position node at t_pos
+	uint16_t support;     // best_num_support
+	uint16_t altsupp[3];
+	uint8_t kind;         // best_edit_type: 0 none, 1 substitution, 2 insertion, 3 deletion
+	uint8_t flags;
+	uint8_t draft;        // draft_char
+	uint8_t base;         // best_sub_base
+	uint8_t altbase[3];
+	uint8_t indel_len;    // insertion: number of bases in indel[]; deletion: number of deleted bases
+	char indel[5];        // inserted bases
+	uint8_t pad_;
+};
+static_assert(sizeof(Event) == 36, "Event layout");
+// The reference declares best_sub_base / altbase1..3 without initialisers inside its loop body (ntedit.cpp:1881-1885);
+// the compiled reference keeps them in fixed slots, so a site can report a base that an EARLIER site left behind
+// (observable in mode 2 through tryIndels' altsupp1 side channel).  A walker that starts mid-contig does not know what
+// its predecessors left, so such bytes travel symbolically: STALE_REF|j means "slot j (0 best_sub, 1..3 altbase1..3) as
+// it was when this walker started"; the host resolves them while replaying walkers in contig order.
+constexpr uint8_t STALE_REF = 0x80;
+constexpr uint8_t EV_TOUCHED = 1;  // a substitution trial patched and reverted the tail char: it is now draft (upper case), ntedit.cpp:1975-1981
+
+// Per-launch device counters.
+struct Counters
+{
+	uint32_t n_events;   // arena fill
+	uint32_t overflow;
+};
+
+} // namespace ntb

@@ -1,0 +1,363 @@
+// Batch orchestration of the polishing path, independent of where the kernels run: cut contigs into segments, launch
+// the scan (K1) and the walkers (K2) through a Backend, stitch the per-segment results into the order the
+// reference's strictly sequential loop (ntedit.cpp:1797-2139) would have produced, re-launch the few segments whose
+// speculative clean start turned out to be wrong, then replay the accepted events into ropes (replay.hpp).
+//
+// Backend concept:
+//   void scan_visit(const KParams&);                       -- K1: build the visit bitmap for the whole batch
+//   int  walk(const KParams&, const std::vector<Task>&, std::vector<TaskResult>&, std::vector<Event>&);
+// The product instantiates this with the CUDA backend (capi.cu); tests/hostsim instantiates it with a CPU
+// simulator of the same engine so the stitch/replay logic can be fuzzed without a GPU.
+#pragma once
+#include "replay.hpp"
+
+#include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <cmath>
+#include <memory>
+#include <thread>
+
+namespace ntb {
+
+struct ContigResult
+{
+	bool polished = false;
+	std::vector<ntb_node> nodes;
+	std::vector<ntb_srec> srecs;
+};
+
+struct ResultImpl
+{
+	std::vector<ContigResult> contigs;
+	ntb_stats stats;
+};
+
+// smallest integer count c such that (float)c >= x, as the reference compares (e.g. ntedit.cpp:1659-1663)
+inline uint32_t
+threshold_from_float(float x)
+{
+	if (std::isnan(x)) {
+		return NONE32;
+	}
+	if (x <= 0.0f) {
+		return 0;
+	}
+	if (x > 1.0e9f) {
+		return NONE32;
+	}
+	return (uint32_t)std::ceil(x);
+}
+
+// Fill the kernel parameters from the user parameters with the reference's own float arithmetic.
+inline int
+make_kparams(const ntb_params& u, uint32_t k, uint32_t h, uint32_t h_rep, bool counting, KParams& kp, std::string& err)
+{
+	static const uint32_t num_tries[6] = { 0, 1, 5, 21, 85, 341 }; // ntedit.cpp:172
+	std::memset(&kp, 0, sizeof kp);
+	if (k < KMIN || k > KMAX) {
+		err = "unsupported k (supported: " + std::to_string(KMIN) + ".." + std::to_string(KMAX) + ")";
+		return NTB_EINVAL;
+	}
+	if (h == 0 || h > HMAX || h_rep > HMAX) {
+		err = "unsupported hash_num";
+		return NTB_EINVAL;
+	}
+	if (u.jump == 0) {
+		err = "jump (-j) must be positive";
+		return NTB_EINVAL;
+	}
+	if (u.mode < 0 || u.mode > 2) {
+		err = "mode (-m) must be 0, 1 or 2";
+		return NTB_EINVAL;
+	}
+	uint32_t max_ins = u.max_insertions, max_del = u.max_deletions;
+	if (u.snv) { // ntedit.cpp:2411-2413
+		max_ins = 0;
+		max_del = 0;
+	}
+	if ((max_ins == 0 && max_del > 0) || (max_ins == 1 && max_del > 1)) { // ntedit.cpp:2478-2483
+		max_del = max_ins;
+	}
+	if (max_ins > 5) { // ntedit.cpp:2485-2493
+		max_ins = 5;
+	}
+	if (max_del > 10) {
+		max_del = 10;
+	}
+	kp.k = k;
+	kp.h = h;
+	kp.h_rep = h_rep;
+	kp.jump = u.jump;
+	kp.mode = u.mode;
+	kp.snv = u.snv ? 1 : 0;
+	kp.mask = u.mask ? 1 : 0;
+	kp.max_ins_tries = num_tries[max_ins];
+	kp.max_deletions = max_del;
+	kp.counting = counting ? 1 : 0;
+	kp.min_threshold = (!counting && u.min_threshold != 1) ? 1 : u.min_threshold; // ntedit.cpp:2453-2458
+	kp.max_threshold = u.max_threshold;
+	kp.insertion_cap = (uint32_t)((float)k * 1.5f); // ntedit.cpp:2450-2451 (overrides any -c)
+	const float fk = (float)k;
+	if (!u.use_ratio) {
+		kp.thr_missing = threshold_from_float(fk / u.missing_threshold);
+		kp.thr_edit = threshold_from_float(fk / u.edit_threshold);
+		kp.thr_edit_del = kp.thr_edit;
+	} else {
+		const float per_jump = fk / (float)u.jump;
+		kp.thr_missing = threshold_from_float(per_jump * u.missing_ratio);
+		kp.thr_edit = threshold_from_float(per_jump * u.edit_ratio);
+		kp.thr_edit_del = threshold_from_float((1 + per_jump) * u.edit_ratio); // ntedit.cpp:1533-1535
+	}
+	const uint64_t seeds[4] = { SEED_A, SEED_C, SEED_G, SEED_T };
+	for (int c = 0; c < 4; c++) {
+		kp.seed_rot_k[c] = sroln(seeds[c], k);
+		kp.seed_rot_k1[c] = sroln(seeds[c], k - 1);
+	}
+	return NTB_OK;
+}
+
+struct Segment
+{
+	uint32_t contig;
+	uint32_t p0, p1;      // nominal range of tail positions
+	uint32_t run_start;   // start of the run whose result is stored
+	int32_t arena;        // which round's event arena holds the events (-1: no result yet)
+	TaskResult res;
+};
+
+template<class Backend>
+int
+polish_run(Backend& be, const KParams& kp, const ntb_params& up, char* host_bases, const uint64_t* offsets, uint64_t n_contigs,
+           ResultImpl& out, std::string& err)
+{
+	using clk = std::chrono::steady_clock;
+	out.contigs.assign(n_contigs, ContigResult());
+	std::memset(&out.stats, 0, sizeof out.stats);
+	uint32_t seg_len = up.segment_len ? up.segment_len : (kp.snv ? 1024u : 4096u);
+	if (seg_len < 4 * kp.k) {
+		seg_len = 4 * kp.k;
+	}
+
+	// ---- segments
+	std::vector<Segment> segs;
+	std::vector<uint64_t> first_seg(n_contigs + 1, 0);
+	for (uint64_t c = 0; c < n_contigs; c++) {
+		first_seg[c] = segs.size();
+		const uint64_t len64 = offsets[c + 1] - offsets[c] - 1;
+		if (len64 >= 0xFFFFFFFEULL) {
+			err = "contig longer than 2^32-2 bases";
+			return NTB_EINVAL;
+		}
+		const uint32_t len = (uint32_t)len64;
+		if (len < up.min_contig_len || len == 0) {
+			continue; // dropped from all outputs, ntedit.cpp:2242-2245
+		}
+		out.contigs[c].polished = true;
+		out.stats.bases += len;
+		out.stats.contigs++;
+		if (len < kp.k) {
+			continue; // no k-mer: the rope stays the root node
+		}
+		for (uint32_t p = 0; p < len; p += seg_len) {
+			Segment s;
+			s.contig = (uint32_t)c;
+			s.p0 = p;
+			s.p1 = (len - p <= seg_len) ? len : p + seg_len;
+			s.run_start = p;
+			s.arena = -1;
+			std::memset(&s.res, 0, sizeof s.res);
+			segs.push_back(s);
+			if (s.p1 == len) {
+				break;
+			}
+		}
+	}
+	first_seg[n_contigs] = segs.size();
+
+	be.scan_visit(kp);
+
+	// ---- rounds of walkers + stitching
+	std::vector<std::unique_ptr<std::vector<Event>>> arenas;
+	std::vector<uint64_t> pending; // segment indices to (re)run
+	pending.reserve(segs.size());
+	for (uint64_t i = 0; i < segs.size(); i++) {
+		pending.push_back(i);
+	}
+	std::vector<Task> tasks;
+	std::vector<TaskResult> results;
+	double host_ms = 0;
+	while (!pending.empty()) {
+		tasks.resize(pending.size());
+		for (size_t i = 0; i < pending.size(); i++) {
+			const Segment& s = segs[pending[i]];
+			Task& t = tasks[i];
+			t.text_off = offsets[s.contig];
+			t.len = (uint32_t)(offsets[s.contig + 1] - offsets[s.contig] - 1);
+			t.start = s.run_start;
+			t.end = s.p1;
+			t.contig = s.contig;
+			t.flags = (s.p0 == 0 && s.run_start == 0) ? TASK_CONTIG_START : 0;
+			t.pad_ = 0;
+		}
+		arenas.emplace_back(new std::vector<Event>());
+		const int rc = be.walk(kp, tasks, results, *arenas.back());
+		if (rc != NTB_OK) {
+			err = be.error();
+			return rc;
+		}
+		out.stats.rounds++;
+		out.stats.segments += tasks.size();
+		if (out.stats.rounds > 1) {
+			out.stats.reruns += tasks.size();
+		}
+		const auto t0 = clk::now();
+		for (size_t i = 0; i < pending.size(); i++) {
+			Segment& s = segs[pending[i]];
+			s.res = results[i];
+			s.arena = (int32_t)arenas.size() - 1;
+			if (s.res.status & ST_ROPE_OVERFLOW) {
+				err = "device rope capacity exceeded (pathological insertion run); input not supported";
+				return NTB_EINTERNAL;
+			}
+			if (!(s.res.status & ST_DONE) || (s.res.status & ST_EV_OVERFLOW)) {
+				err = "device walker did not finish";
+				return NTB_EINTERNAL;
+			}
+			out.stats.sites += s.res.n_sites;
+		}
+		// stitch pass: accept results in contig order; where a predecessor ran past a successor's first site, re-run
+		// that successor from the predecessor's clean end (optimistically assuming the re-run will end on its own border)
+		pending.clear();
+		for (uint64_t c = 0; c < n_contigs; c++) {
+			uint32_t prev_end = 0;
+			for (uint64_t i = first_seg[c]; i < first_seg[c + 1]; i++) {
+				Segment& s = segs[i];
+				const uint32_t need = std::max(prev_end, s.p0);
+				if (need >= s.p1) {
+					continue; // entirely covered by the predecessor's overrun
+				}
+				const uint32_t ft = s.res.first_touch != NONE32 ? std::min(s.res.first_touch, s.res.end_pos) : s.res.end_pos;
+				const bool valid = s.arena >= 0 && s.run_start <= need && need <= ft;
+				if (valid) {
+					prev_end = s.res.end_pos;
+					if (s.res.status & ST_CONTIG_END) {
+						break;
+					}
+				} else {
+					s.run_start = need;
+					s.arena = -1;
+					pending.push_back(i);
+					prev_end = s.p1;
+				}
+			}
+		}
+		host_ms += std::chrono::duration<double, std::milli>(clk::now() - t0).count();
+		if (out.stats.rounds > 64) {
+			err = "stitcher did not converge";
+			return NTB_EINTERNAL;
+		}
+	}
+
+	// ---- replay accepted events into ropes, contigs in parallel
+	const auto t1 = clk::now();
+	std::atomic<uint64_t> next(0);
+	std::atomic<int> failed(0);
+	std::atomic<uint64_t> n_edits(0);
+	std::string first_error;
+	std::atomic_flag err_lock = ATOMIC_FLAG_INIT;
+	auto worker = [&]() {
+		std::vector<const Event*> chain;
+		for (;;) {
+			const uint64_t c = next.fetch_add(1);
+			if (c >= n_contigs) {
+				break;
+			}
+			ContigResult& cr = out.contigs[c];
+			if (!cr.polished) {
+				continue;
+			}
+			const uint32_t len = (uint32_t)(offsets[c + 1] - offsets[c] - 1);
+			// without a host copy of the bases, substitutions are only reported through the records
+			RopeReplay rp(host_bases ? host_bases + offsets[c] : nullptr, len, kp.k, kp.insertion_cap, kp.snv, kp.mask);
+			uint32_t prev_end = 0;
+			uint64_t edits = 0;
+			uint8_t stale[4] = { 0, 0, 0, 0 }; // see STALE_REF
+			auto resolve = [&stale](uint8_t v) -> uint8_t { return (v & STALE_REF) ? stale[v & 3] : v; };
+			for (uint64_t i = first_seg[c]; i < first_seg[c + 1] && !rp.ended; i++) {
+				const Segment& s = segs[i];
+				const uint32_t need = std::max(prev_end, s.p0);
+				if (need >= s.p1) {
+					continue;
+				}
+				const std::vector<Event>& arena = *arenas[(size_t)s.arena];
+				chain.clear();
+				for (uint32_t e = s.res.last_event; e != NONE32; e = arena[e].prev) {
+					chain.push_back(&arena[e]);
+				}
+				for (size_t q = chain.size(); q > 0; q--) {
+					Event ev = *chain[q - 1];
+					ev.base = resolve(ev.base);
+					for (int a = 0; a < 3; a++) {
+						ev.altbase[a] = resolve(ev.altbase[a]);
+					}
+					if (!rp.apply(ev)) {
+						break;
+					}
+					if (chain[q - 1]->kind) {
+						edits++;
+					}
+				}
+				if (!rp.error.empty()) {
+					break;
+				}
+				const uint8_t next_stale[4] = { resolve(s.res.stale[0]), resolve(s.res.stale[1]), resolve(s.res.stale[2]),
+					                            resolve(s.res.stale[3]) };
+				std::memcpy(stale, next_stale, 4);
+				prev_end = s.res.end_pos;
+				if (s.res.status & ST_CONTIG_END) {
+					break;
+				}
+			}
+			if (!rp.error.empty()) {
+				failed = 1;
+				while (err_lock.test_and_set()) {
+				}
+				if (first_error.empty()) {
+					first_error = "contig " + std::to_string(c) + ": " + rp.error;
+				}
+				err_lock.clear();
+				continue;
+			}
+			n_edits += edits;
+			cr.nodes.swap(rp.rope);
+			cr.srecs.swap(rp.recs);
+		}
+	};
+	unsigned nthreads = std::thread::hardware_concurrency();
+	if (nthreads == 0) {
+		nthreads = 4;
+	}
+	nthreads = (unsigned)std::min<uint64_t>(nthreads, std::max<uint64_t>(1, n_contigs));
+	if (nthreads <= 1) {
+		worker();
+	} else {
+		std::vector<std::thread> pool;
+		for (unsigned i = 0; i < nthreads; i++) {
+			pool.emplace_back(worker);
+		}
+		for (auto& th : pool) {
+			th.join();
+		}
+	}
+	if (failed) {
+		err = first_error;
+		return NTB_EINTERNAL;
+	}
+	host_ms += std::chrono::duration<double, std::milli>(clk::now() - t1).count();
+	out.stats.edits = n_edits;
+	out.stats.ms_host = (float)host_ms;
+	return NTB_OK;
+}
+
+} // namespace ntb

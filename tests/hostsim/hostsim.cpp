@@ -1,0 +1,167 @@
+// TEST INFRASTRUCTURE ONLY -- never part of the product library.
+//
+// CPU simulator of the device side of ntedit_b200: it compiles the very same engine header the CUDA kernels
+// instantiate (ntedit_b200/csrc/engine.h) for the host and plugs it into the product's stitch/replay driver
+// (polish_driver.hpp).  It exists so the walker state machine, the segment stitcher and the rope replay can be
+// fuzzed against the reference in a container without a GPU; the GPU tests then only have to show that the CUDA
+// build of the same engine gives the same events.
+#include "../../ntedit_b200/csrc/engine.h"
+#include "../../ntedit_b200/csrc/polish_driver.hpp"
+#include "../../ntedit_b200/csrc/writer.hpp"
+
+#include <cstdlib>
+
+using namespace ntb;
+
+namespace {
+
+FilterView
+make_view(const uint8_t* data, uint64_t bytes, uint32_t h, int counting)
+{
+	FilterView v;
+	std::memset(&v, 0, sizeof v);
+	v.data = data;
+	v.bytes = bytes;
+	v.mod = counting ? bytes : bytes * 8;
+	v.recip = v.mod ? 0xFFFFFFFFFFFFFFFFULL / v.mod : 0;
+	v.mask = (v.mod && (v.mod & (v.mod - 1)) == 0 && v.mod > 1) ? v.mod - 1 : 0;
+	v.hash_num = h;
+	v.counting = counting ? 1u : 0u;
+	return v;
+}
+
+struct HostBackend
+{
+	const unsigned char* bases;
+	uint64_t total;
+	FilterView bloom, rep;
+	std::vector<uint32_t> visit;
+	std::string err;
+
+	const std::string& error() const { return err; }
+
+	// CPU stand-in for the scan kernel K1
+	void scan_visit(const KParams& kp)
+	{
+		visit.assign((total + 63) / 32 + 2, 0u);
+		uint64_t run = 0;
+		HashState hs;
+		hs.fh = hs.rh = 0;
+		for (uint64_t g = 0; g < total; g++) {
+			const unsigned char c = bases[g];
+			run = is_accepted_any_case(c) ? run + 1 : 0;
+			if (run < kp.k) {
+				continue;
+			}
+			const unsigned char* w = bases + g + 1 - kp.k;
+			hash_seed(hs, kp.k, [w](unsigned i) { return w[i]; });
+			bool site;
+			if (kp.snv) {
+				site = true;
+			} else if (kp.counting) {
+				const unsigned cnt = filter_count(bloom, hash_canonical(hs), kp.k);
+				site = cnt == 0 || cnt < kp.min_threshold;
+			} else {
+				site = !filter_contains(bloom, hash_canonical(hs), kp.k);
+			}
+			if (site) {
+				visit[g >> 5] |= 1u << (g & 31);
+			}
+		}
+	}
+
+	int walk(const KParams& kp, const std::vector<Task>& tasks, std::vector<TaskResult>& results, std::vector<Event>& events)
+	{
+		results.resize(tasks.size());
+		events.assign(1u << 16, Event());
+		for (;;) {
+			Counters ctr = { 0, 0 };
+			for (size_t i = 0; i < tasks.size(); i++) {
+				WalkerIO io;
+				io.text = bases + tasks[i].text_off;
+				io.len = tasks[i].len;
+				io.visit = visit.data();
+				io.goff = tasks[i].text_off;
+				io.bloom = bloom;
+				io.rep = rep;
+				io.events = events.data();
+				io.ev_cap = (uint32_t)events.size();
+				io.ctr = &ctr;
+				Walker<352>* w = new Walker<352>(io, kp);
+				w->run(tasks[i], results[i]);
+				delete w;
+			}
+			if (!ctr.overflow) {
+				events.resize(ctr.n_events);
+				return NTB_OK;
+			}
+			events.assign(events.size() * 4, Event());
+		}
+	}
+};
+
+char*
+dup_out(const std::string& s, size_t* n)
+{
+	char* p = (char*)std::malloc(s.size() + 1);
+	std::memcpy(p, s.data(), s.size());
+	p[s.size()] = 0;
+	*n = s.size();
+	return p;
+}
+
+} // namespace
+
+extern "C" {
+
+// polishes a batch on the CPU simulator and formats the three outputs (TSV with its header, VCF rows without header)
+int
+hostsim_polish(const uint8_t* filt, uint64_t fbytes, uint32_t k, uint32_t h, int counting, const uint8_t* rep, uint64_t rbytes,
+               uint32_t rh, int rcounting, const ntb_params* up, char* bases, const uint64_t* offsets, uint64_t n_contigs,
+               const char* const* headers, char** fa, size_t* fa_len, char** tsv, size_t* tsv_len, char** vcf, size_t* vcf_len,
+               ntb_stats* stats, char* errbuf, size_t errlen)
+{
+	KParams kp;
+	std::string err;
+	int rc = make_kparams(*up, k, h, rep ? rh : 0, counting != 0, kp, err);
+	if (rc == NTB_OK) {
+		HostBackend be;
+		be.bases = (const unsigned char*)bases;
+		be.total = offsets[n_contigs];
+		be.bloom = make_view(filt, fbytes, h, counting);
+		be.rep = rep ? make_view(rep, rbytes, rh, rcounting) : make_view(nullptr, 0, 0, 0);
+		// the walkers must see the ORIGINAL draft while the replay mutates the caller's buffer
+		std::vector<unsigned char> pristine(be.bases, be.bases + be.total);
+		be.bases = pristine.data();
+		ResultImpl res;
+		rc = polish_run(be, kp, *up, bases, offsets, n_contigs, res, err);
+		if (rc == NTB_OK) {
+			std::string sfa, stsv = tsv_header(k, up->jump, counting != 0), svcf;
+			for (uint64_t c = 0; c < n_contigs; c++) {
+				const ContigResult& cr = res.contigs[c];
+				if (!cr.polished) {
+					continue;
+				}
+				format_contig(headers[c], bases + offsets[c], cr.nodes.data(), cr.nodes.size(), cr.srecs.data(), cr.srecs.size(),
+				              up->snv != 0, nullptr, &sfa, &stsv, &svcf);
+			}
+			*fa = dup_out(sfa, fa_len);
+			*tsv = dup_out(stsv, tsv_len);
+			*vcf = dup_out(svcf, vcf_len);
+			if (stats) {
+				*stats = res.stats;
+			}
+		}
+	}
+	if (rc != NTB_OK && errbuf && errlen) {
+		std::snprintf(errbuf, errlen, "%s", err.c_str());
+	}
+	return rc;
+}
+
+void
+hostsim_free(char* p)
+{
+	std::free(p);
+}
+}
