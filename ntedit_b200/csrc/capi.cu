@@ -1,0 +1,991 @@
+// C ABI of libntedit_b200.so (include/ntedit_b200.h): filter objects, batches, the CUDA backend of the polishing driver.
+#include "../../include/ntedit_b200.h"
+#include "filter_io.hpp"
+#include "kernels.cuh"
+#include "polish_driver.hpp"
+#include "writer.hpp"
+
+#include <cstdio>
+#include <cstdlib>
+#include <mutex>
+#include <new>
+
+using namespace ntb;
+
+namespace {
+
+thread_local std::string g_error;
+
+int
+fail(int code, const std::string& msg)
+{
+	g_error = msg;
+	return code;
+}
+
+int
+cuda_fail(cudaError_t e, const char* what)
+{
+	const int code = (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver) ? NTB_ENODEV
+	                 : (e == cudaErrorMemoryAllocation)                          ? NTB_ENOMEM
+	                                                                             : NTB_ECUDA;
+	return fail(code, std::string(what) + ": " + cudaGetErrorString(e));
+}
+
+#define NTB_CUDA(call)                           \
+	do {                                         \
+		cudaError_t e_ = (call);                 \
+		if (e_ != cudaSuccess) {                 \
+			return cuda_fail(e_, #call);         \
+		}                                        \
+	} while (0)
+
+int
+select_device(int device)
+{
+	int n = 0;
+	cudaError_t e = cudaGetDeviceCount(&n);
+	if (e != cudaSuccess || n == 0) {
+		return fail(NTB_ENODEV, "no CUDA device available (ntedit_b200 has no CPU fallback)");
+	}
+	if (device < 0 || device >= n) {
+		return fail(NTB_EINVAL, "device index out of range");
+	}
+	NTB_CUDA(cudaSetDevice(device));
+	return NTB_OK;
+}
+
+int
+sm_count(int device)
+{
+	int n = 148;
+	cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, device);
+	return n > 0 ? n : 148;
+}
+
+} // namespace
+
+struct ntb_filter
+{
+	uint8_t* d = nullptr; // device bytes (padded to 16)
+	uint64_t bytes = 0;
+	uint32_t k = 0, h = 0;
+	int counting = 0;
+	int device = 0;
+	bool owned = true;
+	double fpr = -1.0; // cached; reset by inserts
+
+	FilterView view() const
+	{
+		FilterView v;
+		std::memset(&v, 0, sizeof v);
+		v.data = d;
+		v.bytes = bytes;
+		v.mod = counting ? bytes : bytes * 8;
+		v.recip = v.mod ? 0xFFFFFFFFFFFFFFFFULL / v.mod : 0;
+		v.mask = (v.mod > 1 && (v.mod & (v.mod - 1)) == 0) ? v.mod - 1 : 0;
+		v.hash_num = h;
+		v.counting = counting ? 1u : 0u;
+		return v;
+	}
+};
+
+struct ntb_batch
+{
+	uint8_t* d_alloc = nullptr; // SCAN_HALO zero bytes, the text, zero padding to whole scan tiles
+	uint8_t* d_text = nullptr;  // d_alloc + SCAN_HALO
+	uint64_t total = 0;         // bytes of text (including the NUL separators)
+	uint64_t n_tiles = 0;
+	std::vector<uint64_t> offsets;
+	int device = 0;
+	float ms_h2d = 0;
+};
+
+struct ntb_result
+{
+	ResultImpl impl;
+};
+
+namespace {
+
+int
+batch_alloc(ntb_batch* b, uint64_t total)
+{
+	b->total = total;
+	b->n_tiles = (total + SCAN_TILE - 1) / SCAN_TILE;
+	const uint64_t padded = b->n_tiles * SCAN_TILE;
+	NTB_CUDA(cudaMalloc((void**)&b->d_alloc, SCAN_HALO + padded + 64));
+	b->d_text = b->d_alloc + SCAN_HALO;
+	NTB_CUDA(cudaMemsetAsync(b->d_alloc, 0, SCAN_HALO, 0));
+	NTB_CUDA(cudaMemsetAsync(b->d_text + total, 0, padded - total + 64, 0));
+	return NTB_OK;
+}
+
+int
+check_offsets(const uint64_t* offsets, uint64_t n_contigs)
+{
+	if (!offsets) {
+		return fail(NTB_EINVAL, "offsets is NULL");
+	}
+	if (offsets[0] != 0) {
+		return fail(NTB_EINVAL, "offsets[0] must be 0");
+	}
+	for (uint64_t c = 0; c < n_contigs; c++) {
+		if (offsets[c + 1] <= offsets[c]) {
+			return fail(NTB_EINVAL, "offsets must be strictly increasing (every contig carries its NUL terminator)");
+		}
+	}
+	return NTB_OK;
+}
+
+void
+fill_scan_tables(ScanArgs& a, uint32_t k)
+{
+	const uint64_t seeds[5] = { SEED_A, SEED_C, SEED_G, SEED_T, 0 };
+	for (int i = 0; i < 5; i++) {
+		a.seed[i] = seeds[i];
+		a.rotk[i] = sroln(seeds[i], k);
+	}
+	for (unsigned i = 0; i < HMAX; i++) {
+		a.mult[i] = (uint64_t)i ^ ((uint64_t)k * MULTISEED);
+	}
+}
+
+// CUDA implementation of the Backend concept of polish_driver.hpp
+struct CudaBackend
+{
+	ntb_filter* bloom;
+	ntb_filter* rep;
+	ntb_batch* batch;
+	cudaStream_t stream = 0;
+	uint32_t* d_visit = nullptr;
+	Task* d_tasks = nullptr;
+	TaskResult* d_results = nullptr;
+	Event* d_events = nullptr;
+	Counters* d_ctr = nullptr;
+	size_t cap_tasks = 0;
+	size_t cap_events = 0;
+	cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+	float ms_scan = 0, ms_walk = 0, ms_d2h = 0;
+	uint32_t launches = 0;
+	std::string err;
+	int rc = NTB_OK;
+
+	const std::string& error() const { return err; }
+
+	int cuda_err(cudaError_t e, const char* what)
+	{
+		err = std::string(what) + ": " + cudaGetErrorString(e);
+		rc = e == cudaErrorMemoryAllocation ? NTB_ENOMEM : NTB_ECUDA;
+		return rc;
+	}
+
+#define NTB_BE(call)                          \
+	do {                                      \
+		cudaError_t e_ = (call);              \
+		if (e_ != cudaSuccess) {              \
+			return cuda_err(e_, #call);       \
+		}                                     \
+	} while (0)
+
+	int init()
+	{
+		NTB_BE(cudaEventCreate(&ev0));
+		NTB_BE(cudaEventCreate(&ev1));
+		NTB_BE(cudaMalloc((void**)&d_visit, batch->n_tiles * SCAN_BITWORDS * 4 + 64));
+		NTB_BE(cudaMalloc((void**)&d_ctr, sizeof(Counters)));
+		return NTB_OK;
+	}
+
+	~CudaBackend()
+	{
+		cudaFree(d_visit);
+		cudaFree(d_tasks);
+		cudaFree(d_results);
+		cudaFree(d_events);
+		cudaFree(d_ctr);
+		if (ev0) {
+			cudaEventDestroy(ev0);
+		}
+		if (ev1) {
+			cudaEventDestroy(ev1);
+		}
+	}
+
+	int scan_impl(const KParams& kp)
+	{
+		ScanArgs a;
+		std::memset(&a, 0, sizeof a);
+		a.text = batch->d_text;
+		a.n_tiles = batch->n_tiles;
+		a.filter = bloom->view();
+		a.k = kp.k;
+		a.min_threshold = kp.min_threshold;
+		a.snv = (uint32_t)kp.snv;
+		a.visit = d_visit;
+		fill_scan_tables(a, kp.k);
+		const int grid = (int)std::min<uint64_t>(batch->n_tiles, (uint64_t)sm_count(batch->device) * 3);
+		NTB_BE(cudaEventRecord(ev0, stream));
+		if (grid > 0) {
+			NTB_BE(launch_scan(a, bloom->counting != 0, false, grid, stream));
+			launches++;
+		}
+		NTB_BE(cudaEventRecord(ev1, stream));
+		NTB_BE(cudaEventSynchronize(ev1));
+		float ms = 0;
+		NTB_BE(cudaEventElapsedTime(&ms, ev0, ev1));
+		ms_scan += ms;
+		return NTB_OK;
+	}
+
+	void scan_visit(const KParams& kp)
+	{
+		if (rc == NTB_OK) {
+			scan_impl(kp);
+		}
+	}
+
+	int walk(const KParams& kp, const std::vector<Task>& tasks, std::vector<TaskResult>& results, std::vector<Event>& events)
+	{
+		if (rc != NTB_OK) {
+			return rc;
+		}
+		const size_t n = tasks.size();
+		results.resize(n);
+		events.clear();
+		if (n == 0) {
+			return NTB_OK;
+		}
+		if (n > 0xFFFFFFF0ULL) {
+			err = "too many segments in one batch";
+			return rc = NTB_EINVAL;
+		}
+		if (n > cap_tasks) {
+			cudaFree(d_tasks);
+			cudaFree(d_results);
+			d_tasks = nullptr;
+			d_results = nullptr;
+			NTB_BE(cudaMalloc((void**)&d_tasks, n * sizeof(Task)));
+			NTB_BE(cudaMalloc((void**)&d_results, n * sizeof(TaskResult)));
+			cap_tasks = n;
+		}
+		if (cap_events == 0) {
+			// sized for the recipe's ~1.1e-3 edits per base with headroom; grown on overflow
+			size_t want = std::max<size_t>(1u << 16, (size_t)(batch->total / 96));
+			NTB_BE(cudaMalloc((void**)&d_events, want * sizeof(Event)));
+			cap_events = want;
+		}
+		NTB_BE(cudaMemcpyAsync(d_tasks, tasks.data(), n * sizeof(Task), cudaMemcpyHostToDevice, stream));
+		const FilterView fb = bloom->view();
+		FilterView fr;
+		std::memset(&fr, 0, sizeof fr);
+		if (rep) {
+			fr = rep->view();
+		}
+		for (;;) {
+			NTB_BE(cudaMemsetAsync(d_ctr, 0, sizeof(Counters), stream));
+			NTB_BE(cudaEventRecord(ev0, stream));
+			const unsigned block = 64;
+			const unsigned grid = (unsigned)((n + block - 1) / block);
+			walk_kernel<<<grid, block, 0, stream>>>(batch->d_text, d_visit, fb, fr, kp, d_tasks, d_results, (uint32_t)n, d_events,
+			                                        (uint32_t)std::min<size_t>(cap_events, 0xFFFFFFF0u), d_ctr);
+			launches++;
+			NTB_BE(cudaGetLastError());
+			NTB_BE(cudaEventRecord(ev1, stream));
+			Counters ctr;
+			NTB_BE(cudaMemcpyAsync(&ctr, d_ctr, sizeof ctr, cudaMemcpyDeviceToHost, stream));
+			NTB_BE(cudaStreamSynchronize(stream));
+			float ms = 0;
+			NTB_BE(cudaEventElapsedTime(&ms, ev0, ev1));
+			ms_walk += ms;
+			if (ctr.overflow) {
+				cudaFree(d_events);
+				d_events = nullptr;
+				cap_events *= 4;
+				NTB_BE(cudaMalloc((void**)&d_events, cap_events * sizeof(Event)));
+				continue;
+			}
+			NTB_BE(cudaEventRecord(ev0, stream));
+			events.resize(ctr.n_events);
+			if (ctr.n_events) {
+				NTB_BE(cudaMemcpyAsync(events.data(), d_events, (size_t)ctr.n_events * sizeof(Event), cudaMemcpyDeviceToHost, stream));
+			}
+			NTB_BE(cudaMemcpyAsync(results.data(), d_results, n * sizeof(TaskResult), cudaMemcpyDeviceToHost, stream));
+			NTB_BE(cudaEventRecord(ev1, stream));
+			NTB_BE(cudaStreamSynchronize(stream));
+			NTB_BE(cudaEventElapsedTime(&ms, ev0, ev1));
+			ms_d2h += ms;
+			return NTB_OK;
+		}
+	}
+#undef NTB_BE
+};
+
+int
+polish_common(ntb_filter* bloom, ntb_filter* rep, const ntb_params* p, ntb_batch* batch, char* host_bases, ntb_result** out)
+{
+	if (!bloom || !p || !batch || !out) {
+		return fail(NTB_EINVAL, "NULL argument");
+	}
+	if (bloom->device != batch->device || (rep && rep->device != batch->device)) {
+		return fail(NTB_EINVAL, "filter and batch live on different devices");
+	}
+	if (rep && rep->k != bloom->k) { // ntedit.cpp:2580-2585
+		return fail(NTB_EINVAL, "secondary Bloom filter k size (" + std::to_string(rep->k) + ") is different than main Bloom filter k size (" +
+		                            std::to_string(bloom->k) + ")");
+	}
+	int rc = select_device(batch->device);
+	if (rc != NTB_OK) {
+		return rc;
+	}
+	KParams kp;
+	std::string err;
+	rc = make_kparams(*p, bloom->k, bloom->h, rep ? rep->h : 0, bloom->counting != 0, kp, err);
+	if (rc != NTB_OK) {
+		return fail(rc, err);
+	}
+	ntb_result* res = new (std::nothrow) ntb_result();
+	if (!res) {
+		return fail(NTB_ENOMEM, "out of memory");
+	}
+	CudaBackend be;
+	be.bloom = bloom;
+	be.rep = rep;
+	be.batch = batch;
+	rc = be.init();
+	if (rc == NTB_OK) {
+		rc = polish_run(be, kp, *p, host_bases, batch->offsets.data(), batch->offsets.size() - 1, res->impl, err);
+		if (rc == NTB_OK && be.rc != NTB_OK) {
+			rc = be.rc;
+			err = be.err;
+		}
+	} else {
+		err = be.err;
+	}
+	if (rc != NTB_OK) {
+		delete res;
+		return fail(rc, err);
+	}
+	res->impl.stats.ms_scan = be.ms_scan;
+	res->impl.stats.ms_walk = be.ms_walk;
+	res->impl.stats.ms_d2h = be.ms_d2h;
+	res->impl.stats.ms_h2d = batch->ms_h2d;
+	res->impl.stats.kernel_launches = be.launches;
+	*out = res;
+	return NTB_OK;
+}
+
+void
+strbuf_append(ntb_strbuf* b, const std::string& s)
+{
+	if (!b || s.empty()) {
+		return;
+	}
+	if (b->len + s.size() + 1 > b->cap) {
+		size_t c = b->cap ? b->cap : 4096;
+		while (c < b->len + s.size() + 1) {
+			c *= 2;
+		}
+		b->data = (char*)std::realloc(b->data, c);
+		b->cap = c;
+	}
+	std::memcpy(b->data + b->len, s.data(), s.size());
+	b->len += s.size();
+	b->data[b->len] = 0;
+}
+
+} // namespace
+
+extern "C" {
+
+const char*
+ntb_last_error(void)
+{
+	return g_error.c_str();
+}
+
+const char*
+ntb_version(void)
+{
+	return "ntedit_b200 0.1 (ntEdit v2.1.1 hot path, sm_100a)";
+}
+
+int
+ntb_device_count(void)
+{
+	int n = 0;
+	if (cudaGetDeviceCount(&n) != cudaSuccess) {
+		return 0;
+	}
+	return n;
+}
+
+void
+ntb_params_init(ntb_params* p)
+{
+	if (!p) {
+		return;
+	}
+	std::memset(p, 0, sizeof *p);
+	p->jump = 3;
+	p->max_insertions = 5;
+	p->max_deletions = 5;
+	p->edit_threshold = 9.0f;
+	p->missing_threshold = 5.0f;
+	p->edit_ratio = 0.5f;
+	p->missing_ratio = 0.5f;
+	p->min_threshold = 1;
+	p->max_threshold = 255;
+	p->min_contig_len = 100;
+}
+
+// ---------------------------------------------------------------- filters
+int
+ntb_filter_create(uint64_t bytes, uint32_t k, uint32_t hash_num, int counting, int device, ntb_filter** out)
+{
+	if (!out || bytes == 0 || k == 0 || hash_num == 0 || hash_num > HMAX) {
+		return fail(NTB_EINVAL, "bad filter geometry");
+	}
+	int rc = select_device(device);
+	if (rc != NTB_OK) {
+		return rc;
+	}
+	ntb_filter* f = new (std::nothrow) ntb_filter();
+	if (!f) {
+		return fail(NTB_ENOMEM, "out of memory");
+	}
+	f->bytes = bytes;
+	f->k = k;
+	f->h = hash_num;
+	f->counting = counting ? 1 : 0;
+	f->device = device;
+	const uint64_t padded = (bytes + 15) / 16 * 16 + 16;
+	cudaError_t e = cudaMalloc((void**)&f->d, padded);
+	if (e == cudaSuccess) {
+		e = cudaMemset(f->d, 0, padded);
+	}
+	if (e != cudaSuccess) {
+		cudaFree(f->d);
+		delete f;
+		return cuda_fail(e, "cudaMalloc(filter)");
+	}
+	*out = f;
+	return NTB_OK;
+}
+
+int
+ntb_filter_wrap_device(void* dev_bytes, uint64_t bytes, uint32_t k, uint32_t hash_num, int counting, int device, ntb_filter** out)
+{
+	if (!out || !dev_bytes || bytes == 0 || k == 0 || hash_num == 0 || hash_num > HMAX) {
+		return fail(NTB_EINVAL, "bad filter geometry");
+	}
+	int rc = select_device(device);
+	if (rc != NTB_OK) {
+		return rc;
+	}
+	ntb_filter* f = new (std::nothrow) ntb_filter();
+	if (!f) {
+		return fail(NTB_ENOMEM, "out of memory");
+	}
+	f->d = (uint8_t*)dev_bytes;
+	f->bytes = bytes;
+	f->k = k;
+	f->h = hash_num;
+	f->counting = counting ? 1 : 0;
+	f->device = device;
+	f->owned = false;
+	*out = f;
+	return NTB_OK;
+}
+
+int
+ntb_filter_load(const char* path, int device, ntb_filter** out)
+{
+	if (!path || !out) {
+		return fail(NTB_EINVAL, "NULL argument");
+	}
+	FilterHeader hdr;
+	std::string err;
+	if (!read_filter_header(path, hdr, err)) {
+		return fail(NTB_EIO, err);
+	}
+	ntb_filter* f = nullptr;
+	int rc = ntb_filter_create(hdr.bytes, hdr.k, hdr.hash_num, hdr.counting ? 1 : 0, device, &f);
+	if (rc != NTB_OK) {
+		return rc;
+	}
+	// stream the payload through a pinned staging buffer
+	const size_t chunk = (size_t)64 << 20;
+	char* stage = nullptr;
+	cudaError_t e = cudaMallocHost((void**)&stage, chunk);
+	if (e != cudaSuccess) {
+		ntb_filter_free(f);
+		return cuda_fail(e, "cudaMallocHost");
+	}
+	FILE* fp = std::fopen(path, "rb");
+	bool ok = fp && fseeko(fp, (off_t)hdr.data_offset, SEEK_SET) == 0;
+	uint64_t done = 0;
+	while (ok && done < hdr.bytes) {
+		const size_t want = (size_t)std::min<uint64_t>(chunk, hdr.bytes - done);
+		if (std::fread(stage, 1, want, fp) != want) {
+			ok = false;
+			break;
+		}
+		e = cudaMemcpy(f->d + done, stage, want, cudaMemcpyHostToDevice);
+		if (e != cudaSuccess) {
+			break;
+		}
+		done += want;
+	}
+	if (fp) {
+		std::fclose(fp);
+	}
+	cudaFreeHost(stage);
+	if (e != cudaSuccess) {
+		ntb_filter_free(f);
+		return cuda_fail(e, "cudaMemcpy(filter)");
+	}
+	if (!ok) {
+		ntb_filter_free(f);
+		return fail(NTB_EIO, std::string("truncated Bloom filter file ") + path);
+	}
+	*out = f;
+	return NTB_OK;
+}
+
+int
+ntb_filter_get_info(ntb_filter* f, ntb_filter_info* info)
+{
+	if (!f || !info) {
+		return fail(NTB_EINVAL, "NULL argument");
+	}
+	int rc = select_device(f->device);
+	if (rc != NTB_OK) {
+		return rc;
+	}
+	if (f->fpr < 0) {
+		unsigned long long* d_cnt = nullptr;
+		NTB_CUDA(cudaMalloc((void**)&d_cnt, 8));
+		NTB_CUDA(cudaMemset(d_cnt, 0, 8));
+		occupancy_kernel<<<sm_count(f->device) * 8, 256>>>(f->d, f->bytes, f->counting, d_cnt);
+		unsigned long long cnt = 0;
+		cudaError_t e = cudaMemcpy(&cnt, d_cnt, 8, cudaMemcpyDeviceToHost);
+		cudaFree(d_cnt);
+		if (e != cudaSuccess) {
+			return cuda_fail(e, "occupancy_kernel");
+		}
+		const double denom = f->counting ? (double)f->bytes : (double)f->bytes * 8.0;
+		f->fpr = std::pow((double)cnt / denom, (double)f->h);
+	}
+	info->bytes = f->bytes;
+	info->k = f->k;
+	info->hash_num = f->h;
+	info->counting = f->counting;
+	info->device = f->device;
+	info->fpr = f->fpr;
+	return NTB_OK;
+}
+
+void*
+ntb_filter_device_ptr(ntb_filter* f)
+{
+	return f ? f->d : nullptr;
+}
+
+int
+ntb_filter_insert_batch(ntb_filter* f, const ntb_batch* b)
+{
+	if (!f || !b) {
+		return fail(NTB_EINVAL, "NULL argument");
+	}
+	if (f->device != b->device) {
+		return fail(NTB_EINVAL, "filter and batch live on different devices");
+	}
+	if (f->k < 2 || f->k > KMAX) {
+		return fail(NTB_EINVAL, "unsupported k");
+	}
+	int rc = select_device(f->device);
+	if (rc != NTB_OK) {
+		return rc;
+	}
+	ntb_params up;
+	ntb_params_init(&up);
+	KParams kp;
+	std::memset(&kp, 0, sizeof kp);
+	kp.k = f->k;
+	kp.h = f->h;
+	const uint64_t seeds[4] = { SEED_A, SEED_C, SEED_G, SEED_T };
+	for (int c = 0; c < 4; c++) {
+		kp.seed_rot_k[c] = sroln(seeds[c], f->k);
+		kp.seed_rot_k1[c] = sroln(seeds[c], f->k - 1);
+	}
+	const uint64_t strips = (b->total + 255) / 256;
+	const unsigned block = 128;
+	const uint64_t grid = (strips + block - 1) / block;
+	if (grid > 0x7FFFFFFFULL) {
+		return fail(NTB_EINVAL, "batch too large");
+	}
+	if (grid > 0) {
+		insert_kernel<<<(unsigned)grid, block>>>(b->d_text, b->total, f->d, f->view(), kp);
+		NTB_CUDA(cudaGetLastError());
+		NTB_CUDA(cudaDeviceSynchronize());
+	}
+	f->fpr = -1.0;
+	return NTB_OK;
+}
+
+int
+ntb_filter_insert(ntb_filter* f, const char* bases, const uint64_t* offsets, uint64_t n_contigs)
+{
+	if (!f) {
+		return fail(NTB_EINVAL, "NULL argument");
+	}
+	ntb_batch* b = nullptr;
+	int rc = ntb_batch_upload(bases, offsets, n_contigs, f->device, &b);
+	if (rc != NTB_OK) {
+		return rc;
+	}
+	rc = ntb_filter_insert_batch(f, b);
+	ntb_batch_free(b);
+	return rc;
+}
+
+int
+ntb_filter_download(ntb_filter* f, void* host_dst, uint64_t bytes)
+{
+	if (!f || !host_dst || bytes > f->bytes) {
+		return fail(NTB_EINVAL, "bad argument");
+	}
+	int rc = select_device(f->device);
+	if (rc != NTB_OK) {
+		return rc;
+	}
+	NTB_CUDA(cudaMemcpy(host_dst, f->d, bytes, cudaMemcpyDeviceToHost));
+	return NTB_OK;
+}
+
+int
+ntb_filter_save(ntb_filter* f, const char* path)
+{
+	if (!f || !path) {
+		return fail(NTB_EINVAL, "NULL argument");
+	}
+	int rc = select_device(f->device);
+	if (rc != NTB_OK) {
+		return rc;
+	}
+	FILE* fp = std::fopen(path, "wb");
+	if (!fp) {
+		return fail(NTB_EIO, std::string("cannot open ") + path + " for writing");
+	}
+	const std::string hdr = format_filter_header(f->bytes, f->k, f->h, f->counting != 0);
+	bool ok = std::fwrite(hdr.data(), 1, hdr.size(), fp) == hdr.size();
+	const size_t chunk = (size_t)64 << 20;
+	std::vector<char> stage(std::min<uint64_t>(chunk, f->bytes));
+	uint64_t done = 0;
+	cudaError_t e = cudaSuccess;
+	while (ok && done < f->bytes) {
+		const size_t want = (size_t)std::min<uint64_t>(chunk, f->bytes - done);
+		e = cudaMemcpy(stage.data(), f->d + done, want, cudaMemcpyDeviceToHost);
+		if (e != cudaSuccess) {
+			break;
+		}
+		ok = std::fwrite(stage.data(), 1, want, fp) == want;
+		done += want;
+	}
+	std::fclose(fp);
+	if (e != cudaSuccess) {
+		return cuda_fail(e, "cudaMemcpy(filter)");
+	}
+	return ok ? NTB_OK : fail(NTB_EIO, std::string("short write to ") + path);
+}
+
+void
+ntb_filter_free(ntb_filter* f)
+{
+	if (!f) {
+		return;
+	}
+	if (f->owned && f->d) {
+		cudaSetDevice(f->device);
+		cudaFree(f->d);
+	}
+	delete f;
+}
+
+// ---------------------------------------------------------------- batches
+int
+ntb_batch_upload(const char* bases, const uint64_t* offsets, uint64_t n_contigs, int device, ntb_batch** out)
+{
+	if (!bases || !out) {
+		return fail(NTB_EINVAL, "NULL argument");
+	}
+	int rc = check_offsets(offsets, n_contigs);
+	if (rc != NTB_OK) {
+		return rc;
+	}
+	for (uint64_t c = 0; c < n_contigs; c++) {
+		if (bases[offsets[c + 1] - 1] != 0) {
+			return fail(NTB_EINVAL, "contig " + std::to_string(c) + " is not NUL-terminated inside the batch buffer");
+		}
+	}
+	rc = select_device(device);
+	if (rc != NTB_OK) {
+		return rc;
+	}
+	ntb_batch* b = new (std::nothrow) ntb_batch();
+	if (!b) {
+		return fail(NTB_ENOMEM, "out of memory");
+	}
+	b->device = device;
+	b->offsets.assign(offsets, offsets + n_contigs + 1);
+	rc = batch_alloc(b, offsets[n_contigs]);
+	if (rc != NTB_OK) {
+		ntb_batch_free(b);
+		return rc;
+	}
+	cudaEvent_t e0, e1;
+	cudaEventCreate(&e0);
+	cudaEventCreate(&e1);
+	cudaEventRecord(e0, 0);
+	cudaError_t e = cudaMemcpyAsync(b->d_text, bases, b->total, cudaMemcpyHostToDevice, 0);
+	cudaEventRecord(e1, 0);
+	if (e == cudaSuccess) {
+		e = cudaEventSynchronize(e1);
+	}
+	if (e == cudaSuccess) {
+		cudaEventElapsedTime(&b->ms_h2d, e0, e1);
+	}
+	cudaEventDestroy(e0);
+	cudaEventDestroy(e1);
+	if (e != cudaSuccess) {
+		ntb_batch_free(b);
+		return cuda_fail(e, "cudaMemcpy(batch)");
+	}
+	*out = b;
+	return NTB_OK;
+}
+
+int
+ntb_batch_wrap_device(void* dev_bases, const uint64_t* host_offsets, uint64_t n_contigs, int device, ntb_batch** out)
+{
+	if (!dev_bases || !out) {
+		return fail(NTB_EINVAL, "NULL argument");
+	}
+	int rc = check_offsets(host_offsets, n_contigs);
+	if (rc != NTB_OK) {
+		return rc;
+	}
+	rc = select_device(device);
+	if (rc != NTB_OK) {
+		return rc;
+	}
+	ntb_batch* b = new (std::nothrow) ntb_batch();
+	if (!b) {
+		return fail(NTB_ENOMEM, "out of memory");
+	}
+	b->device = device;
+	b->offsets.assign(host_offsets, host_offsets + n_contigs + 1);
+	// the kernels want SCAN_HALO readable bytes in front and whole-tile zero padding behind: take a padded device copy
+	rc = batch_alloc(b, host_offsets[n_contigs]);
+	if (rc != NTB_OK) {
+		ntb_batch_free(b);
+		return rc;
+	}
+	cudaError_t e = cudaMemcpy(b->d_text, dev_bases, b->total, cudaMemcpyDeviceToDevice);
+	if (e != cudaSuccess) {
+		ntb_batch_free(b);
+		return cuda_fail(e, "cudaMemcpy(batch, device to device)");
+	}
+	*out = b;
+	return NTB_OK;
+}
+
+uint64_t
+ntb_batch_total_bases(const ntb_batch* b)
+{
+	if (!b || b->offsets.empty()) {
+		return 0;
+	}
+	return b->total - (b->offsets.size() - 1);
+}
+
+void
+ntb_batch_free(ntb_batch* b)
+{
+	if (!b) {
+		return;
+	}
+	if (b->d_alloc) {
+		cudaSetDevice(b->device);
+		cudaFree(b->d_alloc);
+	}
+	delete b;
+}
+
+// ---------------------------------------------------------------- K1 through the ABI
+int
+ntb_scan(ntb_filter* f, const char* bases, const uint64_t* offsets, uint64_t n_contigs, uint8_t* counts, uint32_t* valid_bits)
+{
+	if (!f) {
+		return fail(NTB_EINVAL, "NULL argument");
+	}
+	if (f->k < 2 || f->k > KMAX) {
+		return fail(NTB_EINVAL, "unsupported k");
+	}
+	ntb_batch* b = nullptr;
+	int rc = ntb_batch_upload(bases, offsets, n_contigs, f->device, &b);
+	if (rc != NTB_OK) {
+		return rc;
+	}
+	const uint64_t words = b->n_tiles * SCAN_BITWORDS;
+	const uint64_t padded = b->n_tiles * SCAN_TILE;
+	uint32_t *d_visit = nullptr, *d_valid = nullptr;
+	uint8_t* d_counts = nullptr;
+	cudaError_t e = cudaMalloc((void**)&d_visit, words * 4 + 64);
+	if (e == cudaSuccess) {
+		e = cudaMalloc((void**)&d_valid, words * 4 + 64);
+	}
+	if (e == cudaSuccess) {
+		e = cudaMalloc((void**)&d_counts, padded + 64);
+	}
+	if (e == cudaSuccess) {
+		ScanArgs a;
+		std::memset(&a, 0, sizeof a);
+		a.text = b->d_text;
+		a.n_tiles = b->n_tiles;
+		a.filter = f->view();
+		a.k = f->k;
+		a.min_threshold = 1;
+		a.snv = 0;
+		a.visit = d_visit;
+		a.valid = d_valid;
+		a.counts = d_counts;
+		fill_scan_tables(a, f->k);
+		const int grid = (int)std::min<uint64_t>(b->n_tiles, (uint64_t)sm_count(f->device) * 2);
+		if (grid > 0) {
+			e = launch_scan(a, f->counting != 0, true, grid, 0);
+		}
+	}
+	if (e == cudaSuccess) {
+		e = cudaDeviceSynchronize();
+	}
+	if (e == cudaSuccess && counts) {
+		e = cudaMemcpy(counts, d_counts, b->total, cudaMemcpyDeviceToHost);
+	}
+	if (e == cudaSuccess && valid_bits) {
+		e = cudaMemcpy(valid_bits, d_valid, (b->total + 31) / 32 * 4, cudaMemcpyDeviceToHost);
+	}
+	cudaFree(d_visit);
+	cudaFree(d_valid);
+	cudaFree(d_counts);
+	ntb_batch_free(b);
+	if (e != cudaSuccess) {
+		return cuda_fail(e, "scan");
+	}
+	return NTB_OK;
+}
+
+// ---------------------------------------------------------------- polishing
+int
+ntb_polish_device(ntb_filter* bloom, ntb_filter* rep, const ntb_params* p, ntb_batch* batch, char* host_bases, ntb_result** out)
+{
+	return polish_common(bloom, rep, p, batch, host_bases, out);
+}
+
+int
+ntb_polish_batch(ntb_filter* bloom, ntb_filter* rep, const ntb_params* p, char* bases, const uint64_t* offsets, uint64_t n_contigs,
+                 ntb_result** out)
+{
+	if (!bloom) {
+		return fail(NTB_EINVAL, "NULL argument");
+	}
+	ntb_batch* b = nullptr;
+	int rc = ntb_batch_upload(bases, offsets, n_contigs, bloom->device, &b);
+	if (rc != NTB_OK) {
+		return rc;
+	}
+	rc = polish_common(bloom, rep, p, b, bases, out);
+	ntb_batch_free(b);
+	return rc;
+}
+
+int
+ntb_result_contig(const ntb_result* r, uint64_t contig, int* polished, const ntb_node** nodes, uint64_t* n_nodes, const ntb_srec** srecs,
+                  uint64_t* n_srecs)
+{
+	if (!r || contig >= r->impl.contigs.size()) {
+		return fail(NTB_EINVAL, "bad contig index");
+	}
+	const ContigResult& c = r->impl.contigs[contig];
+	if (polished) {
+		*polished = c.polished ? 1 : 0;
+	}
+	if (nodes) {
+		*nodes = c.nodes.data();
+	}
+	if (n_nodes) {
+		*n_nodes = c.nodes.size();
+	}
+	if (srecs) {
+		*srecs = c.srecs.data();
+	}
+	if (n_srecs) {
+		*n_srecs = c.srecs.size();
+	}
+	return NTB_OK;
+}
+
+int
+ntb_result_stats(const ntb_result* r, ntb_stats* st)
+{
+	if (!r || !st) {
+		return fail(NTB_EINVAL, "NULL argument");
+	}
+	*st = r->impl.stats;
+	return NTB_OK;
+}
+
+void
+ntb_result_free(ntb_result* r)
+{
+	delete r;
+}
+
+// ---------------------------------------------------------------- writer
+int
+ntb_format_contig(const char* header, const char* seq, const ntb_node* nodes, uint64_t n_nodes, const ntb_srec* srecs, uint64_t n_srecs,
+                  int snv, ntb_strbuf* fa, ntb_strbuf* tsv, ntb_strbuf* vcf)
+{
+	if (!header || !seq || !nodes) {
+		return fail(NTB_EINVAL, "NULL argument");
+	}
+	std::string sfa, stsv, svcf;
+	format_contig(header, seq, nodes, (size_t)n_nodes, srecs, (size_t)n_srecs, snv != 0, nullptr, fa ? &sfa : nullptr, tsv ? &stsv : nullptr,
+	              vcf ? &svcf : nullptr);
+	strbuf_append(fa, sfa);
+	strbuf_append(tsv, stsv);
+	strbuf_append(vcf, svcf);
+	return NTB_OK;
+}
+
+int
+ntb_format_tsv_header(uint32_t k, uint32_t jump, int counting, ntb_strbuf* tsv)
+{
+	if (!tsv || jump == 0) {
+		return fail(NTB_EINVAL, "bad argument");
+	}
+	strbuf_append(tsv, tsv_header(k, jump, counting != 0));
+	return NTB_OK;
+}
+
+void
+ntb_strbuf_free(ntb_strbuf* b)
+{
+	if (b) {
+		std::free(b->data);
+		b->data = nullptr;
+		b->len = b->cap = 0;
+	}
+}
+}

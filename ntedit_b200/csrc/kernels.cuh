@@ -1,0 +1,60 @@
+// sm_100a kernels of the ntEdit hot path.
+//   K1 scan_kernel    : ntHash roll over every base + h-way filter probe -> visit bitmap (and, on request, counts / validity)
+//                       replaces the main-loop test + roll of ntedit.cpp:1806-1807, 2118-2138
+//   K2 walk_kernel    : one thread per segment replays the edit state machine (engine.h) at the flagged positions
+//                       replaces ntedit.cpp:1808-2116 (check-missing, substitutions, tryIndels, tryDeletion, makeEdit decisions)
+//   K4 occupancy_kernel : popcount / non-zero count of the filter (btllib get_fpr, printed by ntedit.cpp:387-395)
+//   K5 insert_kernel  : filter construction (src/ntedit_make_genome_bf.cpp:151-156)
+#pragma once
+#include "engine.h"
+
+#include <cuda_runtime.h>
+
+namespace ntb {
+
+// ------------------------------------------------------------------------------------------------------------------
+// K1 geometry: a CTA of SCAN_THREADS threads owns a tile of SCAN_TILE consecutive buffer positions; thread i owns the strip
+// [i*SCAN_STRIP, (i+1)*SCAN_STRIP).  SCAN_STRIP is 4 (mod 128) bytes so that the 32 lanes of a warp, each reading the same
+// word index of its own strip, hit 32 different shared-memory banks.
+constexpr int SCAN_THREADS = 256;
+constexpr int SCAN_STRIP = 132;
+constexpr int SCAN_TILE = SCAN_THREADS * SCAN_STRIP;   // 33792 positions = 1056 bitmap words
+constexpr int SCAN_HALO = 128;                          // bytes staged in front of a tile (>= KMAX+3, keeps 16-byte alignment)
+constexpr int SCAN_STAGE_BYTES = SCAN_HALO + SCAN_TILE; // one staged tile
+constexpr int SCAN_STAGES = 2;
+constexpr int SCAN_BITWORDS = SCAN_TILE / 32;
+// dynamic shared memory of one scan CTA: staged tiles, 1 (or 2 with the optional outputs) tile bitmaps, class table,
+// seed tables, mbarriers
+inline size_t
+scan_smem_bytes(bool extra)
+{
+	return (size_t)SCAN_STAGES * SCAN_STAGE_BYTES + (size_t)SCAN_BITWORDS * 4 * (extra ? 2 : 1) + 256 + 16 * 8 + SCAN_STAGES * 8;
+}
+
+struct ScanArgs
+{
+	const uint8_t* text;   // buffer position 0; SCAN_HALO readable bytes precede it and the buffer is zero-padded to whole tiles
+	uint64_t n_tiles;
+	FilterView filter;
+	uint32_t k;
+	uint32_t min_threshold;
+	uint32_t snv;          // visit = valid (no probes)
+	uint32_t* visit;       // bit per position: window valid and the main loop would enter its edit block
+	uint32_t* valid;       // optional: bit per position: window valid
+	uint8_t* counts;       // optional: byte per position: 0/1 (bit filter) or min counter (counting filter); 0 when invalid
+	uint64_t mult[HMAX];   // i ^ (k * MULTISEED)
+	uint64_t seed[5];      // A C G T none
+	uint64_t rotk[5];      // srol^k of the same
+};
+
+// launches scan_kernel<hash_num, counting, extra> on `grid` persistent CTAs
+cudaError_t launch_scan(const ScanArgs& a, bool counting, bool extra, int grid, cudaStream_t stream);
+
+__global__ void walk_kernel(const uint8_t* text, const uint32_t* visit, FilterView bloom, FilterView rep, const __grid_constant__ KParams kp,
+                            const Task* tasks, TaskResult* results, uint32_t n_tasks, Event* events, uint32_t ev_cap, Counters* ctr);
+
+__global__ void insert_kernel(const uint8_t* text, uint64_t total, uint8_t* data, FilterView f, const __grid_constant__ KParams kp);
+
+__global__ void occupancy_kernel(const uint8_t* data, uint64_t bytes, int counting, unsigned long long* out);
+
+} // namespace ntb

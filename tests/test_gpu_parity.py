@@ -1,0 +1,143 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI, against the oracle (C restatement) and, when the
+prebuilt oracle/_ref/ntedit_ref travelled to the box, against the unmodified reference binary.  Bit-exact."""
+import os
+import tempfile
+
+import numpy as np
+import pytest
+
+from ntedit_b200 import synth
+from tests import cases as tc
+
+pytestmark = pytest.mark.gpu
+
+
+def device_filters(nb, inp):
+    bloom = nb.BloomFilter.create(inp["fbytes"], inp["k"], inp["h"], counting=inp["counting"], device=0)
+    for t in inp["truths"]:
+        for _ in range(inp["cov"]):
+            bloom.insert([(b"t", t)])
+    rep = None
+    if inp["rep_truth"] is not None:
+        rep = nb.BloomFilter.create(inp["fbytes"] // 4, inp["k"], inp["h"], counting=False, device=0)
+        rep.insert([(b"r", inp["rep_truth"])])
+    return bloom, rep
+
+
+@pytest.mark.parametrize("case", tc.CASES, ids=[c["name"] for c in tc.CASES])
+@pytest.mark.parametrize("segment_len", [0, 160])
+def test_polish_matches_oracle_and_reference(nb, oracle, case, segment_len):
+    inp = tc.make_inputs(1000 * tc.CASES.index(case) + 1, **case.get("g", {}))
+    ofilt, orep = tc.oracle_filters(oracle, inp)
+    bloom, rep = device_filters(nb, inp)
+    # filter construction parity (K5) -- byte-identical arrays
+    assert np.array_equal(ofilt.data(), bloom.download())
+    if rep:
+        assert np.array_equal(orep.data(), rep.download())
+
+    params = nb.default_params(segment_len=segment_len, **case["p"])
+    fa, tsv, vcf, st = nb.polish(inp["contigs"], bloom, params, bloomrep=rep)
+
+    op = oracle.default_params(inp["k"], inp["h"], **tc.oracle_param_overrides(case["p"]))
+    if orep:
+        op.secbf = 1
+    ofa, otsv, ovcf = oracle.polish(inp["contigs"], ofilt, op, bloomrep=orep,
+                                    min_contig_len=case["p"].get("min_contig_len", 100))
+    assert fa == ofa
+    assert tsv == otsv
+    assert vcf == ovcf
+
+    if oracle.have_ref():
+        tmp = tempfile.mkdtemp(prefix="gpupar_")
+        fpath = os.path.join(tmp, "f.bf")
+        bloom.save(fpath)          # the product's own writer of the btllib format feeds the reference
+        rpath = None
+        if rep:
+            rpath = os.path.join(tmp, "rep.bf")
+            rep.save(rpath)
+        dpath = os.path.join(tmp, "draft.fa")
+        synth.write_fasta(dpath, inp["contigs"])
+        rfa, rtsv, rvcf = oracle.run_ref(dpath, fpath, workdir=tmp, extra=case["flags"], rep_path=rpath)
+        assert fa == rfa
+        assert tsv == rtsv
+        assert vcf == b"".join(l for l in rvcf.splitlines(True) if not l.startswith(b"#"))
+    ofilt.free()
+    if orep:
+        orep.free()
+
+
+@pytest.mark.parametrize("counting", [False, True])
+@pytest.mark.parametrize("k,h,fbytes", [(25, 3, 1 << 16), (32, 4, 100003), (19, 1, 77777), (64, 2, 1 << 15)])
+def test_scan_matches_oracle(nb, oracle, k, h, fbytes, counting):
+    """K1 through the ABI: per-position count and window validity, including contig borders, N runs, lower case."""
+    rng = np.random.default_rng(k * 100 + h)
+    truth = synth.random_genome(90000, rng)
+    draft = synth.mutate(truth, rng, 5e-3, 1e-3, lower_frac=0.02, n_frac=0.01, iupac_frac=0.001)
+    contigs = [(b"a", draft[:40000].tobytes()), (b"b", draft[40000:40000 + k - 1].tobytes()), (b"c", b"A"),
+               (b"d", draft[45000:].tobytes())]
+    ofilt = oracle.OracleFilter.new(fbytes, k, h, counting)
+    ofilt.insert_seq(truth.tobytes())
+    if counting:
+        ofilt.insert_seq(truth[:30000].tobytes())
+    bloom = nb.BloomFilter.create(fbytes, k, h, counting=counting, device=0)
+    bloom.insert([(b"t", truth.tobytes())])
+    if counting:
+        bloom.insert([(b"t2", truth[:30000].tobytes())])
+    assert np.array_equal(ofilt.data(), bloom.download())
+    counts, valid, offs = nb.scan(bloom, contigs)
+    for c, (_, s) in enumerate(contigs):
+        want = ofilt.scan_counts(s)
+        o = int(offs[c])
+        got_valid = valid[o:o + len(s)]
+        got = counts[o:o + len(s)]
+        assert np.array_equal(got_valid, want != 0xFF)  # counts stay far below 255 here, so 0xFF only marks invalid
+        inval = ~got_valid
+        assert np.array_equal(got[got_valid], want[got_valid])
+        assert not got[inval].any()
+    # NUL separators are never valid windows
+    assert not valid[[int(x) - 1 for x in offs[1:]]].any()
+    ofilt.free()
+
+
+def test_filter_file_roundtrip_and_fpr(nb, oracle, tmp_path):
+    rng = np.random.default_rng(5)
+    truth = synth.random_genome(50000, rng)
+    for counting in (False, True):
+        bloom = nb.BloomFilter.create(123457, 25, 3, counting=counting, device=0)
+        bloom.insert([(b"t", truth.tobytes())])
+        p = str(tmp_path / ("f%d.bf" % counting))
+        bloom.save(p)
+        of = oracle.OracleFilter.load(p)          # the oracle's reader of the btllib format
+        assert of.k == 25 and of.h == 3 and of.counting == counting and of.nbytes == 123457
+        assert np.array_equal(of.data(), bloom.download())
+        assert abs(of.fpr() - bloom.get_fpr()) < 1e-12
+        again = nb.BloomFilter.load(p, device=0)  # and the product's reader
+        assert np.array_equal(again.download(), bloom.download())
+        assert again.get_k() == 25 and again.get_hash_num() == 3 and again.is_counting() == counting
+        of.free()
+
+
+def test_large_batch_properties(nb, oracle):
+    """Size-independent properties at a size the oracle cannot check exhaustively in the test budget:
+    polishing an error-free draft is the identity; polishing twice is idempotent on the second pass."""
+    rng = np.random.default_rng(11)
+    truth = synth.random_genome(3_000_000, rng)
+    bloom = nb.BloomFilter.create(1 << 24, 25, 3, device=0)
+    bloom.insert([(b"t", truth.tobytes())])
+    p = nb.default_params(mode=0)
+    fa, tsv, vcf, st = nb.polish([(b"clean", truth.tobytes())], bloom, p)
+    assert fa == b">clean\n" + truth.tobytes() + b"\n"
+    assert tsv.count(b"\n") == 1 and vcf == b""
+    draft = synth.mutate(truth, rng, 1e-3, 1e-4)
+    fa1, tsv1, _, st1 = nb.polish([(b"d", draft.tobytes())], bloom, p)
+    seq1 = fa1.split(b"\n")[1]
+    fa2, tsv2, _, st2 = nb.polish([(b"d", seq1)], bloom, p)
+    assert st1["edits"] > 2000
+    # a second pass finds (almost) nothing left to edit and never un-does the first pass
+    assert st2["edits"] <= st1["edits"] // 50
+    # spot-check the big case against the oracle on a prefix
+    ofilt = oracle.OracleFilter.new(1 << 24, 25, 3, False)
+    ofilt.insert_seq(truth.tobytes())
+    ofa, otsv, _ = oracle.polish([(b"d", draft.tobytes())], ofilt, oracle.default_params(25, 3, mode=0))
+    assert fa1 == ofa and tsv1 == otsv
+    ofilt.free()
