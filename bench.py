@@ -1,0 +1,428 @@
+#!/usr/bin/env python
+"""bench.py -- bases polished / second on BASELINE.json's headline configuration.
+
+Workload (configs[2] of BASELINE.json, the one the metric is quoted on): a synthetic 3 Gbp human-like draft
+(24 contigs of 50-250 Mbp + 2000 x 100 kbp, substitution rate 1e-3, indel rate 1e-4, 0.2 % lower case, N runs), a
+4 GiB k=25 h=3 Bloom filter holding every k-mer of the error-free genome, ntEdit mode 1.  A "step" is one pass of the
+whole hot path (scan kernel, walker kernel rounds, host stitch + rope replay) over the whole draft.
+
+  value : bases/s, batch already resident in HBM when the timed region starts (K steps in one bracket)
+  e2e   : bases/s through the C-ABI call a binding makes (ntb_polish_batch) with the draft in pinned HOST memory --
+          host->device copy of the bases and device->host copy of the edit events inside the timed region
+  roofline : scan kernel (K1), algorithmic bytes = (1 + 32*h) per base (one text byte + h random
+          32-byte sectors), duration from CUDA events on its stream
+  cpu_baseline : the UNMODIFIED reference (oracle/_ref/ntedit_ref, OpenMP over contigs) on a bounded sample of the
+          same draft with the same filter file, on this box's host cores
+
+`--impl reference` times that reference binary as the measured arm (same config, bounded sample per step).
+Multi-GPU (torchrun): every rank polishes its own 3 Gbp draft (a different error realisation of the same genome)
+against the same filter -- built on rank 0 and broadcast once over NCCL; no collective on the hot path (weak scaling).
+"""
+import argparse
+import json
+import os
+import shutil
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+K, H = 25, 3
+SEED = 20261017
+
+WORKLOADS = {
+    # name: (total bases, filter bytes, large contigs, small contigs, mode)
+    "3Gbp_k25_4GiB_m1": dict(total=3_000_000_000, fbytes=4 << 30, n_large=24, n_small=2000, small_len=100_000, mode=1),
+    "100Mbp_k25_1GiB_m0": dict(total=100_000_000, fbytes=1 << 30, n_large=100, n_small=0, small_len=0, mode=0),
+    "tiny": dict(total=20_000_000, fbytes=1 << 26, n_large=8, n_small=40, small_len=50_000, mode=1),
+}
+
+
+def contig_lengths(w):
+    small = w["n_small"] * w["small_len"]
+    big_total = w["total"] - small
+    n = w["n_large"]
+    if w["n_small"] == 0:
+        lens = [big_total // n] * n
+    else:
+        weights = np.linspace(50, 250, n)
+        lens = [int(x) for x in weights / weights.sum() * big_total]
+    lens[-1] += big_total - sum(lens)
+    return lens + [w["small_len"]] * w["n_small"]
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.rows = []
+        self.stop_flag = threading.Event()
+        self.proc = None
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                self.rows.append([x.strip() for x in line.split(",")])
+                if self.stop_flag.is_set():
+                    break
+        except Exception:
+            pass
+
+    def finish(self):
+        self.stop_flag.set()
+        if self.proc:
+            self.proc.terminate()
+        sm = []
+        smax = 0
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                smax = max(smax, float(r[1]))
+                for nm, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                continue
+        busy = [x for x in sm if x > 0]
+        return {"sm_mhz": float(np.median(busy)) if busy else None, "sm_max_mhz": smax or None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def build_workload(w, dev, rank, bloom, nb):
+    """Returns (draft buffer uint8 tensor on device with NUL separators, offsets np.uint64).  When `bloom` is given,
+    every k-mer of the error-free genome is inserted into it (filter construction kernel)."""
+    lens = contig_lengths(w)
+    drafts = []
+    for ci, n in enumerate(lens):
+        g = torch.Generator(device=dev)
+        g.manual_seed(SEED + ci)          # genome: same on every rank
+        # the error realisation differs per rank: re-seed after the genome part by deriving a second generator
+        truth, draft = gen_contig_rank(n, g, dev, rank, ci)
+        if bloom is not None:
+            tb = torch.cat([truth, torch.zeros(1, dtype=torch.uint8, device=dev)])
+            offs = np.array([0, len(tb)], dtype=np.uint64)
+            b = nb.Batch.wrap_device(tb.data_ptr(), offs, device=dev.index)
+            bloom.insert_batch(b)
+            b.free()
+            del tb
+        drafts.append(draft)
+        del truth
+    total = sum(len(d) + 1 for d in drafts)
+    buf = torch.zeros(total, dtype=torch.uint8, device=dev)
+    offs = np.zeros(len(drafts) + 1, dtype=np.uint64)
+    o = 0
+    for i, d in enumerate(drafts):
+        buf[o:o + len(d)] = d
+        o += len(d) + 1
+        offs[i + 1] = o
+    del drafts
+    torch.cuda.empty_cache()
+    return buf, offs
+
+
+def gen_contig_rank(n, g, dev, rank, ci):
+    """Genome from generator g (rank independent); errors from a rank-specific generator."""
+    lut = torch.tensor(list(b"ACGT"), dtype=torch.uint8, device=dev)
+    code = torch.randint(0, 4, (n,), dtype=torch.uint8, device=dev, generator=g)
+    n_dup = min(2000, int(n * 0.05 / 5000)) if n > 100_000 else 0
+    if n_dup:
+        lens = torch.randint(1000, 10000, (n_dup,), generator=g, device=dev).tolist()
+        src = torch.randint(0, n - 10000, (n_dup,), generator=g, device=dev).tolist()
+        dst = torch.randint(0, n - 10000, (n_dup,), generator=g, device=dev).tolist()
+        for ln, s, d in zip(lens, src, dst):
+            code[d:d + ln] = code[s:s + ln].clone()
+    truth = lut[code.long()]
+    e = torch.Generator(device=dev)
+    e.manual_seed(SEED * 31 + 1000003 * rank + ci)
+    d_code = code
+    sub = (torch.rand(n, device=dev, generator=e) < 1e-3).nonzero().flatten()
+    d_code[sub] = (d_code[sub] + torch.randint(1, 4, (len(sub),), dtype=torch.uint8, device=dev, generator=e)) % 4
+    rep = torch.ones(n, dtype=torch.int32, device=dev)
+    site = (torch.rand(n, device=dev, generator=e) < 1e-4).nonzero().flatten()
+    ln = torch.randint(1, 6, (len(site),), device=dev, generator=e)
+    is_del = torch.rand(len(site), device=dev, generator=e) < 0.5
+    rep[site[~is_del]] = 1 + ln[~is_del].int()
+    dsite, dln = site[is_del], ln[is_del]
+    for j in range(5):
+        m = dln > j
+        rep[(dsite[m] + j).clamp(max=n - 1)] = 0
+    src_idx = torch.repeat_interleave(torch.arange(n, device=dev, dtype=torch.int32), rep)
+    out = d_code[src_idx.long()]
+    first = torch.ones(len(src_idx), dtype=torch.bool, device=dev)
+    first[1:] = src_idx[1:] != src_idx[:-1]
+    ins_pos = (~first).nonzero().flatten()
+    out[ins_pos] = torch.randint(0, 4, (len(ins_pos),), dtype=torch.uint8, device=dev, generator=e)
+    del src_idx, first, rep, ins_pos
+    draft = lut[out.long()]
+    del out
+    m = len(draft)
+    low = (torch.rand(m, device=dev, generator=e) < 2e-3).nonzero().flatten()
+    draft[low] |= 0x20
+    n_runs = int(m * 1e-3 / 500)
+    if n_runs:
+        starts = torch.randint(0, max(1, m - 1000), (n_runs,), generator=e, device=dev).tolist()
+        lens = torch.randint(10, 1000, (n_runs,), generator=e, device=dev).tolist()
+        for s, l in zip(starts, lens):
+            draft[s:s + l] = ord("N")
+    return truth, draft
+
+
+def write_sample_fasta(path, host_buf, offs, target_bases, chunk=1_000_000):
+    """Bounded sample for the CPU reference: the draft cut into <=1 Mbp pseudo-contigs (the reference parallelises
+    over contigs only, ntedit.cpp:2213-2252) until target_bases are written.  Returns bases written."""
+    written = 0
+    n = 0
+    with open(path, "wb") as fh:
+        for c in range(len(offs) - 1):
+            s, e = int(offs[c]), int(offs[c + 1]) - 1
+            p = s
+            while p < e and written < target_bases:
+                q = min(e, p + chunk)
+                if q - p >= 1000:
+                    fh.write(b">sample%d\n" % n)
+                    fh.write(host_buf[p:q].tobytes())
+                    fh.write(b"\n")
+                    written += q - p
+                    n += 1
+                p = q
+            if written >= target_bases:
+                break
+    return written
+
+
+def time_reference(ref_bin, draft_path, tiny_path, filter_path, threads, mode, workdir):
+    """wall(sample) - wall(200 bp draft): isolates filter load + FPR popcount."""
+    def run(dp, tag):
+        t0 = time.perf_counter()
+        subprocess.run([ref_bin, "-f", dp, "-r", filter_path, "-b", os.path.join(workdir, tag), "-t", str(threads),
+                        "-m", str(mode)], check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        return time.perf_counter() - t0
+    t_load = run(tiny_path, "tiny")
+    t_all = run(draft_path, "sample")
+    return max(1e-6, t_all - t_load), t_load, t_all
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=os.environ.get("NTB_BENCH_WORKLOAD", "3Gbp_k25_4GiB_m1"))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--sample-mbp", type=float, default=0.0, help="CPU reference sample size (0 = from core count)")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    w = WORKLOADS[args.workload]
+    cores = os.cpu_count() or 1
+
+    if args.impl == "reference" and rank != 0:
+        return 0
+
+    import ntedit_b200 as nb
+    nb.lib.load()  # fails loudly if the CUDA library is not built
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+
+    dist = None
+    if world > 1 and args.impl == "ours":
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    # ------------------------------------------------------------------ inputs
+    t_setup = time.perf_counter()
+    # the filter lives in a torch tensor so that it can be replicated with one NCCL broadcast at load time -- the only
+    # collective of the design; the library wraps the device pointer
+    filt = torch.zeros(w["fbytes"] + 64, dtype=torch.uint8, device=dev)
+    bloom = nb.BloomFilter.wrap_device(filt.data_ptr(), w["fbytes"], K, H, counting=False, device=dev.index)
+    buf, offs = build_workload(w, dev, rank, bloom if (rank == 0 or dist is None) else None, nb)
+    if dist is not None:
+        torch.cuda.synchronize()
+        dist.broadcast(filt, src=0)
+    torch.cuda.synchronize()
+    n_contigs = len(offs) - 1
+    bases = int(offs[-1]) - n_contigs
+    fpr = bloom.get_fpr()
+    setup_s = time.perf_counter() - t_setup
+
+    params = nb.default_params(mode=w["mode"])
+    host = torch.empty(len(buf), dtype=torch.uint8, pin_memory=True)
+    host.copy_(buf)
+    torch.cuda.synchronize()
+    host_np = host.numpy()
+
+    # ------------------------------------------------------------------ reference arm / cpu baseline helper
+    def reference_run(steps, warmup):
+        from oracle import pyoracle as po
+        if not po.have_ref():
+            return None
+        tmp = tempfile.mkdtemp(prefix="ntb_ref_")
+        try:
+            fpath = os.path.join(tmp, "filter.bf")
+            bloom.save(fpath)
+            target = int(args.sample_mbp * 1e6) if args.sample_mbp > 0 else int(min(bases, cores * 1.0e6 * 12))
+            dpath = os.path.join(tmp, "sample.fa")
+            sample_bases = write_sample_fasta(dpath, host_np, offs, target)
+            tiny = os.path.join(tmp, "tiny.fa")
+            with open(tiny, "wb") as fh:
+                fh.write(b">tiny\n" + host_np[:200].tobytes() + b"\n")
+            times = []
+            for i in range(warmup + steps):
+                dt, t_load, t_all = time_reference(po.REF_BIN, dpath, tiny, fpath, cores, w["mode"], tmp)
+                if i >= warmup:
+                    times.append(dt)
+            return dict(value=sample_bases * len(times) / sum(times), sample_bases=sample_bases, times=times,
+                        t_load=t_load)
+        finally:
+            shutil.rmtree(tmp, ignore_errors=True)
+
+    config = {"workload": args.workload, "k": K, "hash_num": H, "filter_bytes": w["fbytes"], "filter_fpr": fpr,
+              "mode": w["mode"], "bases_per_gpu": bases, "contigs_per_gpu": n_contigs,
+              "errors": "substitution 1e-3, indel 1e-4 (len 1-5), 0.2% lower case, N runs",
+              "l2_note": "inputs (3 GB draft + 4 GiB filter) are far larger than the 126 MB L2",
+              "parallelism": "contigs sharded per GPU, filter replicated (1 NCCL broadcast at load)" if world > 1 else "1 GPU"}
+
+    if args.impl == "reference":
+        r = reference_run(args.steps, max(0, min(args.warmup, 1)))
+        if r is None:
+            print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/ntedit_ref not present on this box"}))
+            return 0
+        sample = "%d bases of the same draft as <=1 Mbp pseudo-contigs, same 4 GiB filter file; time = wall - wall(200 bp draft)" % r["sample_bases"]
+        line = {"metric": "bases polished/sec", "value": r["value"], "unit": "bases/s", "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * sum(r["times"]) / len(r["times"]),
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+                "impl": "reference", "config": config,
+                "cpu_baseline": {"value": r["value"], "unit": "bases/s", "cores": cores, "kind": "reference", "sample": sample},
+                "e2e": {"value": r["value"], "unit": "bases/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return 0
+
+    # ------------------------------------------------------------------ our arm
+    batch = nb.Batch.wrap_device(buf.data_ptr(), offs, device=dev.index)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def step_resident():
+        res = nb.kmerize_and_correct_device(batch, bloom, params, host_buf=None)
+        st = res.stats()
+        d = st.as_dict()
+        res.free()
+        return d
+
+    for _ in range(args.warmup):
+        last = step_resident()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    barrier()
+    t0 = time.perf_counter()
+    stats = []
+    for _ in range(args.steps):
+        stats.append(step_resident())
+    barrier()
+    dt = time.perf_counter() - t0
+    clocks = sampler.finish()
+
+    # e2e: host buffers through ntb_polish_batch; the call mutates the draft in place (as the reference mutates
+    # contigSeq), so the pinned working copy is restored from a pristine copy between steps, outside the timed region
+    work = torch.empty(len(host), dtype=torch.uint8, pin_memory=True)
+    e2e_t = 0.0
+    e2e_stats = []
+    n_e2e = max(1, min(args.steps, 3))
+    for i in range(1 + n_e2e):
+        work.copy_(host)
+        barrier()
+        t1 = time.perf_counter()
+        res = nb.kmerize_and_correct(work.numpy(), offs, bloom, params)
+        torch.cuda.synchronize()
+        t2 = time.perf_counter()
+        st = res.stats().as_dict()
+        res.free()
+        if i > 0:
+            e2e_t += t2 - t1
+            e2e_stats.append(st)
+
+    dt_t = torch.tensor([dt, e2e_t], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(dt_t, op=dist.ReduceOp.MAX)
+    dt_max, e2e_max = float(dt_t[0]), float(dt_t[1])
+
+    cpu = None
+    if rank == 0 and not args.no_cpu_baseline:
+        try:
+            r = reference_run(1, 0)
+            if r is not None:
+                cpu = {"value": r["value"], "unit": "bases/s", "cores": cores, "kind": "reference",
+                       "sample": "%d bases of the same draft as <=1 Mbp pseudo-contigs, same filter file, %d threads; "
+                                 "time = wall - wall(200 bp draft, %.1f s load)" % (r["sample_bases"], cores, r["t_load"])}
+        except Exception as ex:  # the baseline must never take the bench line down
+            cpu = {"value": None, "unit": "bases/s", "cores": cores, "kind": "reference", "sample": "failed: %r" % (ex,)}
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+        ms_scan = float(np.mean([s["ms_scan"] for s in stats]))
+        ms_walk = float(np.mean([s["ms_walk"] for s in stats]))
+        ms_host = float(np.mean([s["ms_host"] for s in stats]))
+        positions = int(offs[-1])
+        alg_bytes = (1 + 32 * H) * positions
+        achieved = alg_bytes / (ms_scan * 1e-3) / 1e9
+        ev_bytes = 36
+        d2h = int(np.mean([s["edits"] for s in e2e_stats]) * ev_bytes) + 28 * int(e2e_stats[0]["segments"])
+        line = {
+            "metric": "bases polished/sec", "value": world * bases * args.steps / dt_max, "unit": "bases/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * dt_max / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+            "config": config,
+            "e2e": {"value": world * bases * n_e2e / e2e_max, "unit": "bases/s", "h2d_bytes_per_step": int(offs[-1]),
+                    "d2h_bytes_per_step": d2h, "steps": n_e2e,
+                    "note": "ntb_polish_batch on pinned host memory; working copy restored between steps outside the timed region"},
+            "gpu_launches": int(sum(s["kernel_launches"] for s in stats)),
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "kernel": "scan_kernel<3,false,false>", "achieved": achieved, "peak": peak,
+                         "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": ms_scan},
+            "cpu_baseline": cpu,
+            "breakdown_ms": {"scan_kernel": ms_scan, "walk_kernel": ms_walk, "host_stitch_replay": ms_host,
+                             "d2h_events": float(np.mean([s["ms_d2h"] for s in stats])), "rounds": stats[-1]["rounds"],
+                             "segments": stats[-1]["segments"], "reruns": stats[-1]["reruns"], "sites": stats[-1]["sites"],
+                             "edits": stats[-1]["edits"], "setup_s": setup_s},
+        }
+        print(json.dumps(line))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -315,6 +315,27 @@ struct CudaBackend
 			NTB_BE(cudaStreamSynchronize(stream));
 			NTB_BE(cudaEventElapsedTime(&ms, ev0, ev1));
 			ms_d2h += ms;
+			if (std::getenv("NTB_DEBUG_TASKS")) {
+				// diagnostics: the slowest walkers of this launch
+				std::vector<size_t> idx(n);
+				for (size_t i = 0; i < n; i++) {
+					idx[i] = i;
+				}
+				const size_t top = std::min<size_t>(12, n);
+				std::partial_sort(idx.begin(), idx.begin() + top, idx.end(),
+				                  [&](size_t a, size_t b) { return results[a].kcycles > results[b].kcycles; });
+				unsigned long long tot = 0;
+				for (size_t i = 0; i < n; i++) {
+					tot += results[i].kcycles;
+				}
+				std::fprintf(stderr, "[ntb] walk launch: %zu tasks, %.2f ms, sum %.1f Mcycles\n", n, ms_walk, tot / 1024.0);
+				for (size_t q = 0; q < top; q++) {
+					const TaskResult& r = results[idx[q]];
+					const Task& t = tasks[idx[q]];
+					std::fprintf(stderr, "[ntb]   task %zu contig %u [%u,%u) kcycles %u sites %u events %u end %u status %u\n", idx[q], t.contig,
+					             t.start, t.end, r.kcycles, r.n_sites, r.n_events, r.end_pos, r.status);
+				}
+			}
 			return NTB_OK;
 		}
 	}

@@ -344,7 +344,9 @@ walk_kernel(const uint8_t* text, const uint32_t* visit, FilterView bloom, Filter
 	io.ctr = ctr;
 	Walker<352> w(io, kp);
 	TaskResult res;
+	const long long c0 = clock64();
 	w.run(task, res);
+	res.kcycles = (uint32_t)((clock64() - c0) >> 10);
 	results[i] = res;
 }
 

@@ -74,6 +74,7 @@ struct TaskResult
 	uint32_t n_sites;
 	uint32_t status;
 	uint8_t stale[4];      // values of the reference's uninitialised locals after the walker's last site (see STALE_REF)
+	uint32_t kcycles;      // SM clock cycles / 1024 the walker ran for (diagnostics)
 };
 constexpr uint32_t ST_DONE = 1u;          // finished normally
 constexpr uint32_t ST_CONTIG_END = 2u;    // the reference's main loop ended (roll failed / guard): nothing after this walker counts
