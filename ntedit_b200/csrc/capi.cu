@@ -285,12 +285,9 @@ struct CudaBackend
 		for (;;) {
 			NTB_BE(cudaMemsetAsync(d_ctr, 0, sizeof(Counters), stream));
 			NTB_BE(cudaEventRecord(ev0, stream));
-			const unsigned block = 64;
-			const unsigned grid = (unsigned)((n + block - 1) / block);
-			walk_kernel<<<grid, block, 0, stream>>>(batch->d_text, d_visit, fb, fr, kp, d_tasks, d_results, (uint32_t)n, d_events,
-			                                        (uint32_t)std::min<size_t>(cap_events, 0xFFFFFFF0u), d_ctr);
+			NTB_BE(launch_walk(batch->d_text, d_visit, fb, fr, kp, d_tasks, d_results, (uint32_t)n, d_events,
+			                   (uint32_t)std::min<size_t>(cap_events, 0xFFFFFFF0u), d_ctr, sm_count(batch->device), stream));
 			launches++;
-			NTB_BE(cudaGetLastError());
 			NTB_BE(cudaEventRecord(ev1, stream));
 			Counters ctr;
 			NTB_BE(cudaMemcpyAsync(&ctr, d_ctr, sizeof ctr, cudaMemcpyDeviceToHost, stream));

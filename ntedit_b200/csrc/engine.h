@@ -1,15 +1,24 @@
-// Device engine ("walker"): one thread replays ntEdit's per-contig state machine (kmerizeAndCorrect and callees,
+// Device engine ("walker"): one WARP replays ntEdit's per-contig state machine (kmerizeAndCorrect and callees,
 // ntedit.cpp:1216-2151) over one segment of a contig, starting from a clean window, and reports the edit
 // decisions as makeEdit-level events.  The authoritative rope is rebuilt on the host from those events
 // (replay.hpp); the walker keeps only a bounded local copy of the rope tail -- enough to answer every
 // getCharacter/increment/roll the reference would make while the window is "dirty" (overlaps an edit).
+//
+// Execution model.  All walker state lives in one WalkerState object per warp (shared memory on the device).  The
+// control flow is warp-uniform: every lane takes the same branches, decided from that shared state.  State is only
+// ever WRITTEN inside "leader sections" (lane 0, fenced by warp barriers); the expensive part of a site -- hashing
+// and probing the filter for the check-missing subset, the substitution trials and the insertion / deletion
+// candidates (ntedit.cpp:1826-1858, 1917-1981, 1451-1744) -- runs as one candidate per lane: the lane rolls the
+// candidate's k-mers with the same hash_roll the scan uses, issues all Bloom probes of up to PROBE_G sampled k-mers
+// before consuming any of them, and writes its support count to the shared state; the leader then resolves the
+// candidates in the reference's order, so the decision is the one the sequential loop would have taken.
 //
 // While the window is clean (k consecutive, unedited draft bases) the walker does not roll base by base:
 // it jumps to the next position flagged by the scan kernel's visit bitmap (K1) and re-seeds the hash there,
 // which is exactly where the reference's main loop would next find `!bloom.contains(hVal)` (ntedit.cpp:1806).
 //
 // The file compiles for the device (product) and, for the test-only host simulator under tests/hostsim,
-// for the CPU; the product library never instantiates the host version.
+// for the CPU (one "lane"); the product library never instantiates the host version.
 #pragma once
 #include "nthash.h"
 
@@ -17,9 +26,61 @@ namespace ntb {
 
 #if defined(__CUDACC__)
 #define NTB_FN __host__ __device__
+#define NTB_FN_NOINLINE __host__ __device__ __noinline__
 #else
 #define NTB_FN
+#define NTB_FN_NOINLINE __attribute__((noinline))
 #endif
+
+// ------------------------------------------------------------------------------------------------------------------
+// warp execution model (host build: a warp of one lane)
+NTB_FN inline uint32_t
+lane_id()
+{
+#if defined(__CUDA_ARCH__)
+	return threadIdx.x & 31u;
+#else
+	return 0;
+#endif
+}
+
+NTB_FN inline uint32_t
+lane_count()
+{
+#if defined(__CUDA_ARCH__)
+	return 32u;
+#else
+	return 1u;
+#endif
+}
+
+NTB_FN inline void
+warp_sync()
+{
+#if defined(__CUDA_ARCH__)
+	__syncwarp();
+#endif
+}
+
+#define NTB_LEADER_BEGIN \
+	warp_sync();         \
+	if (lane_id() == 0) {
+#define NTB_LEADER_END \
+	}                  \
+	warp_sync();
+
+// filter probes are uniformly random over a multi-GB array: read-only path, do not allocate in L1
+NTB_FN inline uint32_t
+probe_byte(const uint8_t* p)
+{
+#if defined(__CUDA_ARCH__)
+	uint32_t v;
+	asm volatile("ld.global.nc.L1::no_allocate.u8 %0, [%1];" : "=r"(v) : "l"(p));
+	return v;
+#else
+	return *p;
+#endif
+}
 
 struct Cursor
 {
@@ -50,14 +111,41 @@ struct WalkerIO
 	Counters* ctr;
 };
 
+constexpr uint32_t MAX_INS_TRIES = 341;   // num_tries[5], ntedit.cpp:172
+constexpr uint32_t MAX_DELETIONS = 10;    // ntedit.cpp:2489-2493
+constexpr int PROBE_G = 10;               // sampled k-mers whose probes are in flight together, per lane
+constexpr int PROBE_HU = 4;               // hash functions probed per pass (hash_num <= HMAX takes ceil(h/4) passes)
+constexpr uint32_t TEXT_CACHE = 256;      // bytes of contig text kept in the shared state around the window
+constexpr uint32_t LOOKAHEAD = 32;        // dirty-window positions whose site test is evaluated in one pass
+
+// One candidate k-mer series: "change the window's last base to X, then roll Q times; the first `c` incoming bases
+// are synthetic (an insertion string), the rest come from the linearised rope starting at offset `d`; sample the
+// filter after roll `first` and every `period` rolls after it (and, with `pre`, before the first roll)".
+struct Cand
+{
+	uint64_t syn;      // synthetic incoming chars, byte j = j-th
+	uint32_t Q;        // rolls to perform
+	uint32_t c;        // leading synthetic rolls
+	uint32_t d;        // offset into lin_in[] of the first real incoming char
+	uint32_t first;    // index of the first roll after which a sample is taken
+	uint32_t period;   // sampling period (>= 1)
+	uint8_t X;         // new tail char (when change)
+	uint8_t change;    // apply NTMC64_changelast(draft -> X) first
+	uint8_t pre;       // sample the changed k-mer itself
+	uint8_t patch;     // the outgoing char read at the tail's own slot is X (in-place substitution trial)
+	uint8_t kind;      // CK_*
+};
+constexpr uint8_t CK_CHECK = 0; // record the raw filter value of every sample (check-missing loop)
+constexpr uint8_t CK_SOLID = 1; // count samples that are present && solid
+constexpr uint8_t CK_SITE = 2;  // one sample: would the main loop enter its edit block here?
+
+// Everything a walker mutates.  One per warp; written by the leader lane only.
 template<int NCAP>
-struct Walker
+struct WalkerState
 {
 	static constexpr int OVCAP = KMAX + 8;
-	static constexpr int PREVCAP = 2 * KMAX + 16;
 
-	const WalkerIO& io;
-	const KParams& P;
+	WalkerIO io;
 
 	// bounded copy of the rope tail (seqNode vector, ntedit.cpp:613-620)
 	int8_t ty[NCAP];
@@ -69,10 +157,6 @@ struct Walker
 	uint32_t ov_pos[OVCAP];
 	uint8_t ov_ch[OVCAP];
 	uint32_t ov_n;
-	// temporary substitution of a trial (ntedit.cpp:1936-1940)
-	uint32_t patch_pos;
-	uint8_t patch_ch;
-	bool patch_on;
 
 	Cursor h, t;
 	HashState hs;
@@ -86,33 +170,91 @@ struct Walker
 	bool anchored;
 	uint32_t last_event, n_events, n_sites, first_touch, status;
 
-	NTB_FN Walker(const WalkerIO& io_, const KParams& p_) : io(io_), P(p_) {}
+	// main-loop control (decided by the leader, read by every lane)
+	uint32_t end_pos;
+	uint32_t act;
+	uint32_t visit_hit;
+	bool need_seed, do_seed, site_now;
+
+	// contig text around the window
+	uint8_t tc[TEXT_CACHE];
+	uint32_t tc_base, tc_n;
+
+	// ---- scratch of the site being evaluated
+	// linearised rope: chars the next rolls would push out of / pull into the window (roll(), ntedit.cpp:1216-1247)
+	uint8_t lin_out[KMAX + LOOKAHEAD + 2];
+	uint8_t lin_in[KMAX + LOOKAHEAD + 2];
+	uint32_t n_rolls;     // successful simulated rolls
+	uint32_t n_check;     // completed iterations of the check-missing loop
+	uint32_t patch_idx;   // index into lin_out[] that reads the tail's own slot
+	bool dnf;             // do_not_fix
+	unsigned char raw, draft;
+	uint32_t cands;       // substitution candidates, packed
+	bool tail_is_pos, tail_is_chr, touched;
+	uint32_t next;        // what the candidate loop does next
+	unsigned char index_char;
+	Site s;
+	uint32_t num_deletions;
+	bool site_ok;
+	// phase results
+	uint8_t chk[KMAX + 1];
+	uint32_t chk_n;
+	uint8_t gate[4];
+	uint32_t sup[4];
+	uint8_t ins_sup[MAX_INS_TRIES];
+	uint8_t del_sup[MAX_DELETIONS + 2];
+	// tryIndels bookkeeping across chunks
+	uint32_t ti_i0, ti_i1, ti_nd0, ti_ndel;
+	uint32_t tb_support, ta_support, tb_type, tb_len;
+	char tb_indel[8];
+	bool ti_done, ti_ret;
+	// dirty-window lookahead: bit j = the main loop would enter its edit block after j more plain rolls
+	uint32_t la_bits, la_n, la_used;
+};
+
+constexpr uint32_t ACT_STOP = 0, ACT_CLEAN = 1, ACT_DIRTY = 2;
+constexpr uint32_t NEXT_CAND = 0, NEXT_INDELS = 1, NEXT_STOP = 2;
+
+template<int NCAP>
+struct Walker
+{
+	static constexpr int OVCAP = WalkerState<NCAP>::OVCAP;
+	static constexpr int PREVCAP = 2 * KMAX + 16;
+
+	WalkerState<NCAP>& S;
+	const KParams& P;
+
+	NTB_FN Walker(WalkerState<NCAP>& s_, const KParams& p_) : S(s_), P(p_) {}
 
 	// ---------------------------------------------------------------- text / rope access
 	NTB_FN unsigned char rd(uint32_t pos) const
 	{
-		if (patch_on && pos == patch_pos) {
-			return patch_ch;
-		}
-		for (uint32_t i = 0; i < ov_n; i++) {
-			if (ov_pos[i] == pos) {
-				return ov_ch[i];
+		for (uint32_t i = 0; i < S.ov_n; i++) {
+			if (S.ov_pos[i] == pos) {
+				return S.ov_ch[i];
 			}
 		}
-		return pos < io.len ? io.text[pos] : 0;
+		if (pos >= S.io.len) {
+			return 0;
+		}
+		const uint32_t o = pos - S.tc_base;
+		if (o < S.tc_n) {
+			return S.tc[o];
+		}
+		return S.io.text[pos];
 	}
 
 	// getCharacter, ntedit.cpp:812-823
 	NTB_FN unsigned char cchar(const Cursor& c) const
 	{
-		if (c.ni >= nn) {
+		if (c.ni >= S.nn) {
 			return 0;
 		}
-		if (ty[c.ni] == 0) {
+		if (S.ty[c.ni] == 0) {
 			return rd(c.pos);
 		}
-		if (ty[c.ni] == 1) {
-			return ch[c.ni];
+		if (S.ty[c.ni] == 1) {
+			return S.ch[c.ni];
 		}
 		return 0;
 	}
@@ -120,22 +262,22 @@ struct Walker
 	// increment, ntedit.cpp:826-844
 	NTB_FN void step(Cursor& c) const
 	{
-		if (c.ni >= nn) {
+		if (c.ni >= S.nn) {
 			return;
 		}
-		const int8_t tp = ty[c.ni];
+		const int8_t tp = S.ty[c.ni];
 		if (tp == 0) {
 			c.pos++;
-			if (c.pos > ep[c.ni]) {
+			if (c.pos > S.ep[c.ni]) {
 				c.ni++;
-				if (c.ni < nn && ty[c.ni] == 0) {
-					c.pos = sp[c.ni];
+				if (c.ni < S.nn && S.ty[c.ni] == 0) {
+					c.pos = S.sp[c.ni];
 				}
 			}
 		} else if (tp == 1) {
 			c.ni++;
-			if (c.ni < nn && ty[c.ni] == 0) {
-				c.pos = sp[c.ni];
+			if (c.ni < S.nn && S.ty[c.ni] == 0) {
+				c.pos = S.sp[c.ni];
 			}
 		}
 	}
@@ -143,52 +285,53 @@ struct Walker
 	// roll, ntedit.cpp:1216-1247
 	NTB_FN bool roll(Cursor& hh, Cursor& tt, unsigned char& out, unsigned char& in) const
 	{
-		if (hh.pos >= io.len || hh.ni >= nn) {
+		if (hh.pos >= S.io.len || hh.ni >= S.nn) {
 			return false;
 		}
 		out = cchar(hh);
 		step(hh);
-		if (tt.pos >= io.len || tt.ni >= nn) {
+		if (tt.pos >= S.io.len || tt.ni >= S.nn) {
 			return false;
 		}
 		step(tt);
-		if (tt.pos >= io.len || tt.ni >= nn) {
+		if (tt.pos >= S.io.len || tt.ni >= S.nn) {
 			return false;
 		}
 		in = cchar(tt);
 		return true;
 	}
 
+	// ---- rope surgery: leader only
 	NTB_FN void put(uint32_t i, int8_t type, uint8_t c, uint32_t s, uint32_t e)
 	{
 		if (i >= (uint32_t)NCAP) {
-			status |= ST_ROPE_OVERFLOW;
+			S.status |= ST_ROPE_OVERFLOW;
 			return;
 		}
-		ty[i] = type;
-		ch[i] = c;
-		sp[i] = s;
-		ep[i] = e;
-		if (i >= nn) {
-			nn = i + 1;
+		S.ty[i] = type;
+		S.ch[i] = c;
+		S.sp[i] = s;
+		S.ep[i] = e;
+		if (i >= S.nn) {
+			S.nn = i + 1;
 		}
 	}
 
 	NTB_FN void move_node(uint32_t dst, uint32_t src)
 	{
-		ty[dst] = ty[src];
-		ch[dst] = ch[src];
-		sp[dst] = sp[src];
-		ep[dst] = ep[src];
+		S.ty[dst] = S.ty[src];
+		S.ch[dst] = S.ch[src];
+		S.sp[dst] = S.sp[src];
+		S.ep[dst] = S.ep[src];
 	}
 
 	// makeInsertion, ntedit.cpp:625-714
 	NTB_FN void rope_insert(uint32_t& t_ni, uint32_t insert_pos, const char* bases, uint32_t nb)
 	{
-		const int8_t otype = ty[t_ni];
-		const uint32_t os = sp[t_ni], oe = ep[t_ni];
+		const int8_t otype = S.ty[t_ni];
+		const uint32_t os = S.sp[t_ni], oe = S.ep[t_ni];
 		if (otype == 0 && insert_pos > os) {
-			ep[t_ni] = insert_pos - 1;
+			S.ep[t_ni] = insert_pos - 1;
 			for (uint32_t i = 0; i < nb; i++) {
 				put(t_ni + i + 1, 1, (uint8_t)bases[i], 0, 0);
 			}
@@ -199,15 +342,15 @@ struct Walker
 		if (otype == 0 || otype == 1) {
 			// lift the live run starting at the tail node and put it back behind the inserted characters
 			uint32_t nlift = 0;
-			while (t_ni + nlift < nn && ty[t_ni + nlift] != -1) {
+			while (t_ni + nlift < S.nn && S.ty[t_ni + nlift] != -1) {
 				nlift++;
 			}
 			if (t_ni + nb + nlift > (uint32_t)NCAP) {
-				status |= ST_ROPE_OVERFLOW;
+				S.status |= ST_ROPE_OVERFLOW;
 				return;
 			}
-			if (t_ni + nb + nlift > nn) {
-				nn = t_ni + nb + nlift;
+			if (t_ni + nb + nlift > S.nn) {
+				S.nn = t_ni + nb + nlift;
 			}
 			for (uint32_t q = nlift; q > 0; q--) {
 				move_node(t_ni + nb + q - 1, t_ni + q - 1);
@@ -215,10 +358,10 @@ struct Walker
 			// slots between the lifted run's old end and its new start that were not overwritten stay as the
 			// reference leaves them: the old entries were marked dead before being re-appended
 			for (uint32_t q = 0; q < nb; q++) {
-				ty[t_ni + q] = 1;
-				ch[t_ni + q] = (uint8_t)bases[q];
-				sp[t_ni + q] = 0;
-				ep[t_ni + q] = 0;
+				S.ty[t_ni + q] = 1;
+				S.ch[t_ni + q] = (uint8_t)bases[q];
+				S.sp[t_ni + q] = 0;
+				S.ep[t_ni + q] = 0;
 			}
 		}
 	}
@@ -227,27 +370,27 @@ struct Walker
 	NTB_FN void rope_delete(uint32_t& t_ni, uint32_t& pos, uint32_t num_del)
 	{
 		for (;;) {
-			const int8_t otype = ty[t_ni];
-			const uint32_t os = sp[t_ni], oe = ep[t_ni];
+			const int8_t otype = S.ty[t_ni];
+			const uint32_t os = S.sp[t_ni], oe = S.ep[t_ni];
 			uint32_t leftover = 0;
 			if (otype == 0) {
 				if (pos <= os) {
 					if (pos + num_del <= oe) {
-						sp[t_ni] = pos + num_del;
-						pos = sp[t_ni];
+						S.sp[t_ni] = pos + num_del;
+						pos = S.sp[t_ni];
 						return;
 					}
 					leftover = pos + num_del - oe;
 					pos = oe + 1;
 					uint32_t i = t_ni + 1;
-					while (i < nn && ty[i] != -1) {
+					while (i < S.nn && S.ty[i] != -1) {
 						move_node(i - 1, i);
-						ty[i] = -1;
+						S.ty[i] = -1;
 						i++;
 					}
 				} else {
 					if (pos + num_del <= oe) {
-						ep[t_ni] = pos - 1;
+						S.ep[t_ni] = pos - 1;
 						const uint32_t ns = pos + num_del;
 						pos = ns;
 						t_ni++;
@@ -255,31 +398,31 @@ struct Walker
 						return;
 					}
 					leftover = pos + num_del - oe;
-					ep[t_ni] = pos - 1;
+					S.ep[t_ni] = pos - 1;
 					pos = oe + 1;
 					t_ni++;
 				}
 			} else if (otype == 1) {
 				uint32_t i = t_ni;
 				leftover = num_del;
-				while (i < nn && ty[i] == 1 && leftover > 0) {
-					ty[i] = -1;
+				while (i < S.nn && S.ty[i] == 1 && leftover > 0) {
+					S.ty[i] = -1;
 					leftover--;
 					i++;
 				}
 				uint32_t j = t_ni;
-				while (i < nn && ty[i] != -1) {
+				while (i < S.nn && S.ty[i] != -1) {
 					move_node(j, i);
-					ty[i] = -1;
+					S.ty[i] = -1;
 					i++;
 					j++;
 				}
 			} else {
 				return;
 			}
-			if (leftover > 0 && t_ni < nn && ty[t_ni] != -1) {
-				if (ty[t_ni] == 0) {
-					pos = sp[t_ni];
+			if (leftover > 0 && t_ni < S.nn && S.ty[t_ni] != -1) {
+				if (S.ty[t_ni] == 0) {
+					pos = S.sp[t_ni];
 				}
 				num_del = leftover;
 				continue;
@@ -288,49 +431,194 @@ struct Walker
 		}
 	}
 
-	// ---------------------------------------------------------------- filter queries
-	NTB_FN unsigned q_count(const HashState& s) const { return filter_count(io.bloom, hash_canonical(s), P.k); }
+	// ---------------------------------------------------------------- filter queries (single k-mer, leader lane)
+	// value of a k-mer in a filter: bit filter -> 1 when all hash_num bits are set else 0; counting filter -> min counter
+	// (BFWrapper::contains / get_count, ntedit.cpp:368-376)
+	NTB_FN unsigned q_count(const HashState& s) const { return filter_count(S.io.bloom, hash_canonical(s), P.k); }
 
-	NTB_FN bool q_contains(const HashState& s) const { return filter_contains(io.bloom, hash_canonical(s), P.k); }
-
-	// bloom.contains(hVal) && is_kmer_solid(hVal, bloom, bloomrep), ntedit.cpp:465-473
-	NTB_FN bool q_present_solid(const HashState& s) const
-	{
-		const uint64_t b = hash_canonical(s);
-		if (P.counting) {
-			const unsigned c = filter_count(io.bloom, b, P.k);
-			if (c == 0 || c < P.min_threshold || c > P.max_threshold) {
-				return false;
-			}
-		} else if (!filter_contains(io.bloom, b, P.k)) {
-			return false;
-		}
-		if (P.h_rep && filter_contains(io.rep, b, P.k)) {
-			return false;
-		}
-		return true;
-	}
+	NTB_FN bool q_contains(const HashState& s) const { return filter_contains(S.io.bloom, hash_canonical(s), P.k); }
 
 	NTB_FN bool meets_edit(uint32_t c) const { return c >= P.thr_edit; }
 
-	// ---------------------------------------------------------------- events
+	// the main loop's test, ntedit.cpp:1806-1807
+	NTB_FN bool is_site_value(uint32_t c) const { return P.snv || c == 0 || (P.counting && c < P.min_threshold); }
+
+	// bloom.contains(hVal) && is_kmer_solid(hVal, bloom, bloomrep) without the secondary filter, ntedit.cpp:465-473
+	NTB_FN bool solid_value(uint32_t c) const
+	{
+		if (P.counting) {
+			return !(c == 0 || c < P.min_threshold || c > P.max_threshold);
+		}
+		return c != 0;
+	}
+
+	// ---------------------------------------------------------------- probing a group of sampled k-mers
+	// val[g] = value of k-mer hb[g] in filter F for every g whose bit is set in `valid`.  All loads of a pass are
+	// issued before any is consumed.
+	NTB_FN void probe_group(const FilterView& F, const uint64_t (&hb)[PROBE_G], uint32_t valid, uint32_t (&val)[PROBE_G]) const
+	{
+#pragma unroll
+		for (int g = 0; g < PROBE_G; g++) {
+			val[g] = F.counting ? 255u : 1u;
+		}
+		for (uint32_t i0 = 0; i0 < F.hash_num; i0 += PROBE_HU) {
+			uint32_t got[PROBE_G][PROBE_HU];
+			uint32_t sh[PROBE_G];
+#pragma unroll
+			for (int g = 0; g < PROBE_G; g++) {
+				sh[g] = 0;
+#pragma unroll
+				for (int u = 0; u < PROBE_HU; u++) {
+					got[g][u] = F.counting ? 255u : 0xFFu;
+					if (((valid >> g) & 1u) && i0 + u < F.hash_num) {
+						const uint64_t slot = filter_slot(F, hash_extend(hb[g], P.k, i0 + u));
+						if (F.counting) {
+							got[g][u] = probe_byte(F.data + slot);
+						} else {
+							sh[g] |= ((uint32_t)slot & 7u) << (3 * u);
+							got[g][u] = probe_byte(F.data + (slot >> 3));
+						}
+					}
+				}
+			}
+#pragma unroll
+			for (int g = 0; g < PROBE_G; g++) {
+#pragma unroll
+				for (int u = 0; u < PROBE_HU; u++) {
+					if (F.counting) {
+						val[g] = got[g][u] < val[g] ? got[g][u] : val[g];
+					} else {
+						val[g] &= got[g][u] >> ((sh[g] >> (3 * u)) & 7u);
+					}
+				}
+			}
+		}
+	}
+
+	// ---------------------------------------------------------------- one candidate, one lane
+	// Rolls the candidate's k-mers and classifies the sampled ones.  CK_SOLID: pre_ok = the changed k-mer itself is
+	// present && solid, count = number of sampled k-mers that are.  CK_CHECK: raw values go to S.chk[] (single writer:
+	// the lane that owns the check candidate).  CK_SITE: count = 1 when the (single) sample is a site.
+	NTB_FN_NOINLINE void eval_cand(const Cand& cd, uint32_t& pre_ok, uint32_t& count)
+	{
+		HashState s = S.hs;
+		if (cd.change) {
+			hash_changelast(s, S.draft, cd.X, P);
+		}
+		uint32_t r = 0, jc = cd.first, nchk = 0;
+		bool pre = cd.pre != 0;
+		const uint32_t n_rolls = S.n_rolls;
+		const uint32_t patch_idx = cd.patch ? S.patch_idx : NONE32;
+		pre_ok = 0;
+		count = 0;
+		while (pre || r < cd.Q) {
+			uint64_t hb[PROBE_G];
+			uint32_t valid = 0, premask = 0;
+#pragma unroll
+			for (int g = 0; g < PROBE_G; g++) {
+				hb[g] = 0;
+				if (pre) {
+					hb[g] = hash_canonical(s);
+					valid |= 1u << g;
+					premask = 1u << g;
+					pre = false;
+				} else {
+					while (r < cd.Q) {
+						unsigned char in;
+						if (r < cd.c) {
+							in = (unsigned char)((cd.syn >> (8 * r)) & 0xFF);
+						} else {
+							const uint32_t j = cd.d + r - cd.c;
+							if (j >= n_rolls) {
+								r = cd.Q; // this roll and every later one fails (ntedit.cpp:1216-1247): nothing more is counted
+								break;
+							}
+							in = S.lin_in[j];
+						}
+						const unsigned char out = r == patch_idx ? cd.X : S.lin_out[r];
+						hash_roll(s, out, in, P);
+						const bool samp = jc == 0;
+						jc = samp ? cd.period - 1 : jc - 1;
+						r++;
+						if (samp) {
+							hb[g] = hash_canonical(s);
+							valid |= 1u << g;
+							break;
+						}
+					}
+				}
+			}
+			if (!valid) {
+				break;
+			}
+			uint32_t val[PROBE_G];
+			probe_group(S.io.bloom, hb, valid, val);
+			if (cd.kind == CK_CHECK) {
+#pragma unroll
+				for (int g = 0; g < PROBE_G; g++) {
+					if ((valid >> g) & 1u) {
+						S.chk[nchk++] = (uint8_t)val[g];
+					}
+				}
+			} else if (cd.kind == CK_SITE) {
+#pragma unroll
+				for (int g = 0; g < PROBE_G; g++) {
+					if (((valid >> g) & 1u) && is_site_value(val[g])) {
+						count = 1;
+					}
+				}
+			} else {
+				uint32_t solid = 0;
+#pragma unroll
+				for (int g = 0; g < PROBE_G; g++) {
+					if (((valid >> g) & 1u) && solid_value(val[g])) {
+						solid |= 1u << g;
+					}
+				}
+				if (P.h_rep && solid) {
+					// secondary filter (-e): a k-mer found there is not solid, ntedit.cpp:467-468
+					uint32_t rv[PROBE_G];
+					probe_group(S.io.rep, hb, solid, rv);
+#pragma unroll
+					for (int g = 0; g < PROBE_G; g++) {
+						if (((solid >> g) & 1u) && rv[g] != 0) {
+							solid &= ~(1u << g);
+						}
+					}
+				}
+				if (solid & premask) {
+					pre_ok = 1;
+				}
+#if defined(__CUDA_ARCH__)
+				count += (uint32_t)__popc(solid & ~premask);
+#else
+				count += (uint32_t)__builtin_popcount(solid & ~premask);
+#endif
+			}
+		}
+		if (cd.kind == CK_CHECK) {
+			S.chk_n = nchk;
+		}
+	}
+
+	// ---------------------------------------------------------------- events (leader)
 	NTB_FN void emit(uint8_t kind, uint8_t flags, uint8_t draft, const Site& s)
 	{
 		uint32_t idx;
 #if defined(__CUDA_ARCH__)
-		idx = atomicAdd(&io.ctr->n_events, 1u);
+		idx = atomicAdd(&S.io.ctr->n_events, 1u);
 #else
-		idx = io.ctr->n_events++;
+		idx = S.io.ctr->n_events++;
 #endif
-		if (idx >= io.ev_cap) {
-			status |= ST_EV_OVERFLOW;
-			io.ctr->overflow = 1;
+		if (idx >= S.io.ev_cap) {
+			S.status |= ST_EV_OVERFLOW;
+			S.io.ctr->overflow = 1;
 			return;
 		}
 		Event e;
-		e.prev = last_event;
-		e.t_pos = t.pos;
-		e.advance = anchored ? NONE32 : adv;
+		e.prev = S.last_event;
+		e.t_pos = S.t.pos;
+		e.advance = S.anchored ? NONE32 : S.adv;
 		e.support = (uint16_t)s.best_support;
 		e.altsupp[0] = (uint16_t)s.altsupp1;
 		e.altsupp[1] = (uint16_t)s.altsupp2;
@@ -347,23 +635,23 @@ struct Walker
 			e.indel[i] = s.indel[i];
 		}
 		e.pad_ = 0;
-		io.events[idx] = e;
-		last_event = idx;
-		n_events++;
-		adv = 0;
-		anchored = false;
+		S.io.events[idx] = e;
+		S.last_event = idx;
+		S.n_events++;
+		S.adv = 0;
+		S.anchored = false;
 	}
 
-	// ---------------------------------------------------------------- pieces of makeEdit that need the rope
+	// ---------------------------------------------------------------- pieces of makeEdit that need the rope (leader)
 	// getPrevInsertion, ntedit.cpp:907-922: reverse-complemented run of inserted characters left of the tail
 	NTB_FN uint32_t prev_insertion(char* out) const
 	{
-		uint32_t ni = t.ni, n = 0;
-		if ((ni < nn && ty[ni] == 0 && t.pos == sp[ni]) || (ni < nn && ty[ni] == 1)) {
+		uint32_t ni = S.t.ni, n = 0;
+		if ((ni < S.nn && S.ty[ni] == 0 && S.t.pos == S.sp[ni]) || (ni < S.nn && S.ty[ni] == 1)) {
 			ni--;
 		}
-		while (ni < nn && ty[ni] == 1 && n < (uint32_t)PREVCAP - 8) {
-			const unsigned char c = ch[ni];
+		while (ni < S.nn && S.ty[ni] == 1 && n < (uint32_t)PREVCAP - 8) {
+			const unsigned char c = S.ch[ni];
 			const unsigned cc = base_code(c);
 			out[n++] = cc == 0 ? 'T' : cc == 1 ? 'G' : cc == 2 ? 'C' : (cc == 3 && (c | 0x20) == 't') ? 'A' : 'N';
 			ni--;
@@ -395,7 +683,7 @@ struct Walker
 
 	// would makeEdit's case 2 take one of its "skipped_repeat" branches (ntedit.cpp:1315-1380)?  Those branches end the
 	// contig (findAcceptedKmer cannot succeed after the removal), so the walker only has to detect them.
-	NTB_FN bool insertion_guard_fires(const Site& s) const
+	NTB_FN_NOINLINE bool insertion_guard_fires(const Site& s) const
 	{
 		char prev[PREVCAP];
 		uint32_t np = prev_insertion(prev);
@@ -420,32 +708,9 @@ struct Walker
 		return false;
 	}
 
-	// ---------------------------------------------------------------- candidate trials
-	// tryDeletion, ntedit.cpp:1451-1545
-	NTB_FN uint32_t try_deletion(unsigned char draft, uint32_t num_del) const
-	{
-		HashState s = hs;
-		Cursor hh = h, tt = t;
-		unsigned char out = 0, in = 0;
-		for (uint32_t i = 0; i < num_del; i++) {
-			step(tt);
-		}
-		hash_changelast(s, draft, cchar(tt), P);
-		uint32_t present = q_present_solid(s) ? 1u : 0u;
-		for (uint32_t q = 1; q + 2 <= P.k && hh.pos < io.len; q++) {
-			if (roll(hh, tt, out, in)) {
-				hash_roll(s, out, in, P);
-				if (q % P.jump == 0 && q_present_solid(s)) {
-					present++;
-				}
-			}
-		}
-		return present >= P.thr_edit_del ? present : 0u;
-	}
-
 	// i-th string of ntedit.cpp:203-348 for first base `first`: all words of length 1..5 over ACGT that start with
-	// `first`, ordered by (length, lexicographic A<C<G<T)
-	NTB_FN static uint32_t indel_string(unsigned char first, uint32_t q, char* out)
+	// `first`, ordered by (length, lexicographic A<C<G<T).  Chars are packed little-endian; returns the length.
+	NTB_FN static uint32_t indel_string(unsigned char first, uint32_t q, uint64_t& packed)
 	{
 		uint32_t len = 1, start = 0, count = 1;
 		while (q >= start + count) {
@@ -454,103 +719,15 @@ struct Walker
 			len++;
 		}
 		uint32_t r = q - start;
-		out[0] = (char)first;
+		uint64_t p = 0;
 		for (uint32_t i = len - 1; i >= 1; i--) {
 			const uint32_t d = r & 3;
-			out[i] = d == 0 ? 'A' : d == 1 ? 'C' : d == 2 ? 'G' : 'T';
+			const uint64_t c = d == 0 ? 'A' : d == 1 ? 'C' : d == 2 ? 'G' : 'T';
+			p |= c << (8 * i);
 			r >>= 2;
 		}
+		packed = p | (uint64_t)first;
 		return len;
-	}
-
-	// tryIndels, ntedit.cpp:1548-1744
-	NTB_FN bool try_indels(unsigned char draft, unsigned char index_char, uint32_t& num_deletions, Site& site) const
-	{
-		uint32_t tb_support = 0, ta_support = 0, tb_type = 0, tb_len = 0;
-		char tb_indel[11];
-		unsigned char out = 0, in = 0;
-		for (uint32_t i = 0; i < P.max_ins_tries; i++) {
-			char ins[8];
-			uint32_t nins = indel_string(index_char, i, ins);
-			ins[nins++] = (char)draft;
-			HashState s = hs;
-			Cursor hh = h, tt = t;
-			hash_changelast(s, draft, index_char, P);
-			uint32_t present = 0, q = 0;
-			for (; q + 1 < nins && hh.pos < io.len; q++) {
-				hash_roll(s, cchar(hh), (unsigned char)ins[q + 1], P);
-				step(hh);
-				if (q % P.jump == 0 && q_present_solid(s)) {
-					present++;
-				}
-			}
-			for (; q + 1 < P.k && hh.pos < io.len; q++) {
-				if (roll(hh, tt, out, in)) {
-					hash_roll(s, out, in, P);
-					if (q % P.jump == 0 && q_present_solid(s)) {
-						present++;
-					}
-				}
-			}
-			nins--;
-			if (meets_edit(present)) {
-				if (P.mode == 0) {
-					site.best_type = 2;
-					for (uint32_t c = 0; c < nins; c++) {
-						site.indel[c] = ins[c];
-					}
-					site.indel_len = (uint8_t)nins;
-					site.best_support = present;
-					return true;
-				}
-				if (present >= tb_support) {
-					if (tb_support) {
-						ta_support = tb_support;
-					}
-					tb_type = 2;
-					for (uint32_t c = 0; c < nins; c++) {
-						tb_indel[c] = ins[c];
-					}
-					tb_len = nins;
-					tb_support = present;
-				}
-			}
-			if (num_deletions <= P.max_deletions) {
-				const uint32_t del_support = try_deletion(draft, num_deletions);
-				if (del_support > 0) {
-					if (P.mode == 0) {
-						site.best_type = 3;
-						site.indel_len = (uint8_t)num_deletions;
-						site.best_support = del_support;
-						return true;
-					}
-					if (del_support >= tb_support) {
-						if (tb_support) {
-							ta_support = tb_support;
-						}
-						tb_type = 3;
-						tb_len = num_deletions;
-						tb_support = del_support;
-					}
-				}
-				num_deletions++;
-			}
-		}
-		if (tb_support > 0) {
-			if ((P.mode == 2 && tb_support > site.best_support) || P.mode == 1) {
-				site.best_type = tb_type;
-				site.indel_len = (uint8_t)tb_len;
-				if (tb_type == 2) {
-					for (uint32_t c = 0; c < tb_len; c++) {
-						site.indel[c] = tb_indel[c];
-					}
-				}
-				site.best_support = tb_support;
-				site.altsupp1 = ta_support;
-			}
-			return true;
-		}
-		return false;
 	}
 
 	// substitution candidates, ntedit.cpp:178-199; returns up to 4 bases packed little-endian, 0-terminated
@@ -584,51 +761,337 @@ struct Walker
 #undef NTB_PACK
 	}
 
-	// ---------------------------------------------------------------- one site: ntedit.cpp:1808-2116
-	// returns false when the contig is finished (insertion guard fired)
-	NTB_FN bool evaluate_site()
+	// ---------------------------------------------------------------- linearisation of the rope around the window (leader)
+	// Simulates up to `want` calls of roll() from the current cursors without hashing: lin_out[m] / lin_in[m] are the chars
+	// the (m+1)-th roll pushes out / pulls in, n_rolls the number of rolls that succeed.  With `check` it also replays the
+	// control flow of the check-missing loop (ntedit.cpp:1826-1858): n_check iterations complete, dnf = do_not_fix.
+	NTB_FN void linearise(uint32_t want, bool check)
 	{
 		const uint32_t k = P.k;
-		const unsigned char raw = char_in;
-		const unsigned char draft = to_upper(raw);
-		n_sites++;
-		if (first_touch == NONE32) {
-			first_touch = t.pos;
+		S.patch_idx = NONE32;
+		S.n_rolls = 0;
+		if (check) {
+			S.n_check = 0;
+			S.dnf = false;
 		}
+		bool check_open = check;
+		const bool simple = S.nn == 1 && S.ty[0] == 0 && S.h.ni == 0 && S.t.ni == 0 && S.ov_n == 0 && S.t.pos - S.h.pos == k - 1 &&
+		                    S.ep[0] == S.io.len - 1 && S.t.pos < S.io.len;
+		if (simple) {
+			// clean window on a single position node: plain text
+			const uint32_t avail = S.io.len - 1 - S.t.pos;
+			const uint32_t n = avail < want ? avail : want;
+			for (uint32_t m = 0; m < n; m++) {
+				S.lin_out[m] = rd(S.h.pos + m);
+				S.lin_in[m] = rd(S.t.pos + 1 + m);
+			}
+			S.n_rolls = n;
+			S.patch_idx = k - 1;
+			if (check) {
+				uint32_t q = 0;
+				for (; q < k; q++) {
+					if (q >= n) { // roll fails at the end of the contig
+						S.dnf = true;
+						break;
+					}
+					if (!is_accepted_any_case(S.lin_in[q])) {
+						S.dnf = true;
+						break;
+					}
+				}
+				S.n_check = q;
+			}
+			return;
+		}
+		Cursor hh = S.h, tt = S.t;
+		for (uint32_t m = 0; m < want; m++) {
+			if (check_open && m >= k) {
+				check_open = false;
+			}
+			if (check_open && hh.pos >= S.io.len) {
+				check_open = false; // the loop condition ends the check loop without do_not_fix
+			}
+			// roll()
+			if (hh.pos >= S.io.len || hh.ni >= S.nn) {
+				if (check_open) {
+					S.dnf = true;
+				}
+				break;
+			}
+			const bool at_tail = S.tail_is_pos ? (S.ty[hh.ni] == 0 && hh.pos == S.t.pos) : S.tail_is_chr ? hh.ni == S.t.ni : false;
+			if (at_tail && S.patch_idx == NONE32) {
+				S.patch_idx = m;
+			}
+			const unsigned char out = cchar(hh);
+			step(hh);
+			if (tt.pos >= S.io.len || tt.ni >= S.nn) {
+				if (check_open) {
+					S.dnf = true;
+				}
+				break;
+			}
+			step(tt);
+			if (tt.pos >= S.io.len || tt.ni >= S.nn) {
+				if (check_open) {
+					S.dnf = true;
+				}
+				break;
+			}
+			const unsigned char in = cchar(tt);
+			S.lin_out[m] = out;
+			S.lin_in[m] = in;
+			S.n_rolls = m + 1;
+			if (check_open) {
+				if (!is_accepted_any_case(in)) {
+					S.dnf = true;
+					check_open = false;
+				} else {
+					S.n_check = m + 1;
+				}
+			}
+		}
+	}
 
-		// confirm the k-mer is missing on a subset of the next k windows, ntedit.cpp:1819-1864
-		HashState ts = hs;
-		Cursor th = h, tt = t;
-		unsigned char out = 0, in = 0;
-		uint32_t missing = 0, there = 0, nmed = 0;
-		uint8_t med[KMAX];
-		bool do_not_fix = false;
-		for (uint32_t q = 0; q < k && th.pos < io.len; q++) {
-			if (!roll(th, tt, out, in)) {
-				do_not_fix = true;
-				break;
+	// ---------------------------------------------------------------- phases: one candidate per lane
+	// phase 1: job 0 = the check-missing subset, job 1+ci = substitution candidate ci (gate + trial)
+	NTB_FN void phase_check_and_subs()
+	{
+		const uint32_t njobs = 5;
+		warp_sync();
+		for (uint32_t j = lane_id(); j < njobs; j += lane_count()) {
+			Cand cd;
+			cd.syn = 0;
+			cd.c = 0;
+			cd.d = 0;
+			cd.first = 0;
+			cd.period = P.jump;
+			cd.X = 0;
+			cd.change = 0;
+			cd.pre = 0;
+			cd.patch = 0;
+			uint32_t pre_ok = 0, count = 0;
+			if (j == 0) {
+				cd.kind = CK_CHECK;
+				cd.Q = S.n_check;
+				eval_cand(cd, pre_ok, count);
+			} else {
+				const unsigned char sub = (unsigned char)((S.cands >> (8 * (j - 1))) & 0xFF);
+				// candidates are 0-terminated: nothing after the first 0 is tried
+				bool live = sub != 0;
+				for (uint32_t q = 0; q + 1 < j; q++) {
+					if (((S.cands >> (8 * q)) & 0xFF) == 0) {
+						live = false;
+					}
+				}
+				if (live) {
+					cd.kind = CK_SOLID;
+					cd.X = sub;
+					cd.change = 1;
+					cd.pre = 1;
+					cd.patch = 1;
+					cd.Q = S.n_rolls < P.k ? S.n_rolls : P.k;
+					eval_cand(cd, pre_ok, count);
+				}
+				S.gate[j - 1] = (uint8_t)pre_ok;
+				S.sup[j - 1] = count;
 			}
-			hash_roll(ts, out, in, P);
-			if (!is_accepted_any_case(in)) {
-				do_not_fix = true;
-				break;
+		}
+		warp_sync();
+	}
+
+	// phase 2: insertion candidates [i0, i1) of tryIndels for S.index_char and the deletions its iterations would try
+	NTB_FN void phase_indels()
+	{
+		const uint32_t n_ins = S.ti_i1 - S.ti_i0;
+		const uint32_t njobs = n_ins + S.ti_ndel;
+		warp_sync();
+		for (uint32_t j = lane_id(); j < njobs; j += lane_count()) {
+			Cand cd;
+			cd.kind = CK_SOLID;
+			cd.change = 1;
+			cd.patch = 0;
+			cd.period = P.jump;
+			uint32_t pre_ok = 0, count = 0;
+			if (j < n_ins) {
+				// insertion string + the draft char, ntedit.cpp:1583-1645
+				const uint32_t i = S.ti_i0 + j;
+				uint64_t packed;
+				const uint32_t len = indel_string(S.index_char, i, packed);
+				cd.X = S.index_char;
+				cd.syn = (packed >> 8) | ((uint64_t)S.draft << (8 * (len - 1)));
+				cd.c = len;
+				cd.d = 0;
+				cd.pre = 0;
+				cd.first = 0;
+				cd.Q = P.k - 1;
+				eval_cand(cd, pre_ok, count);
+				S.ins_sup[i] = (uint8_t)count;
+			} else {
+				// tryDeletion, ntedit.cpp:1451-1545
+				const uint32_t n = S.ti_nd0 + (j - n_ins);
+				cd.X = n >= 1 && n - 1 < S.n_rolls ? S.lin_in[n - 1] : 0;
+				cd.syn = 0;
+				cd.c = 0;
+				cd.d = n;
+				cd.pre = 1;
+				cd.first = P.jump - 1;
+				cd.Q = P.k - 2;
+				eval_cand(cd, pre_ok, count);
+				S.del_sup[n] = (uint8_t)(pre_ok + count);
 			}
-			if (q % P.jump == 0) {
-				if (P.counting) {
-					const unsigned c = q_count(ts);
-					if (c == 0) {
-						missing++;
-					} else if (is_atgc_upper(draft) && c >= P.min_threshold) {
-						there++;
-						if (nmed < KMAX) {
-							med[nmed++] = (uint8_t)c;
+		}
+		warp_sync();
+	}
+
+	// tryIndels, ntedit.cpp:1548-1744.  Candidates are evaluated in chunks (one per lane), the leader then walks the
+	// iterations of the chunk in the reference's order: insertion i, then deletion num_deletions (shared across the
+	// index bases of a site, ntedit.cpp:1692-1729).
+	NTB_FN bool try_indels()
+	{
+		const uint32_t T = P.max_ins_tries;
+		NTB_LEADER_BEGIN
+		S.tb_support = S.ta_support = S.tb_type = S.tb_len = 0;
+		S.ti_done = false;
+		S.ti_ret = false;
+		S.ti_i0 = 0;
+		NTB_LEADER_END
+		while (S.ti_i0 < T) {
+			NTB_LEADER_BEGIN
+			uint32_t i1 = T;
+			if (P.mode == 0) {
+				// first hit wins: evaluate a small chunk first
+				i1 = S.ti_i0 == 0 ? 24 : S.ti_i0 == 24 ? 88 : T;
+				if (i1 > T) {
+					i1 = T;
+				}
+			}
+			S.ti_i1 = i1;
+			S.ti_nd0 = S.num_deletions;
+			uint32_t nd = 0;
+			if (S.num_deletions <= P.max_deletions) {
+				nd = P.max_deletions - S.num_deletions + 1;
+				if (nd > i1 - S.ti_i0) {
+					nd = i1 - S.ti_i0;
+				}
+			}
+			S.ti_ndel = nd;
+			NTB_LEADER_END
+			phase_indels();
+			NTB_LEADER_BEGIN
+			for (uint32_t i = S.ti_i0; i < S.ti_i1; i++) {
+				const uint32_t present = S.ins_sup[i];
+				if (meets_edit(present)) {
+					uint64_t packed;
+					const uint32_t nins = indel_string(S.index_char, i, packed);
+					if (P.mode == 0) {
+						S.s.best_type = 2;
+						for (uint32_t c = 0; c < nins; c++) {
+							S.s.indel[c] = (char)((packed >> (8 * c)) & 0xFF);
+						}
+						S.s.indel_len = (uint8_t)nins;
+						S.s.best_support = present;
+						S.ti_done = true;
+						S.ti_ret = true;
+						break;
+					}
+					if (present >= S.tb_support) {
+						if (S.tb_support) {
+							S.ta_support = S.tb_support;
+						}
+						S.tb_type = 2;
+						for (uint32_t c = 0; c < nins; c++) {
+							S.tb_indel[c] = (char)((packed >> (8 * c)) & 0xFF);
+						}
+						S.tb_len = nins;
+						S.tb_support = present;
+					}
+				}
+				if (S.num_deletions <= P.max_deletions) {
+					const uint32_t raw = S.del_sup[S.num_deletions];
+					const uint32_t del_support = raw >= P.thr_edit_del ? raw : 0u;
+					if (del_support > 0) {
+						if (P.mode == 0) {
+							S.s.best_type = 3;
+							S.s.indel_len = (uint8_t)S.num_deletions;
+							S.s.best_support = del_support;
+							S.ti_done = true;
+							S.ti_ret = true;
+							break;
+						}
+						if (del_support >= S.tb_support) {
+							if (S.tb_support) {
+								S.ta_support = S.tb_support;
+							}
+							S.tb_type = 3;
+							S.tb_len = S.num_deletions;
+							S.tb_support = del_support;
 						}
 					}
-				} else if (!q_contains(ts)) {
-					missing++;
-				} else if (is_atgc_upper(draft)) {
-					there++;
+					S.num_deletions++;
 				}
+			}
+			S.ti_i0 = S.ti_i1;
+			NTB_LEADER_END
+			if (S.ti_done) {
+				return S.ti_ret;
+			}
+		}
+		NTB_LEADER_BEGIN
+		if (S.tb_support > 0) {
+			if ((P.mode == 2 && S.tb_support > S.s.best_support) || P.mode == 1) {
+				S.s.best_type = S.tb_type;
+				S.s.indel_len = (uint8_t)S.tb_len;
+				if (S.tb_type == 2) {
+					for (uint32_t c = 0; c < S.tb_len; c++) {
+						S.s.indel[c] = S.tb_indel[c];
+					}
+				}
+				S.s.best_support = S.tb_support;
+				S.s.altsupp1 = S.ta_support;
+			}
+			S.ti_ret = true;
+		}
+		NTB_LEADER_END
+		return S.ti_ret;
+	}
+
+	// ---------------------------------------------------------------- one site: ntedit.cpp:1808-2116
+	// leader: what the reference does before the check loop, plus the linearisation
+	NTB_FN void site_begin()
+	{
+		S.raw = S.char_in;
+		S.draft = to_upper(S.raw);
+		S.n_sites++;
+		if (S.first_touch == NONE32) {
+			S.first_touch = S.t.pos;
+		}
+		S.tail_is_pos = S.t.ni < S.nn && S.ty[S.t.ni] == 0;
+		S.tail_is_chr = S.t.ni < S.nn && S.ty[S.t.ni] == 1;
+		linearise(P.k + MAX_DELETIONS + 1, true);
+		S.cands = candidates(S.draft);
+		S.site_ok = true;
+		S.chk_n = 0;
+	}
+
+	// leader: check-missing verdict (ntedit.cpp:1859-1873) and the site locals (ntedit.cpp:1876-1914)
+	NTB_FN bool site_after_check()
+	{
+		uint32_t missing = 0, there = 0, nmed = 0;
+		uint8_t med[KMAX + 1];
+		const bool atgc = is_atgc_upper(S.draft);
+		for (uint32_t i = 0; i < S.chk_n; i++) {
+			const uint32_t c = S.chk[i];
+			if (c == 0) {
+				missing++;
+			} else if (P.counting) {
+				if (atgc && c >= P.min_threshold) {
+					there++;
+					if (nmed < KMAX) {
+						med[nmed++] = (uint8_t)c;
+					}
+				}
+			} else if (atgc) {
+				there++;
 			}
 		}
 		uint32_t there_median = 0;
@@ -645,184 +1108,165 @@ struct Walker
 			}
 			there_median = med[nmed / 2];
 		}
-		const bool attempt =
-		    P.snv || (!do_not_fix && (missing >= P.thr_missing || (P.counting && there_median < P.min_threshold)));
+		const bool attempt = P.snv || (!S.dnf && (missing >= P.thr_missing || (P.counting && there_median < P.min_threshold)));
 		if (!attempt) {
-			return true;
+			return false;
 		}
-
-		Site s;
+		Site& s = S.s;
 		s.best_type = 0;
 		s.best_support = 0;
 		s.altsupp1 = s.altsupp2 = s.altsupp3 = 0;
-		s.best_sub = stale_best_sub;
-		s.altbase1 = stale_alt1;
-		s.altbase2 = stale_alt2;
-		s.altbase3 = stale_alt3;
+		s.best_sub = S.stale_best_sub;
+		s.altbase1 = S.stale_alt1;
+		s.altbase2 = S.stale_alt2;
+		s.altbase3 = S.stale_alt3;
 		s.indel_len = 0;
-		uint32_t num_deletions = 1;
-		bool touched = false;
-
+		S.num_deletions = 1;
+		S.touched = false;
 		if (P.snv && meets_edit(there)) {
-			s.best_sub = draft;
+			s.best_sub = S.draft;
 			s.best_support = P.counting ? there_median : there;
 		}
+		return true;
+	}
 
-		const uint32_t cands = candidates(draft);
-		const bool tail_is_pos = t.ni < nn && ty[t.ni] == 0;
-		const bool tail_is_chr = t.ni < nn && ty[t.ni] == 1;
-		for (uint32_t ci = 0; ci < 4; ci++) {
-			const unsigned char sub = (unsigned char)((cands >> (8 * ci)) & 0xFF);
-			if (!sub) {
-				break;
-			}
-			ts = hs;
-			hash_changelast(ts, draft, sub, P);
-			if (!(P.mode == 2 || q_present_solid(ts))) {
-				continue;
-			}
-			th = h;
-			tt = t;
-			touched = true;
-			if (tail_is_pos) {
-				patch_on = true;
-				patch_pos = t.pos;
-				patch_ch = sub;
-			} else if (tail_is_chr) {
-				ch[t.ni] = sub;
-			}
-			uint32_t present = 0;
-			for (uint32_t q = 0; q < k && th.pos < io.len && tt.pos < io.len; q++) {
-				if (!roll(th, tt, out, in)) {
-					break;
+	// leader: one iteration of the substitution loop (ntedit.cpp:1917-2092) up to the tryIndels call
+	NTB_FN void site_candidate(uint32_t ci)
+	{
+		Site& s = S.s;
+		const unsigned char sub = (unsigned char)((S.cands >> (8 * ci)) & 0xFF);
+		if (!sub) {
+			S.next = NEXT_STOP;
+			return;
+		}
+		S.next = NEXT_CAND;
+		if (!(P.mode == 2 || S.gate[ci])) {
+			return;
+		}
+		S.touched = true;
+		const uint32_t present = S.sup[ci];
+		if (meets_edit(present)) {
+			if (present >= s.best_support) {
+				if (s.altsupp2) {
+					s.altbase3 = s.altbase2;
+					s.altsupp3 = s.altsupp2;
 				}
-				hash_roll(ts, out, in, P);
-				if (q % P.jump == 0 && q_present_solid(ts)) {
-					present++;
+				if (s.altsupp1) {
+					s.altbase2 = s.altbase1;
+					s.altsupp2 = s.altsupp1;
 				}
-			}
-			if (tail_is_pos) {
-				patch_on = false;
-			} else if (tail_is_chr) {
-				ch[t.ni] = draft;
-			}
-			if (meets_edit(present)) {
-				if (present >= s.best_support) {
-					if (s.altsupp2) {
-						s.altbase3 = s.altbase2;
-						s.altsupp3 = s.altsupp2;
-					}
-					if (s.altsupp1) {
-						s.altbase2 = s.altbase1;
-						s.altsupp2 = s.altsupp1;
-					}
-					if (s.best_support) {
-						s.altsupp1 = s.best_support;
-						s.altbase1 = s.best_sub;
-					}
-					s.best_type = 1;
-					s.best_sub = sub;
-					s.best_support = present;
-				} else if (!s.altsupp1) {
+				if (s.best_support) {
+					s.altsupp1 = s.best_support;
+					s.altbase1 = s.best_sub;
+				}
+				s.best_type = 1;
+				s.best_sub = sub;
+				s.best_support = present;
+			} else if (!s.altsupp1) {
+				s.altbase1 = sub;
+				s.altsupp1 = present;
+			} else if (!s.altsupp2) {
+				if (present < s.altsupp1) {
+					s.altbase2 = sub;
+					s.altsupp2 = present;
+				} else {
+					s.altbase2 = s.altbase1;
+					s.altsupp2 = s.altsupp1;
 					s.altbase1 = sub;
 					s.altsupp1 = present;
-				} else if (!s.altsupp2) {
-					if (present < s.altsupp1) {
-						s.altbase2 = sub;
-						s.altsupp2 = present;
-					} else {
-						s.altbase2 = s.altbase1;
-						s.altsupp2 = s.altsupp1;
-						s.altbase1 = sub;
-						s.altsupp1 = present;
-					}
-				} else if (!s.altsupp3) {
-					if (present < s.altsupp2) {
-						s.altbase3 = sub;
-						s.altsupp3 = present;
-					} else if (present < s.altsupp1) {
-						s.altbase3 = s.altbase2;
-						s.altsupp3 = s.altsupp2;
-						s.altbase2 = sub;
-						s.altsupp2 = present;
-					} else {
-						s.altbase3 = s.altbase2;
-						s.altsupp3 = s.altsupp2;
-						s.altbase2 = s.altbase1;
-						s.altsupp2 = s.altsupp1;
-						s.altbase1 = sub;
-						s.altsupp1 = present;
-					}
 				}
-				if (P.mode == 0 || P.mode == 1) {
-					continue;
+			} else if (!s.altsupp3) {
+				if (present < s.altsupp2) {
+					s.altbase3 = sub;
+					s.altsupp3 = present;
+				} else if (present < s.altsupp1) {
+					s.altbase3 = s.altbase2;
+					s.altsupp3 = s.altsupp2;
+					s.altbase2 = sub;
+					s.altsupp2 = present;
+				} else {
+					s.altbase3 = s.altbase2;
+					s.altsupp3 = s.altsupp2;
+					s.altbase2 = s.altbase1;
+					s.altsupp2 = s.altsupp1;
+					s.altbase1 = sub;
+					s.altsupp1 = present;
 				}
 			}
-			if (P.mode == 2 || s.best_type != 1) {
-				if (try_indels(draft, sub, num_deletions, s)) {
-					if (P.mode == 0 || P.mode == 1) {
-						break;
-					}
-				}
+			if (P.mode == 0 || P.mode == 1) {
+				return;
 			}
 		}
-		stale_best_sub = s.best_sub;
-		stale_alt1 = s.altbase1;
-		stale_alt2 = s.altbase2;
-		stale_alt3 = s.altbase3;
+		if (P.mode == 2 || s.best_type != 1) {
+			S.index_char = sub;
+			S.next = NEXT_INDELS;
+		}
+	}
 
-		// makeEdit, ntedit.cpp:1250-1448
-		const uint8_t fl = (touched && raw != draft) ? EV_TOUCHED : 0;
+	// leader: makeEdit, ntedit.cpp:1250-1448.  site_ok = false when the contig is finished (insertion guard fired)
+	NTB_FN void site_commit()
+	{
+		Site& s = S.s;
+		const unsigned char draft = S.draft;
+		S.stale_best_sub = s.best_sub;
+		S.stale_alt1 = s.altbase1;
+		S.stale_alt2 = s.altbase2;
+		S.stale_alt3 = s.altbase3;
+		const uint8_t fl = (S.touched && S.raw != draft) ? EV_TOUCHED : 0;
 		switch (s.best_type) {
 		case 1:
 			emit(1, fl, draft, s);
-			if (tail_is_pos) {
-				if (ov_n >= (uint32_t)OVCAP) {
+			if (S.tail_is_pos) {
+				if (S.ov_n >= (uint32_t)OVCAP) {
 					// drop substitutions the head has already passed
 					uint32_t w = 0;
-					for (uint32_t i = 0; i < ov_n; i++) {
-						if (ov_pos[i] >= h.pos) {
-							ov_pos[w] = ov_pos[i];
-							ov_ch[w] = ov_ch[i];
+					for (uint32_t i = 0; i < S.ov_n; i++) {
+						if (S.ov_pos[i] >= S.h.pos) {
+							S.ov_pos[w] = S.ov_pos[i];
+							S.ov_ch[w] = S.ov_ch[i];
 							w++;
 						}
 					}
-					ov_n = w;
+					S.ov_n = w;
 				}
-				if (ov_n < (uint32_t)OVCAP) {
+				if (S.ov_n < (uint32_t)OVCAP) {
 					// a later substitution at the same position replaces the earlier one
 					uint32_t i = 0;
-					for (; i < ov_n; i++) {
-						if (ov_pos[i] == t.pos) {
+					for (; i < S.ov_n; i++) {
+						if (S.ov_pos[i] == S.t.pos) {
 							break;
 						}
 					}
-					ov_pos[i] = t.pos;
-					ov_ch[i] = s.best_sub;
-					if (i == ov_n) {
-						ov_n++;
+					S.ov_pos[i] = S.t.pos;
+					S.ov_ch[i] = s.best_sub;
+					if (i == S.ov_n) {
+						S.ov_n++;
 					}
 				} else {
-					status |= ST_ROPE_OVERFLOW;
+					S.status |= ST_ROPE_OVERFLOW;
 				}
-			} else if (tail_is_chr) {
-				ch[t.ni] = s.best_sub;
+			} else if (S.tail_is_chr) {
+				S.ch[S.t.ni] = s.best_sub;
 			}
-			hash_changelast(hs, draft, s.best_sub, P);
+			hash_changelast(S.hs, draft, s.best_sub, P);
+			S.la_n = 0;
 			break;
 		case 2: {
 			emit(2, fl, draft, s);
 			if (insertion_guard_fires(s)) {
-				return false;
+				S.site_ok = false;
+				return;
 			}
-			rope_insert(t.ni, t.pos, s.indel, s.indel_len);
-			hash_changelast(hs, draft, (unsigned char)s.indel[0], P);
+			rope_insert(S.t.ni, S.t.pos, s.indel, s.indel_len);
+			hash_changelast(S.hs, draft, (unsigned char)s.indel[0], P);
+			S.la_n = 0;
 			break;
 		}
 		case 3:
 			emit(3, fl, draft, s);
-			rope_delete(t.ni, t.pos, s.indel_len);
-			hash_changelast(hs, draft, cchar(t), P);
+			rope_delete(S.t.ni, S.t.pos, s.indel_len);
+			hash_changelast(S.hs, draft, cchar(S.t), P);
+			S.la_n = 0;
 			break;
 		default:
 			// soft-masking only changes the case of the tail char: no effect on the hash (ntedit.cpp:1410-1424)
@@ -831,17 +1275,51 @@ struct Walker
 			}
 			break;
 		}
-		return true;
+	}
+
+	// returns false when the contig is finished (insertion guard fired)
+	NTB_FN bool evaluate_site()
+	{
+		NTB_LEADER_BEGIN
+		site_begin();
+		NTB_LEADER_END
+		if (!P.snv && S.dnf) {
+			return true; // no attempt is possible (ntedit.cpp:1865): the subset counts are not needed
+		}
+		phase_check_and_subs();
+		NTB_LEADER_BEGIN
+		S.next = site_after_check() ? NEXT_CAND : NEXT_STOP;
+		NTB_LEADER_END
+		if (S.next == NEXT_STOP) {
+			return true;
+		}
+		for (uint32_t ci = 0; ci < 4; ci++) {
+			NTB_LEADER_BEGIN
+			site_candidate(ci);
+			NTB_LEADER_END
+			if (S.next == NEXT_STOP) {
+				break;
+			}
+			if (S.next == NEXT_INDELS) {
+				if (try_indels() && (P.mode == 0 || P.mode == 1)) {
+					break;
+				}
+			}
+		}
+		NTB_LEADER_BEGIN
+		site_commit();
+		NTB_LEADER_END
+		return S.site_ok;
 	}
 
 	// ---------------------------------------------------------------- clean-window handling
 	NTB_FN bool window_clean() const
 	{
-		if (h.ni != t.ni || h.ni >= nn || ty[h.ni] != 0 || t.pos - h.pos != P.k - 1) {
+		if (S.h.ni != S.t.ni || S.h.ni >= S.nn || S.ty[S.h.ni] != 0 || S.t.pos - S.h.pos != P.k - 1) {
 			return false;
 		}
-		for (uint32_t i = 0; i < ov_n; i++) {
-			if (ov_pos[i] >= h.pos) {
+		for (uint32_t i = 0; i < S.ov_n; i++) {
+			if (S.ov_pos[i] >= S.h.pos) {
 				return false;
 			}
 		}
@@ -850,61 +1328,99 @@ struct Walker
 
 	NTB_FN void reset_rope(uint32_t head_pos)
 	{
-		ty[0] = 0;
-		ch[0] = 0;
-		sp[0] = head_pos;
-		ep[0] = io.len - 1;
-		nn = 1;
-		h.ni = t.ni = 0;
-		ov_n = 0;
+		S.ty[0] = 0;
+		S.ch[0] = 0;
+		S.sp[0] = head_pos;
+		S.ep[0] = S.io.len - 1;
+		S.nn = 1;
+		S.h.ni = S.t.ni = 0;
+		S.ov_n = 0;
 	}
 
-	// first position >= from whose visit bit is set, or NONE32 when there is none below `limit`
+	// first position >= from whose visit bit is set, or NONE32 when there is none below `limit`.  Every lane inspects one
+	// bitmap word per round; the result is the same in every lane.
 	NTB_FN uint32_t next_visit(uint32_t from, uint32_t limit) const
 	{
 		if (from >= limit) {
 			return NONE32;
 		}
-		uint64_t g = io.goff + from;
-		const uint64_t gend = io.goff + limit;
-		uint64_t w = g >> 5;
-		uint32_t bits = io.visit[w] & (0xFFFFFFFFu << (g & 31));
-		for (;;) {
-			if (bits) {
-#if defined(__CUDA_ARCH__)
-				const uint64_t hit = (w << 5) + (uint32_t)(__ffs((int)bits) - 1);
-#else
-				const uint64_t hit = (w << 5) + (uint32_t)__builtin_ctz(bits);
-#endif
-				return hit < gend ? (uint32_t)(hit - io.goff) : NONE32;
+		const uint64_t g = S.io.goff + from;
+		const uint64_t gend = S.io.goff + limit;
+		for (uint64_t w0 = g >> 5;; w0 += lane_count()) {
+			const uint64_t w = w0 + lane_id();
+			uint32_t bits = (w << 5) < gend ? S.io.visit[w] : 0u;
+			if (w == (g >> 5)) {
+				bits &= 0xFFFFFFFFu << (g & 31);
 			}
-			w++;
-			if ((w << 5) >= gend) {
+#if defined(__CUDA_ARCH__)
+			const uint32_t any = __ballot_sync(0xFFFFFFFFu, bits != 0);
+			if (any) {
+				const int src = __ffs((int)any) - 1;
+				const uint32_t b = __shfl_sync(0xFFFFFFFFu, bits, src);
+				const uint64_t hit = ((w0 + (uint64_t)src) << 5) + (uint32_t)(__ffs((int)b) - 1);
+				return hit < gend ? (uint32_t)(hit - S.io.goff) : NONE32;
+			}
+#else
+			if (bits) {
+				const uint64_t hit = (w << 5) + (uint32_t)__builtin_ctz(bits);
+				return hit < gend ? (uint32_t)(hit - S.io.goff) : NONE32;
+			}
+#endif
+			if (((w0 + lane_count()) << 5) >= gend) {
 				return NONE32;
 			}
-			bits = io.visit[w];
 		}
 	}
 
+	// all lanes: load TEXT_CACHE bytes of contig text starting at `base`
+	NTB_FN void fill_cache(uint32_t base)
+	{
+		warp_sync();
+		for (uint32_t o = lane_id(); o < TEXT_CACHE; o += lane_count()) {
+			const uint64_t pos = (uint64_t)base + o;
+			S.tc[o] = pos < S.io.len ? S.io.text[pos] : (uint8_t)0;
+		}
+		if (lane_id() == 0) {
+			S.tc_base = base;
+			S.tc_n = TEXT_CACHE;
+		}
+		warp_sync();
+	}
+
+	NTB_FN bool cache_covers_window() const
+	{
+		return S.h.pos >= S.tc_base && (uint64_t)S.t.pos + P.k + MAX_DELETIONS + 2 <= (uint64_t)S.tc_base + S.tc_n;
+	}
+
+	// leader: NTMC64 seeding form over the (unedited) window that ends at `tail`, ntedit.cpp:403-416
 	NTB_FN void seed_at(uint32_t tail)
 	{
 		const uint32_t head = tail + 1 - P.k;
-		h.pos = head;
-		t.pos = tail;
-		const unsigned char* base = io.text + head;
-		hash_seed(hs, P.k, [base](unsigned i) { return base[i]; });
-		char_in = io.text[tail];
+		S.h.pos = head;
+		S.t.pos = tail;
+		const Walker* self = this;
+		hash_seed(S.hs, P.k, [self, head](unsigned i) { return self->text_at(head + i); });
+		S.char_in = text_at(tail);
+	}
+
+	NTB_FN unsigned char text_at(uint32_t pos) const
+	{
+		const uint32_t o = pos - S.tc_base;
+		if (o < S.tc_n) {
+			return S.tc[o];
+		}
+		return S.io.text[pos];
 	}
 
 	// findFirstAcceptedKmer, ntedit.cpp:524-545
 	NTB_FN uint32_t first_accepted_kmer() const
 	{
 		const uint32_t k = P.k;
-		for (uint32_t i = 0; (uint64_t)i + k < io.len;) {
-			if (is_accepted_any_case(io.text[i])) {
+		for (uint32_t i = 0; (uint64_t)i + k < S.io.len;) {
+			if (is_accepted_any_case(S.io.text[i])) {
 				bool good = true;
 				for (uint32_t j = i + 1; j < i + k; j++) {
-					if (!is_accepted_any_case(io.text[j])) {
+					if (!is_accepted_any_case(S.io.text[j])) {
 						good = false;
 						i = j + 1;
 						break;
@@ -917,16 +1433,16 @@ struct Walker
 				i++;
 			}
 		}
-		return io.len - 1;
+		return S.io.len - 1;
 	}
 
 	// drop rope nodes that can no longer be reached so that long dirty stretches fit the bounded array
 	NTB_FN void compact()
 	{
-		uint32_t lo = h.ni < t.ni ? h.ni : t.ni;
+		uint32_t lo = S.h.ni < S.t.ni ? S.h.ni : S.t.ni;
 		// keep the run of inserted characters left of the tail (getPrevInsertion walks it) plus one node
-		uint32_t r = t.ni;
-		while (r > 0 && ty[r - 1] == 1) {
+		uint32_t r = S.t.ni;
+		while (r > 0 && S.ty[r - 1] == 1) {
 			r--;
 		}
 		if (r > 0) {
@@ -938,156 +1454,276 @@ struct Walker
 		if (lo == 0) {
 			return;
 		}
-		for (uint32_t i = lo; i < nn; i++) {
+		for (uint32_t i = lo; i < S.nn; i++) {
 			move_node(i - lo, i);
 		}
-		nn -= lo;
-		h.ni -= lo;
-		t.ni -= lo;
+		S.nn -= lo;
+		S.h.ni -= lo;
+		S.t.ni -= lo;
 	}
 
 	// ---------------------------------------------------------------- the main loop, ntedit.cpp:1797-2139
-	NTB_FN void run(const Task& task, TaskResult& res)
+	// leader: start of a task
+	NTB_FN void task_begin(const Task& task)
 	{
 		const uint32_t k = P.k;
-		nn = 0;
-		ov_n = 0;
-		patch_on = false;
+		S.nn = 0;
+		S.ov_n = 0;
 		if (task.flags & TASK_CONTIG_START) {
-			stale_best_sub = stale_alt1 = stale_alt2 = stale_alt3 = 0;
+			S.stale_best_sub = S.stale_alt1 = S.stale_alt2 = S.stale_alt3 = 0;
 		} else {
-			stale_best_sub = STALE_REF | 0;
-			stale_alt1 = STALE_REF | 1;
-			stale_alt2 = STALE_REF | 2;
-			stale_alt3 = STALE_REF | 3;
+			S.stale_best_sub = STALE_REF | 0;
+			S.stale_alt1 = STALE_REF | 1;
+			S.stale_alt2 = STALE_REF | 2;
+			S.stale_alt3 = STALE_REF | 3;
 		}
-		adv = 0;
-		anchored = true;
-		last_event = NONE32;
-		n_events = n_sites = 0;
-		first_touch = NONE32;
-		status = 0;
-		char_in = 0;
-		hs.fh = hs.rh = 0;
-		uint32_t end_pos = io.len;
-		bool need_seed = true;
-		bool alive = true;
-
+		S.adv = 0;
+		S.anchored = true;
+		S.last_event = NONE32;
+		S.n_events = S.n_sites = 0;
+		S.first_touch = NONE32;
+		S.status = 0;
+		S.char_in = 0;
+		S.hs.fh = S.hs.rh = 0;
+		S.end_pos = S.io.len;
+		S.need_seed = true;
+		S.tc_base = 0;
+		S.tc_n = 0;
+		S.la_n = 0;
+		S.la_used = 0;
+		S.la_bits = 0;
+		S.act = ACT_CLEAN;
+		S.h.ni = S.t.ni = 0;
 		if (task.flags & TASK_CONTIG_START) {
 			const uint32_t h0 = first_accepted_kmer();
-			if ((uint64_t)h0 + k - 1 >= io.len) {
-				status |= ST_CONTIG_END;
-				alive = false;
+			if ((uint64_t)h0 + k - 1 >= S.io.len) {
+				S.status |= ST_CONTIG_END;
+				S.act = ACT_STOP;
+				S.h.pos = S.t.pos = 0;
 			} else {
-				h.pos = h0;
-				t.pos = h0 + k - 1;
+				S.h.pos = h0;
+				S.t.pos = h0 + k - 1;
 			}
 		} else {
-			t.pos = task.start;
-			h.pos = task.start + 1 - k;
+			S.t.pos = task.start;
+			S.h.pos = task.start + 1 - k;
 		}
-		if (alive) {
-			reset_rope(h.pos);
+		if (S.act != ACT_STOP) {
+			reset_rope(S.h.pos);
 		}
+	}
 
-		while (alive) {
-			if ((uint64_t)h.pos + k - 1 >= io.len) {
-				status |= ST_CONTIG_END;
-				break;
+	// leader: top of the main loop
+	NTB_FN void loop_head(const Task& task)
+	{
+		if ((uint64_t)S.h.pos + P.k - 1 >= S.io.len) {
+			S.status |= ST_CONTIG_END;
+			S.act = ACT_STOP;
+			return;
+		}
+		if (S.status & (ST_EV_OVERFLOW | ST_ROPE_OVERFLOW)) {
+			S.act = ACT_STOP;
+			return;
+		}
+		if (S.need_seed || window_clean()) {
+			// clean window: forget the local rope and jump to the next position K1 flagged
+			reset_rope(S.h.pos);
+			S.anchored = true;
+			S.la_n = 0;
+			if (S.t.pos >= task.end) {
+				S.end_pos = S.t.pos;
+				S.act = ACT_STOP;
+				return;
 			}
-			if (status & (ST_EV_OVERFLOW | ST_ROPE_OVERFLOW)) {
-				break;
+			S.act = ACT_CLEAN;
+			return;
+		}
+		if (S.nn + 16 > (uint32_t)NCAP) {
+			compact();
+			if (S.nn + 16 > (uint32_t)NCAP) {
+				S.status |= ST_ROPE_OVERFLOW;
+				S.act = ACT_STOP;
+				return;
 			}
-			if (need_seed || window_clean()) {
-				// clean window: forget the local rope and jump to the next position K1 flagged
-				reset_rope(h.pos);
-				anchored = true;
-				if (t.pos >= task.end) {
-					end_pos = t.pos;
-					break;
-				}
-				const uint32_t nv = next_visit(t.pos, task.end);
-				if (nv == NONE32) {
-					end_pos = task.end;
-					break;
-				}
-				if (nv != t.pos || need_seed) {
-					seed_at(nv);
-					reset_rope(h.pos);
-				}
-				need_seed = false;
-			} else if (nn + 16 > (uint32_t)NCAP) {
-				compact();
-				if (nn + 16 > (uint32_t)NCAP) {
-					status |= ST_ROPE_OVERFLOW;
-					break;
-				}
-			}
+		}
+		S.act = ACT_DIRTY;
+	}
 
-			bool site;
-			if (P.snv) {
-				site = true;
-			} else if (P.counting) {
-				const unsigned c = q_count(hs);
-				site = c == 0 || c < P.min_threshold;
+	// leader: move to the next position after the site test (ntedit.cpp:2118-2138)
+	NTB_FN void advance()
+	{
+		const uint32_t k = P.k;
+		if (window_clean()) {
+			// still on unedited text: the next position the reference acts on is the next flagged one
+			// (its own roll / skip-after-N loop, ntedit.cpp:2118-2138, does nothing observable in between)
+			S.h.pos++;
+			S.t.pos++;
+			S.need_seed = true;
+			return;
+		}
+		// advance; after a non-accepted incoming base skip until k further positions were consumed
+		int64_t target = -1;
+		do {
+			unsigned char out = 0, in = S.char_in;
+			if (roll(S.h, S.t, out, in)) {
+				S.char_in = in;
+				S.adv++;
+				S.la_used++;
+				if (!is_accepted_any_case(in)) {
+					target = (int64_t)(int32_t)S.t.pos + (int64_t)(int32_t)k;
+					S.la_n = 0;
+				}
+				hash_roll(S.hs, out, in, P);
 			} else {
-				site = !q_contains(hs);
+				S.status |= ST_CONTIG_END;
+				S.act = ACT_STOP;
+				return;
 			}
-			if (site) {
-				if (!evaluate_site()) {
-					status |= ST_CONTIG_END;
-					break;
-				}
-			}
-
-			if (window_clean()) {
-				// still on unedited text: the next position the reference acts on is the next flagged one
-				// (its own roll / skip-after-N loop, ntedit.cpp:2118-2138, does nothing observable in between)
-				h.pos++;
-				t.pos++;
-				need_seed = true;
-				continue;
-			}
-
-			// advance; after a non-accepted incoming base skip until k further positions were consumed (ntedit.cpp:2118-2138)
-			int64_t target = -1;
-			bool stop = false;
-			do {
-				unsigned char out = 0;
-				if (roll(h, t, out, char_in)) {
-					adv++;
-					if (!is_accepted_any_case(char_in)) {
-						target = (int64_t)(int32_t)t.pos + (int64_t)(int32_t)k;
-					}
-					hash_roll(hs, out, char_in, P);
-				} else {
-					stop = true;
-					break;
-				}
-				if (target >= 0 && (int64_t)(int32_t)t.pos != target && window_clean()) {
-					// skipping over non-accepted bases on unedited text: same shortcut as above
-					h.pos++;
-					t.pos++;
-					need_seed = true;
-					break;
-				}
-			} while (target >= 0 && (int64_t)(int32_t)t.pos != target);
-			if (stop) {
-				status |= ST_CONTIG_END;
+			if (target >= 0 && (int64_t)(int32_t)S.t.pos != target && window_clean()) {
+				// skipping over non-accepted bases on unedited text: same shortcut as above
+				S.h.pos++;
+				S.t.pos++;
+				S.need_seed = true;
 				break;
 			}
+		} while (target >= 0 && (int64_t)(int32_t)S.t.pos != target);
+	}
+
+	// all lanes: site test of the next LOOKAHEAD dirty-window positions in one pass (lane j: j plain rolls ahead)
+	NTB_FN void lookahead()
+	{
+		NTB_LEADER_BEGIN
+		S.tail_is_pos = S.t.ni < S.nn && S.ty[S.t.ni] == 0;
+		S.tail_is_chr = S.t.ni < S.nn && S.ty[S.t.ni] == 1;
+		linearise(LOOKAHEAD - 1, false);
+		S.la_bits = 0;
+		NTB_LEADER_END
+		const uint32_t n = S.n_rolls + 1 < LOOKAHEAD ? S.n_rolls + 1 : LOOKAHEAD;
+		uint32_t bits = 0;
+		for (uint32_t j = lane_id(); j < n; j += lane_count()) {
+			Cand cd;
+			cd.syn = 0;
+			cd.c = 0;
+			cd.d = 0;
+			cd.X = 0;
+			cd.change = 0;
+			cd.patch = 0;
+			cd.kind = CK_SITE;
+			cd.Q = j;
+			cd.pre = j == 0;
+			cd.first = j == 0 ? 0 : j - 1;
+			cd.period = LOOKAHEAD + 1;
+			uint32_t pre_ok = 0, count = 0;
+			eval_cand(cd, pre_ok, count);
+			if (count) {
+				bits |= 1u << j;
+			}
 		}
-		status |= ST_DONE;
-		res.end_pos = (status & ST_CONTIG_END) ? io.len : end_pos;
-		res.first_touch = first_touch;
-		res.last_event = last_event;
-		res.n_events = n_events;
-		res.n_sites = n_sites;
-		res.status = status;
-		res.stale[0] = stale_best_sub;
-		res.stale[1] = stale_alt1;
-		res.stale[2] = stale_alt2;
-		res.stale[3] = stale_alt3;
+#if defined(__CUDA_ARCH__)
+		// lane j holds bit j only
+		for (int o = 16; o > 0; o >>= 1) {
+			bits |= __shfl_xor_sync(0xFFFFFFFFu, bits, o);
+		}
+#endif
+		NTB_LEADER_BEGIN
+		S.la_bits = bits;
+		S.la_n = n;
+		S.la_used = 0;
+		NTB_LEADER_END
+	}
+
+	// Walks one task.  Called by every lane of the warp with the same arguments.
+	NTB_FN void run(const Task& task, TaskResult& res)
+	{
+		NTB_LEADER_BEGIN
+		task_begin(task);
+		NTB_LEADER_END
+		while (S.act != ACT_STOP) {
+			NTB_LEADER_BEGIN
+			loop_head(task);
+			NTB_LEADER_END
+			if (S.act == ACT_STOP) {
+				break;
+			}
+			if (S.act == ACT_CLEAN) {
+				const uint32_t nv = next_visit(S.t.pos, task.end);
+				NTB_LEADER_BEGIN
+				if (nv == NONE32) {
+					S.end_pos = task.end;
+					S.act = ACT_STOP;
+				} else {
+					S.do_seed = nv != S.t.pos || S.need_seed;
+					S.visit_hit = nv;
+					if (S.do_seed) {
+						S.t.pos = nv;
+						S.h.pos = nv + 1 - P.k;
+					}
+					S.need_seed = false;
+				}
+				NTB_LEADER_END
+				if (S.act == ACT_STOP) {
+					break;
+				}
+				if (!cache_covers_window()) {
+					fill_cache(S.h.pos);
+				}
+				NTB_LEADER_BEGIN
+				if (S.do_seed) {
+					seed_at(S.visit_hit);
+					reset_rope(S.h.pos);
+					S.site_now = true; // K1 flagged this very window
+				} else if (P.snv) {
+					S.site_now = true;
+				} else if (P.counting) {
+					S.site_now = is_site_value(q_count(S.hs));
+				} else {
+					S.site_now = !q_contains(S.hs);
+				}
+				NTB_LEADER_END
+			} else {
+				if (!cache_covers_window()) {
+					fill_cache(S.h.pos);
+				}
+				if (P.snv) {
+					NTB_LEADER_BEGIN
+					S.site_now = true;
+					NTB_LEADER_END
+				} else {
+					if (S.la_used >= S.la_n) {
+						lookahead();
+					}
+					NTB_LEADER_BEGIN
+					S.site_now = ((S.la_bits >> S.la_used) & 1u) != 0;
+					NTB_LEADER_END
+				}
+			}
+			if (S.site_now) {
+				if (!evaluate_site()) {
+					NTB_LEADER_BEGIN
+					S.status |= ST_CONTIG_END;
+					S.act = ACT_STOP;
+					NTB_LEADER_END
+					break;
+				}
+			}
+			NTB_LEADER_BEGIN
+			advance();
+			NTB_LEADER_END
+		}
+		NTB_LEADER_BEGIN
+		S.status |= ST_DONE;
+		res.end_pos = (S.status & ST_CONTIG_END) ? S.io.len : S.end_pos;
+		res.first_touch = S.first_touch;
+		res.last_event = S.last_event;
+		res.n_events = S.n_events;
+		res.n_sites = S.n_sites;
+		res.status = S.status;
+		res.stale[0] = S.stale_best_sub;
+		res.stale[1] = S.stale_alt1;
+		res.stale[2] = S.stale_alt2;
+		res.stale[3] = S.stale_alt3;
+		res.kcycles = 0;
+		NTB_LEADER_END
 	}
 };
 

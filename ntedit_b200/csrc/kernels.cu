@@ -323,31 +323,76 @@ launch_scan(const ScanArgs& a, bool counting, bool extra, int grid, cudaStream_t
 
 // ------------------------------------------------------------------------------------------------------------------
 // K2
-__global__ void __launch_bounds__(64)
+// K2: persistent warps, one task (contig segment) per warp at a time, tasks handed out through an atomic counter.
+// The walker state of every warp lives in shared memory (engine.h: WalkerState); lane 0 is the leader.
+__global__ void __launch_bounds__(WALK_THREADS)
 walk_kernel(const uint8_t* text, const uint32_t* visit, FilterView bloom, FilterView rep, const __grid_constant__ KParams kp,
             const Task* tasks, TaskResult* results, uint32_t n_tasks, Event* events, uint32_t ev_cap, Counters* ctr)
 {
-	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-	if (i >= n_tasks) {
-		return;
+	extern __shared__ __align__(16) uint8_t walk_smem[];
+	WalkState* states = reinterpret_cast<WalkState*>(walk_smem);
+	WalkState& S = states[threadIdx.x >> 5];
+	const uint32_t lane = threadIdx.x & 31u;
+	Walker<WALK_NCAP> w(S, kp);
+	for (;;) {
+		uint32_t i = 0;
+		if (lane == 0) {
+			i = atomicAdd(&ctr->next_task, 1u);
+		}
+		i = __shfl_sync(0xFFFFFFFFu, i, 0);
+		if (i >= n_tasks) {
+			break;
+		}
+		const Task task = tasks[i];
+		__syncwarp();
+		if (lane == 0) {
+			S.io.text = text + task.text_off;
+			S.io.len = task.len;
+			S.io.visit = visit;
+			S.io.goff = task.text_off;
+			S.io.bloom = bloom;
+			S.io.rep = rep;
+			S.io.events = events;
+			S.io.ev_cap = ev_cap;
+			S.io.ctr = ctr;
+		}
+		__syncwarp();
+		TaskResult res;
+		const long long c0 = clock64();
+		w.run(task, res);
+		if (lane == 0) {
+			res.kcycles = (uint32_t)((clock64() - c0) >> 10);
+			results[i] = res;
+		}
 	}
-	const Task task = tasks[i];
-	WalkerIO io;
-	io.text = text + task.text_off;
-	io.len = task.len;
-	io.visit = visit;
-	io.goff = task.text_off;
-	io.bloom = bloom;
-	io.rep = rep;
-	io.events = events;
-	io.ev_cap = ev_cap;
-	io.ctr = ctr;
-	Walker<352> w(io, kp);
-	TaskResult res;
-	const long long c0 = clock64();
-	w.run(task, res);
-	res.kcycles = (uint32_t)((clock64() - c0) >> 10);
-	results[i] = res;
+}
+
+cudaError_t
+launch_walk(const uint8_t* text, const uint32_t* visit, const FilterView& bloom, const FilterView& rep, const KParams& kp, const Task* tasks,
+            TaskResult* results, uint32_t n_tasks, Event* events, uint32_t ev_cap, Counters* ctr, int sm_count, cudaStream_t stream)
+{
+	static int blocks_per_sm = 0;
+	const size_t smem = walk_smem_bytes();
+	if (blocks_per_sm == 0) {
+		cudaError_t e = cudaFuncSetAttribute(walk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+		if (e != cudaSuccess) {
+			return e;
+		}
+		int n = 0;
+		e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, walk_kernel, WALK_THREADS, smem);
+		if (e != cudaSuccess) {
+			return e;
+		}
+		blocks_per_sm = n > 0 ? n : 1;
+	}
+	const uint64_t want = ((uint64_t)n_tasks + WALK_WARPS - 1) / WALK_WARPS;
+	const uint64_t cap = (uint64_t)sm_count * (uint64_t)blocks_per_sm;
+	const unsigned grid = (unsigned)(want < cap ? want : cap);
+	if (grid == 0) {
+		return cudaSuccess;
+	}
+	walk_kernel<<<grid, WALK_THREADS, smem, stream>>>(text, visit, bloom, rep, kp, tasks, results, n_tasks, events, ev_cap, ctr);
+	return cudaGetLastError();
 }
 
 // ------------------------------------------------------------------------------------------------------------------

@@ -1,7 +1,8 @@
 // sm_100a kernels of the ntEdit hot path.
 //   K1 scan_kernel    : ntHash roll over every base + h-way filter probe -> visit bitmap (and, on request, counts / validity)
 //                       replaces the main-loop test + roll of ntedit.cpp:1806-1807, 2118-2138
-//   K2 walk_kernel    : one thread per segment replays the edit state machine (engine.h) at the flagged positions
+//   K2 walk_kernel    : one warp per segment replays the edit state machine (engine.h) at the flagged positions, one
+//                       candidate k-mer series per lane
 //                       replaces ntedit.cpp:1808-2116 (check-missing, substitutions, tryIndels, tryDeletion, makeEdit decisions)
 //   K4 occupancy_kernel : popcount / non-zero count of the filter (btllib get_fpr, printed by ntedit.cpp:387-395)
 //   K5 insert_kernel  : filter construction (src/ntedit_make_genome_bf.cpp:151-156)
@@ -50,8 +51,21 @@ struct ScanArgs
 // launches scan_kernel<hash_num, counting, extra> on `grid` persistent CTAs
 cudaError_t launch_scan(const ScanArgs& a, bool counting, bool extra, int grid, cudaStream_t stream);
 
-__global__ void walk_kernel(const uint8_t* text, const uint32_t* visit, FilterView bloom, FilterView rep, const __grid_constant__ KParams kp,
-                            const Task* tasks, TaskResult* results, uint32_t n_tasks, Event* events, uint32_t ev_cap, Counters* ctr);
+// K2 geometry: WALK_WARPS walkers per CTA, each with its own WalkerState in dynamic shared memory
+constexpr int WALK_NCAP = 352;
+constexpr int WALK_WARPS = 8;
+constexpr int WALK_THREADS = WALK_WARPS * 32;
+using WalkState = WalkerState<WALK_NCAP>;
+inline size_t
+walk_smem_bytes()
+{
+	return (size_t)WALK_WARPS * sizeof(WalkState);
+}
+
+// launches walk_kernel on a persistent grid sized from the occupancy of the kernel
+cudaError_t launch_walk(const uint8_t* text, const uint32_t* visit, const FilterView& bloom, const FilterView& rep, const KParams& kp,
+                        const Task* tasks, TaskResult* results, uint32_t n_tasks, Event* events, uint32_t ev_cap, Counters* ctr, int sm_count,
+                        cudaStream_t stream);
 
 __global__ void insert_kernel(const uint8_t* text, uint64_t total, uint8_t* data, FilterView f, const __grid_constant__ KParams kp);
 

@@ -113,6 +113,8 @@ struct Counters
 {
 	uint32_t n_events;   // arena fill
 	uint32_t overflow;
+	uint32_t next_task;  // work queue of the persistent walker warps
+	uint32_t pad_;
 };
 
 } // namespace ntb

@@ -75,9 +75,10 @@ struct HostBackend
 		results.resize(tasks.size());
 		events.assign(1u << 16, Event());
 		for (;;) {
-			Counters ctr = { 0, 0 };
+			Counters ctr = { 0, 0, 0, 0 };
+			WalkerState<352>* st = new WalkerState<352>();
 			for (size_t i = 0; i < tasks.size(); i++) {
-				WalkerIO io;
+				WalkerIO& io = st->io;
 				io.text = bases + tasks[i].text_off;
 				io.len = tasks[i].len;
 				io.visit = visit.data();
@@ -87,10 +88,10 @@ struct HostBackend
 				io.events = events.data();
 				io.ev_cap = (uint32_t)events.size();
 				io.ctr = &ctr;
-				Walker<352>* w = new Walker<352>(io, kp);
-				w->run(tasks[i], results[i]);
-				delete w;
+				Walker<352> w(*st, kp);
+				w.run(tasks[i], results[i]);
 			}
+			delete st;
 			if (!ctr.overflow) {
 				events.resize(ctr.n_events);
 				return NTB_OK;
