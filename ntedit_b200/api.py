@@ -251,6 +251,31 @@ def write_edits(headers, buf, offs, result, params, k, counting):
     return tuple(out)
 
 
+def polish_per_contig(contigs, bloom, params, bloomrep=None):
+    """[(header, seq)] -> one (edited_fa, tsv_rows, vcf_rows) per contig, None for contigs below min_contig_len.
+    The unit the multi-GPU driver (shard.py) merges in input order."""
+    buf, offs = pack_contigs(contigs)
+    res = kmerize_and_correct(buf, offs, bloom, params, bloomrep)
+    L = _l.load()
+    base = buf.ctypes.data
+    out = []
+    for c, (hdr, _) in enumerate(contigs):
+        pol, nodes, nn, srecs, ns = res.contig(c)
+        if not pol:
+            out.append(None)
+            continue
+        fa, tsv, vcf = _l.StrBuf(), _l.StrBuf(), _l.StrBuf()
+        _l.check(L.ntb_format_contig(hdr, C.c_void_p(base + int(offs[c])), nodes, nn, srecs, ns, int(params.snv),
+                                     C.byref(fa), C.byref(tsv), C.byref(vcf)))
+        piece = []
+        for b in (fa, tsv, vcf):
+            piece.append(C.string_at(b.data, b.len) if b.len else b"")
+            L.ntb_strbuf_free(C.byref(b))
+        out.append(tuple(piece))
+    res.free()
+    return out
+
+
 def polish(contigs, bloom, params, bloomrep=None):
     """Convenience: [(header, seq)] -> (edited_fa, changes_tsv, vcf_rows, stats dict)."""
     buf, offs = pack_contigs(contigs)

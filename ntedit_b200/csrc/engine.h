@@ -22,6 +22,8 @@
 #pragma once
 #include "nthash.h"
 
+#include <cstring>
+
 namespace ntb {
 
 #if defined(__CUDACC__)
@@ -59,6 +61,40 @@ warp_sync()
 {
 #if defined(__CUDA_ARCH__)
 	__syncwarp();
+#endif
+}
+
+// smallest value of v over the lanes of the warp
+NTB_FN inline uint32_t
+warp_min(uint32_t v)
+{
+#if defined(__CUDA_ARCH__)
+	return __reduce_min_sync(0xFFFFFFFFu, v);
+#else
+	return v;
+#endif
+}
+
+NTB_FN inline uint64_t
+warp_xor64(uint64_t v)
+{
+#if defined(__CUDA_ARCH__)
+	uint32_t lo = (uint32_t)v, hi = (uint32_t)(v >> 32);
+	lo = __reduce_xor_sync(0xFFFFFFFFu, lo);
+	hi = __reduce_xor_sync(0xFFFFFFFFu, hi);
+	return ((uint64_t)hi << 32) | lo;
+#else
+	return v;
+#endif
+}
+
+NTB_FN inline uint32_t
+warp_or(uint32_t v)
+{
+#if defined(__CUDA_ARCH__)
+	return __reduce_or_sync(0xFFFFFFFFu, v);
+#else
+	return v;
 #endif
 }
 
@@ -111,6 +147,12 @@ struct WalkerIO
 	Counters* ctr;
 };
 
+#if defined(__CUDACC__)
+#define NTB_LANES 32
+#else
+#define NTB_LANES 1
+#endif
+
 constexpr uint32_t MAX_INS_TRIES = 341;   // num_tries[5], ntedit.cpp:172
 constexpr uint32_t MAX_DELETIONS = 10;    // ntedit.cpp:2489-2493
 constexpr int PROBE_G = 10;               // sampled k-mers whose probes are in flight together, per lane
@@ -123,7 +165,7 @@ constexpr uint32_t LOOKAHEAD = 32;        // dirty-window positions whose site t
 // filter after roll `first` and every `period` rolls after it (and, with `pre`, before the first roll)".
 struct Cand
 {
-	uint64_t syn;      // synthetic incoming chars, byte j = j-th
+	uint64_t syn_cls;  // class bytes (cls_of) of the synthetic incoming chars, byte j = j-th
 	uint32_t Q;        // rolls to perform
 	uint32_t c;        // leading synthetic rolls
 	uint32_t d;        // offset into lin_in[] of the first real incoming char
@@ -184,10 +226,20 @@ struct WalkerState
 	// linearised rope: chars the next rolls would push out of / pull into the window (roll(), ntedit.cpp:1216-1247)
 	uint8_t lin_out[KMAX + LOOKAHEAD + 2];
 	uint8_t lin_in[KMAX + LOOKAHEAD + 2];
+	uint8_t lin_out_c[KMAX + LOOKAHEAD + 2]; // class bytes of the same
+	uint8_t lin_in_c[KMAX + LOOKAHEAD + 2];
+	uint64_t seed_tab[8];                    // forward seeds by code (A C G T, none)
+	uint64_t rotk_tab[8];                    // srol^k of the same
+	uint64_t hb[PROBE_G][NTB_LANES];         // sampled k-mer hashes of every lane, waiting to be probed
+	uint32_t pv[PROBE_G][PROBE_HU][NTB_LANES]; // probed filter words (cp.async destinations)
+	uint8_t psh[PROBE_G][PROBE_HU][NTB_LANES]; // bit offset of the probed bit / counter inside the word
+	uint8_t pval[PROBE_G][NTB_LANES];        // filter value of each sampled k-mer
 	uint32_t n_rolls;     // successful simulated rolls
 	uint32_t n_check;     // completed iterations of the check-missing loop
 	uint32_t patch_idx;   // index into lin_out[] that reads the tail's own slot
 	bool dnf;             // do_not_fix
+	bool lin_simple;      // the window sits on one position node that runs to the end of the contig
+	bool jumped;          // the dirty run after an edit was skipped in one step
 	unsigned char raw, draft;
 	uint32_t cands;       // substitution candidates, packed
 	bool tail_is_pos, tail_is_chr, touched;
@@ -209,7 +261,7 @@ struct WalkerState
 	char tb_indel[8];
 	bool ti_done, ti_ret;
 	// dirty-window lookahead: bit j = the main loop would enter its edit block after j more plain rolls
-	uint32_t la_bits, la_n, la_used;
+	uint32_t la_bits, la_n, la_used, la_J;
 };
 
 constexpr uint32_t ACT_STOP = 0, ACT_CLEAN = 1, ACT_DIRTY = 2;
@@ -326,7 +378,7 @@ struct Walker
 	}
 
 	// makeInsertion, ntedit.cpp:625-714
-	NTB_FN void rope_insert(uint32_t& t_ni, uint32_t insert_pos, const char* bases, uint32_t nb)
+	NTB_FN_NOINLINE void rope_insert(uint32_t& t_ni, uint32_t insert_pos, const char* bases, uint32_t nb)
 	{
 		const int8_t otype = S.ty[t_ni];
 		const uint32_t os = S.sp[t_ni], oe = S.ep[t_ni];
@@ -367,7 +419,7 @@ struct Walker
 	}
 
 	// makeDeletion, ntedit.cpp:719-809 (the recursion of the reference is a loop here)
-	NTB_FN void rope_delete(uint32_t& t_ni, uint32_t& pos, uint32_t num_del)
+	NTB_FN_NOINLINE void rope_delete(uint32_t& t_ni, uint32_t& pos, uint32_t num_del)
 	{
 		for (;;) {
 			const int8_t otype = S.ty[t_ni];
@@ -453,43 +505,80 @@ struct Walker
 	}
 
 	// ---------------------------------------------------------------- probing a group of sampled k-mers
-	// val[g] = value of k-mer hb[g] in filter F for every g whose bit is set in `valid`.  All loads of a pass are
-	// issued before any is consumed.
-	NTB_FN void probe_group(const FilterView& F, const uint64_t (&hb)[PROBE_G], uint32_t valid, uint32_t (&val)[PROBE_G]) const
+	// class byte of a base: bits 0-2 code of the forward seed, bits 3-5 code of the reverse-strand seed (btllib's
+	// SEED_TAB[c & 7] path); code 4 = no seed
+	NTB_FN static uint8_t cls_of(unsigned char c) { return (uint8_t)(base_code(c) | (rev_code(c) << 3)); }
+
+	// NTMC64 rolling form (ntedit.cpp:418-432) on class bytes, seeds from the per-warp tables
+	NTB_FN void roll_cls(HashState& s, uint32_t co, uint32_t ci) const
 	{
-#pragma unroll
-		for (int g = 0; g < PROBE_G; g++) {
-			val[g] = F.counting ? 255u : 1u;
-		}
-		for (uint32_t i0 = 0; i0 < F.hash_num; i0 += PROBE_HU) {
-			uint32_t got[PROBE_G][PROBE_HU];
-			uint32_t sh[PROBE_G];
-#pragma unroll
-			for (int g = 0; g < PROBE_G; g++) {
-				sh[g] = 0;
-#pragma unroll
-				for (int u = 0; u < PROBE_HU; u++) {
-					got[g][u] = F.counting ? 255u : 0xFFu;
-					if (((valid >> g) & 1u) && i0 + u < F.hash_num) {
-						const uint64_t slot = filter_slot(F, hash_extend(hb[g], P.k, i0 + u));
-						if (F.counting) {
-							got[g][u] = probe_byte(F.data + slot);
-						} else {
-							sh[g] |= ((uint32_t)slot & 7u) << (3 * u);
-							got[g][u] = probe_byte(F.data + (slot >> 3));
-						}
-					}
-				}
+		s.fh = srol1(s.fh) ^ S.seed_tab[ci & 7u] ^ S.rotk_tab[co & 7u];
+		s.rh = sror1(s.rh ^ S.rotk_tab[(ci >> 3) & 7u] ^ S.seed_tab[(co >> 3) & 7u]);
+	}
+
+	// Issues the probes of the first `ng` sampled k-mers of this lane (S.hb[g][lane], only those whose bit is set in
+	// `want`) for hash functions [i0, i0 + PROBE_HU) of filter F.  On the device every probe is an asynchronous 4-byte copy
+	// of the aligned filter word into the lane's slot of S.pv (cp.async: no register is tied up while the load is in
+	// flight, so all ng x PROBE_HU loads of a lane overlap without unrolling anything); S.psh keeps the bit offset of the
+	// probed byte / bit inside that word.
+	NTB_FN void probe_issue(const FilterView& F, uint32_t ng, uint32_t want, uint32_t i0)
+	{
+		const uint32_t ln = lane_id();
+		const uint32_t hn = F.hash_num - i0 < (uint32_t)PROBE_HU ? F.hash_num - i0 : (uint32_t)PROBE_HU;
+		for (uint32_t g = 0; g < ng; g++) {
+			if (!((want >> g) & 1u)) {
+				continue;
 			}
-#pragma unroll
-			for (int g = 0; g < PROBE_G; g++) {
-#pragma unroll
-				for (int u = 0; u < PROBE_HU; u++) {
-					if (F.counting) {
-						val[g] = got[g][u] < val[g] ? got[g][u] : val[g];
-					} else {
-						val[g] &= got[g][u] >> ((sh[g] >> (3 * u)) & 7u);
-					}
+			const uint64_t hb = S.hb[g][ln];
+			for (uint32_t u = 0; u < hn; u++) {
+				const uint64_t slot = filter_slot(F, hash_extend(hb, P.k, i0 + u));
+				const uint64_t byte = F.counting ? slot : slot >> 3;
+				S.psh[g][u][ln] = (uint8_t)(((uint32_t)byte & 3u) * 8u + (F.counting ? 0u : ((uint32_t)slot & 7u)));
+				const uint8_t* src = F.data + (byte & ~3ULL);
+#if defined(__CUDA_ARCH__)
+				const uint32_t dst = (uint32_t)__cvta_generic_to_shared(&S.pv[g][u][ln]);
+				asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+#else
+				uint32_t w;
+				std::memcpy(&w, src, 4);
+				S.pv[g][u][ln] = w;
+#endif
+			}
+		}
+#if defined(__CUDA_ARCH__)
+		asm volatile("cp.async.commit_group;" ::: "memory");
+		asm volatile("cp.async.wait_group 0;" ::: "memory");
+#endif
+	}
+
+	// value of sampled k-mer g after probe_issue(F, .., i0): folds hash functions [i0, i0 + PROBE_HU) into `val`
+	// (bit filter: AND of the probed bits; counting filter: min of the probed counters)
+	NTB_FN uint32_t probe_fold(const FilterView& F, uint32_t g, uint32_t i0, uint32_t val) const
+	{
+		const uint32_t ln = lane_id();
+		const uint32_t hn = F.hash_num - i0 < (uint32_t)PROBE_HU ? F.hash_num - i0 : (uint32_t)PROBE_HU;
+		for (uint32_t u = 0; u < hn; u++) {
+			const uint32_t w = S.pv[g][u][ln] >> S.psh[g][u][ln];
+			if (F.counting) {
+				const uint32_t c = w & 0xFFu;
+				val = c < val ? c : val;
+			} else {
+				val &= w;
+			}
+		}
+		return val;
+	}
+
+	// values of the first ng sampled k-mers of this lane in filter F -> S.pval[g][lane] (only those in `want`)
+	NTB_FN_NOINLINE void probe_values(const FilterView& F, uint32_t ng, uint32_t want)
+	{
+		const uint32_t ln = lane_id();
+		for (uint32_t i0 = 0; i0 < F.hash_num; i0 += PROBE_HU) {
+			probe_issue(F, ng, want, i0);
+			for (uint32_t g = 0; g < ng; g++) {
+				if ((want >> g) & 1u) {
+					const uint32_t start = i0 == 0 ? (F.counting ? 255u : 1u) : (uint32_t)S.pval[g][ln];
+					S.pval[g][ln] = (uint8_t)probe_fold(F, g, i0, start);
 				}
 			}
 		}
@@ -505,83 +594,74 @@ struct Walker
 		if (cd.change) {
 			hash_changelast(s, S.draft, cd.X, P);
 		}
+		const uint32_t ln = lane_id();
+		const uint32_t Q = cd.Q, nsyn = cd.c, d = cd.d, period = cd.period, kind = cd.kind;
+		const uint64_t syn_cls = cd.syn_cls;
 		uint32_t r = 0, jc = cd.first, nchk = 0;
 		bool pre = cd.pre != 0;
 		const uint32_t n_rolls = S.n_rolls;
 		const uint32_t patch_idx = cd.patch ? S.patch_idx : NONE32;
+		const uint32_t x_cls = cls_of(cd.X);
 		pre_ok = 0;
 		count = 0;
-		while (pre || r < cd.Q) {
-			uint64_t hb[PROBE_G];
-			uint32_t valid = 0, premask = 0;
-#pragma unroll
-			for (int g = 0; g < PROBE_G; g++) {
-				hb[g] = 0;
-				if (pre) {
-					hb[g] = hash_canonical(s);
-					valid |= 1u << g;
-					premask = 1u << g;
-					pre = false;
+		while (pre || r < Q) {
+			// collect up to PROBE_G sampled k-mers
+			uint32_t ng = 0, premask = 0;
+			if (pre) {
+				S.hb[0][ln] = hash_canonical(s);
+				ng = 1;
+				premask = 1;
+				pre = false;
+			}
+			while (r < Q && ng < (uint32_t)PROBE_G) {
+				uint32_t ci;
+				if (r < nsyn) {
+					ci = (uint32_t)(syn_cls >> (8 * r)) & 0xFFu;
 				} else {
-					while (r < cd.Q) {
-						unsigned char in;
-						if (r < cd.c) {
-							in = (unsigned char)((cd.syn >> (8 * r)) & 0xFF);
-						} else {
-							const uint32_t j = cd.d + r - cd.c;
-							if (j >= n_rolls) {
-								r = cd.Q; // this roll and every later one fails (ntedit.cpp:1216-1247): nothing more is counted
-								break;
-							}
-							in = S.lin_in[j];
-						}
-						const unsigned char out = r == patch_idx ? cd.X : S.lin_out[r];
-						hash_roll(s, out, in, P);
-						const bool samp = jc == 0;
-						jc = samp ? cd.period - 1 : jc - 1;
-						r++;
-						if (samp) {
-							hb[g] = hash_canonical(s);
-							valid |= 1u << g;
-							break;
-						}
+					const uint32_t j = d + r - nsyn;
+					if (j >= n_rolls) {
+						r = Q; // this roll and every later one fails (ntedit.cpp:1216-1247): nothing more is counted
+						break;
 					}
+					ci = S.lin_in_c[j];
+				}
+				const uint32_t co = r == patch_idx ? x_cls : S.lin_out_c[r];
+				roll_cls(s, co, ci);
+				const bool samp = jc == 0;
+				jc = samp ? period - 1 : jc - 1;
+				r++;
+				if (samp) {
+					S.hb[ng][ln] = hash_canonical(s);
+					ng++;
 				}
 			}
-			if (!valid) {
+			if (ng == 0) {
 				break;
 			}
-			uint32_t val[PROBE_G];
-			probe_group(S.io.bloom, hb, valid, val);
-			if (cd.kind == CK_CHECK) {
-#pragma unroll
-				for (int g = 0; g < PROBE_G; g++) {
-					if ((valid >> g) & 1u) {
-						S.chk[nchk++] = (uint8_t)val[g];
-					}
+			const uint32_t valid = (1u << ng) - 1u;
+			probe_values(S.io.bloom, ng, valid);
+			if (kind == CK_CHECK) {
+				for (uint32_t g = 0; g < ng; g++) {
+					S.chk[nchk++] = S.pval[g][ln];
 				}
-			} else if (cd.kind == CK_SITE) {
-#pragma unroll
-				for (int g = 0; g < PROBE_G; g++) {
-					if (((valid >> g) & 1u) && is_site_value(val[g])) {
+			} else if (kind == CK_SITE) {
+				for (uint32_t g = 0; g < ng; g++) {
+					if (is_site_value(S.pval[g][ln])) {
 						count = 1;
 					}
 				}
 			} else {
 				uint32_t solid = 0;
-#pragma unroll
-				for (int g = 0; g < PROBE_G; g++) {
-					if (((valid >> g) & 1u) && solid_value(val[g])) {
+				for (uint32_t g = 0; g < ng; g++) {
+					if (solid_value(S.pval[g][ln])) {
 						solid |= 1u << g;
 					}
 				}
 				if (P.h_rep && solid) {
 					// secondary filter (-e): a k-mer found there is not solid, ntedit.cpp:467-468
-					uint32_t rv[PROBE_G];
-					probe_group(S.io.rep, hb, solid, rv);
-#pragma unroll
-					for (int g = 0; g < PROBE_G; g++) {
-						if (((solid >> g) & 1u) && rv[g] != 0) {
+					probe_values(S.io.rep, ng, solid);
+					for (uint32_t g = 0; g < ng; g++) {
+						if (((solid >> g) & 1u) && S.pval[g][ln] != 0) {
 							solid &= ~(1u << g);
 						}
 					}
@@ -596,13 +676,13 @@ struct Walker
 #endif
 			}
 		}
-		if (cd.kind == CK_CHECK) {
+		if (kind == CK_CHECK) {
 			S.chk_n = nchk;
 		}
 	}
 
 	// ---------------------------------------------------------------- events (leader)
-	NTB_FN void emit(uint8_t kind, uint8_t flags, uint8_t draft, const Site& s)
+	NTB_FN_NOINLINE void emit(uint8_t kind, uint8_t flags, uint8_t draft, const Site& s)
 	{
 		uint32_t idx;
 #if defined(__CUDA_ARCH__)
@@ -761,48 +841,71 @@ struct Walker
 #undef NTB_PACK
 	}
 
-	// ---------------------------------------------------------------- linearisation of the rope around the window (leader)
+	// ---------------------------------------------------------------- linearisation of the rope around the window
 	// Simulates up to `want` calls of roll() from the current cursors without hashing: lin_out[m] / lin_in[m] are the chars
 	// the (m+1)-th roll pushes out / pulls in, n_rolls the number of rolls that succeed.  With `check` it also replays the
 	// control flow of the check-missing loop (ntedit.cpp:1826-1858): n_check iterations complete, dnf = do_not_fix.
+	// Called by every lane.  When the window sits on a single position node that runs to the end of the contig the chars
+	// are plain text (plus in-place substitutions) and the lanes fetch them in parallel; otherwise the leader walks the rope.
 	NTB_FN void linearise(uint32_t want, bool check)
 	{
 		const uint32_t k = P.k;
+		NTB_LEADER_BEGIN
+		S.tail_is_pos = S.t.ni < S.nn && S.ty[S.t.ni] == 0;
+		S.tail_is_chr = S.t.ni < S.nn && S.ty[S.t.ni] == 1;
 		S.patch_idx = NONE32;
 		S.n_rolls = 0;
 		if (check) {
 			S.n_check = 0;
 			S.dnf = false;
 		}
-		bool check_open = check;
-		const bool simple = S.nn == 1 && S.ty[0] == 0 && S.h.ni == 0 && S.t.ni == 0 && S.ov_n == 0 && S.t.pos - S.h.pos == k - 1 &&
-		                    S.ep[0] == S.io.len - 1 && S.t.pos < S.io.len;
-		if (simple) {
-			// clean window on a single position node: plain text
+		S.lin_simple = S.nn == 1 && S.ty[0] == 0 && S.h.ni == 0 && S.t.ni == 0 && S.t.pos - S.h.pos == k - 1 &&
+		               S.ep[0] == S.io.len - 1 && S.t.pos < S.io.len && S.sp[0] <= S.h.pos;
+		if (S.lin_simple) {
 			const uint32_t avail = S.io.len - 1 - S.t.pos;
-			const uint32_t n = avail < want ? avail : want;
-			for (uint32_t m = 0; m < n; m++) {
-				S.lin_out[m] = rd(S.h.pos + m);
-				S.lin_in[m] = rd(S.t.pos + 1 + m);
-			}
-			S.n_rolls = n;
+			S.n_rolls = avail < want ? avail : want;
 			S.patch_idx = k - 1;
-			if (check) {
-				uint32_t q = 0;
-				for (; q < k; q++) {
-					if (q >= n) { // roll fails at the end of the contig
-						S.dnf = true;
-						break;
-					}
-					if (!is_accepted_any_case(S.lin_in[q])) {
-						S.dnf = true;
-						break;
-					}
-				}
-				S.n_check = q;
-			}
+		} else {
+			linearise_rope(want, check);
+		}
+		NTB_LEADER_END
+		if (!S.lin_simple) {
 			return;
 		}
+		const uint32_t n = S.n_rolls;
+		uint32_t bad = k; // first iteration of the check loop that does not complete
+		for (uint32_t m0 = 0; m0 < n || (check && m0 < k); m0 += lane_count()) {
+			const uint32_t m = m0 + lane_id();
+			if (m < n) {
+				const unsigned char in = rd(S.t.pos + 1 + m);
+				const unsigned char out = rd(S.h.pos + m);
+				S.lin_out[m] = out;
+				S.lin_in[m] = in;
+				S.lin_out_c[m] = cls_of(out);
+				S.lin_in_c[m] = cls_of(in);
+				if (m < k && !is_accepted_any_case(in) && m < bad) {
+					bad = m;
+				}
+			} else if (m < k && m < bad) {
+				bad = m; // roll fails at the end of the contig
+			}
+		}
+		if (check) {
+			bad = warp_min(bad);
+			NTB_LEADER_BEGIN
+			S.n_check = bad;
+			S.dnf = bad < k;
+			NTB_LEADER_END
+		} else {
+			warp_sync();
+		}
+	}
+
+	// leader: the general case of linearise()
+	NTB_FN_NOINLINE void linearise_rope(uint32_t want, bool check)
+	{
+		const uint32_t k = P.k;
+		bool check_open = check;
 		Cursor hh = S.h, tt = S.t;
 		for (uint32_t m = 0; m < want; m++) {
 			if (check_open && m >= k) {
@@ -840,6 +943,8 @@ struct Walker
 			const unsigned char in = cchar(tt);
 			S.lin_out[m] = out;
 			S.lin_in[m] = in;
+			S.lin_out_c[m] = cls_of(out);
+			S.lin_in_c[m] = cls_of(in);
 			S.n_rolls = m + 1;
 			if (check_open) {
 				if (!is_accepted_any_case(in)) {
@@ -860,7 +965,7 @@ struct Walker
 		warp_sync();
 		for (uint32_t j = lane_id(); j < njobs; j += lane_count()) {
 			Cand cd;
-			cd.syn = 0;
+			cd.syn_cls = 0;
 			cd.c = 0;
 			cd.d = 0;
 			cd.first = 0;
@@ -918,7 +1023,11 @@ struct Walker
 				uint64_t packed;
 				const uint32_t len = indel_string(S.index_char, i, packed);
 				cd.X = S.index_char;
-				cd.syn = (packed >> 8) | ((uint64_t)S.draft << (8 * (len - 1)));
+				uint64_t sc = 0;
+				for (uint32_t q = 1; q < len; q++) {
+					sc |= (uint64_t)cls_of((unsigned char)((packed >> (8 * q)) & 0xFF)) << (8 * (q - 1));
+				}
+				cd.syn_cls = sc | ((uint64_t)cls_of(S.draft) << (8 * (len - 1)));
 				cd.c = len;
 				cd.d = 0;
 				cd.pre = 0;
@@ -930,7 +1039,7 @@ struct Walker
 				// tryDeletion, ntedit.cpp:1451-1545
 				const uint32_t n = S.ti_nd0 + (j - n_ins);
 				cd.X = n >= 1 && n - 1 < S.n_rolls ? S.lin_in[n - 1] : 0;
-				cd.syn = 0;
+				cd.syn_cls = 0;
 				cd.c = 0;
 				cd.d = n;
 				cd.pre = 1;
@@ -1065,9 +1174,6 @@ struct Walker
 		if (S.first_touch == NONE32) {
 			S.first_touch = S.t.pos;
 		}
-		S.tail_is_pos = S.t.ni < S.nn && S.ty[S.t.ni] == 0;
-		S.tail_is_chr = S.t.ni < S.nn && S.ty[S.t.ni] == 1;
-		linearise(P.k + MAX_DELETIONS + 1, true);
 		S.cands = candidates(S.draft);
 		S.site_ok = true;
 		S.chk_n = 0;
@@ -1283,6 +1389,7 @@ struct Walker
 		NTB_LEADER_BEGIN
 		site_begin();
 		NTB_LEADER_END
+		linearise(P.k + MAX_DELETIONS + 1, true);
 		if (!P.snv && S.dnf) {
 			return true; // no attempt is possible (ntedit.cpp:1865): the subset counts are not needed
 		}
@@ -1413,7 +1520,7 @@ struct Walker
 	}
 
 	// findFirstAcceptedKmer, ntedit.cpp:524-545
-	NTB_FN uint32_t first_accepted_kmer() const
+	NTB_FN_NOINLINE uint32_t first_accepted_kmer() const
 	{
 		const uint32_t k = P.k;
 		for (uint32_t i = 0; (uint64_t)i + k < S.io.len;) {
@@ -1437,7 +1544,7 @@ struct Walker
 	}
 
 	// drop rope nodes that can no longer be reached so that long dirty stretches fit the bounded array
-	NTB_FN void compact()
+	NTB_FN_NOINLINE void compact()
 	{
 		uint32_t lo = S.h.ni < S.t.ni ? S.h.ni : S.t.ni;
 		// keep the run of inserted characters left of the tail (getPrevInsertion walks it) plus one node
@@ -1494,6 +1601,10 @@ struct Walker
 		S.la_bits = 0;
 		S.act = ACT_CLEAN;
 		S.h.ni = S.t.ni = 0;
+		for (unsigned c = 0; c < 8; c++) {
+			S.seed_tab[c] = c < 4 ? seed_of_code(c) : 0;
+			S.rotk_tab[c] = c < 4 ? P.seed_rot_k[c] : 0;
+		}
 		if (task.flags & TASK_CONTIG_START) {
 			const uint32_t h0 = first_accepted_kmer();
 			if ((uint64_t)h0 + k - 1 >= S.io.len) {
@@ -1592,17 +1703,12 @@ struct Walker
 	// all lanes: site test of the next LOOKAHEAD dirty-window positions in one pass (lane j: j plain rolls ahead)
 	NTB_FN void lookahead()
 	{
-		NTB_LEADER_BEGIN
-		S.tail_is_pos = S.t.ni < S.nn && S.ty[S.t.ni] == 0;
-		S.tail_is_chr = S.t.ni < S.nn && S.ty[S.t.ni] == 1;
 		linearise(LOOKAHEAD - 1, false);
-		S.la_bits = 0;
-		NTB_LEADER_END
 		const uint32_t n = S.n_rolls + 1 < LOOKAHEAD ? S.n_rolls + 1 : LOOKAHEAD;
 		uint32_t bits = 0;
 		for (uint32_t j = lane_id(); j < n; j += lane_count()) {
 			Cand cd;
-			cd.syn = 0;
+			cd.syn_cls = 0;
 			cd.c = 0;
 			cd.d = 0;
 			cd.X = 0;
@@ -1619,16 +1725,42 @@ struct Walker
 				bits |= 1u << j;
 			}
 		}
-#if defined(__CUDA_ARCH__)
-		// lane j holds bit j only
-		for (int o = 16; o > 0; o >>= 1) {
-			bits |= __shfl_xor_sync(0xFFFFFFFFu, bits, o);
+		bits = warp_or(bits); // lane j holds bit j only
+		// Can the whole dirty run be skipped?  With only in-place substitutions in the window, it is clean again after
+		// J = (last substituted position - head + 1) rolls.  When none of the J dirty windows is a site and every incoming
+		// base is accepted, rolling through them one by one (ntedit.cpp:2118-2138) has no observable effect: jump.
+		NTB_LEADER_BEGIN
+		uint32_t J = 0;
+		if (S.lin_simple) {
+			for (uint32_t i = 0; i < S.ov_n; i++) {
+				if (S.ov_pos[i] >= S.h.pos && S.ov_pos[i] - S.h.pos + 1 > J) {
+					J = S.ov_pos[i] - S.h.pos + 1;
+				}
+			}
 		}
-#endif
+		S.la_J = (J >= 1 && J <= n && J <= S.n_rolls && J <= 32) ? J : 0;
+		NTB_LEADER_END
+		const uint32_t J = S.la_J;
+		uint32_t blocked = J == 0 ? 1u : 0u;
+		for (uint32_t m = lane_id(); m < J; m += lane_count()) {
+			if (!is_accepted_any_case(S.lin_in[m])) {
+				blocked = 1;
+			}
+		}
+		blocked = warp_or(blocked);
 		NTB_LEADER_BEGIN
 		S.la_bits = bits;
 		S.la_n = n;
 		S.la_used = 0;
+		S.jumped = false;
+		if (!blocked && (bits & (J >= 32 ? 0xFFFFFFFFu : ((1u << J) - 1u))) == 0) {
+			S.h.pos += J;
+			S.t.pos += J;
+			S.adv += J;
+			S.need_seed = true; // the window is clean: the hash is re-seeded at the next flagged position
+			S.la_n = 0;
+			S.jumped = true;
+		}
 		NTB_LEADER_END
 	}
 
@@ -1691,6 +1823,9 @@ struct Walker
 				} else {
 					if (S.la_used >= S.la_n) {
 						lookahead();
+						if (S.jumped) {
+							continue; // now on a clean window: back to the top of the main loop
+						}
 					}
 					NTB_LEADER_BEGIN
 					S.site_now = ((S.la_bits >> S.la_used) & 1u) != 0;

@@ -1,0 +1,81 @@
+"""CPU tests of the host logic around the kernels: the engine header the CUDA walker instantiates (engine.h, compiled
+for the host as a one-lane warp by tests/hostsim), the segment stitcher, the rope replay and the writer -- against the
+golden fixtures of the unmodified reference and against the oracle on seeded inputs."""
+import numpy as np
+import pytest
+
+from ntedit_b200 import synth
+from tests import cases as tc
+from tests import golden_util as gu
+from tests.hostsim import pyhostsim as hs
+
+
+def run_hostsim(contigs, filt, params_kw, rep=None, segment_len=0):
+    params = hs.default_params(segment_len=segment_len, **params_kw)
+    repa = (rep.data().tobytes(), rep.h, rep.counting) if rep else None
+    return hs.polish(contigs, filt.data().tobytes(), filt.k, filt.h, filt.counting, params, rep=repa)
+
+
+@pytest.mark.parametrize("segment_len", [0, 150])
+@pytest.mark.parametrize("name", gu.names())
+def test_host_engine_reproduces_reference_golden(oracle, name, segment_len):
+    g = gu.load(name)
+    filt = oracle.OracleFilter.load(g["filter_path"])
+    rep = oracle.OracleFilter.load(g["rep_path"]) if g["rep_path"] else None
+    fa, tsv, vcf, st = run_hostsim(g["contigs"], filt, g["case"]["params"], rep=rep, segment_len=segment_len)
+    assert fa == g["fa"]
+    assert tsv == g["tsv"]
+    assert vcf == g["vcf"]
+    filt.free()
+    if rep:
+        rep.free()
+
+
+@pytest.mark.parametrize("case", tc.CASES, ids=[c["name"] for c in tc.CASES])
+def test_host_engine_matches_oracle(oracle, case):
+    inp = tc.make_inputs(500 + tc.CASES.index(case), **dict(case.get("g", {}), n=min(case.get("g", {}).get("n", 9000), 9000)))
+    filt, rep = tc.oracle_filters(oracle, inp)
+    op = oracle.default_params(inp["k"], inp["h"], **tc.oracle_param_overrides(case["p"]))
+    if rep:
+        op.secbf = 1
+    ofa, otsv, ovcf = oracle.polish(inp["contigs"], filt, op, bloomrep=rep,
+                                    min_contig_len=case["p"].get("min_contig_len", 100))
+    for seg in (0, 130):
+        fa, tsv, vcf, st = run_hostsim(inp["contigs"], filt, case["p"], rep=rep, segment_len=seg)
+        assert fa == ofa and tsv == otsv and vcf == ovcf
+    filt.free()
+    if rep:
+        rep.free()
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_neighbouring_errors_at_every_distance(oracle, mode):
+    """Two draft errors d bases apart, d = 1..70 (k = 25): the dirty-window paths of the walker (look-ahead, the jump over
+    a dirty run, indel ropes) against the oracle.  Kinds: substitution, 1-3 base deletion from / insertion into the draft."""
+    rng = np.random.default_rng(17 + mode)
+    k, h = 25, 3
+    truth = synth.random_genome(1600, rng)
+    filt = oracle.OracleFilter.new(1 << 16, k, h, False)
+    filt.insert_seq(truth.tobytes())
+    op = oracle.default_params(k, h, mode=mode)
+
+    def apply(seq, pos, kind):
+        if kind == 0:
+            alt = b"ACGT"[(b"ACGT".index(seq[pos]) + 1) % 4]
+            return seq[:pos] + bytes([alt]) + seq[pos + 1:]
+        if kind in (1, 2):
+            return seq[:pos] + seq[pos + kind:]
+        return seq[:pos] + b"GATTACA"[: kind - 2] + seq[pos:]
+
+    contigs = []
+    for d in range(1, 71):
+        for kinds in ((0, 0), (0, 1), (3, 0), (2, 4), (5, 0)):
+            s = truth.tobytes()
+            s = apply(s, 800 + d, kinds[1])
+            s = apply(s, 800, kinds[0])
+            contigs.append((b"d%d_%d%d" % (d, kinds[0], kinds[1]), s))
+    ofa, otsv, ovcf = oracle.polish(contigs, filt, op)
+    fa, tsv, vcf, st = run_hostsim(contigs, filt, dict(mode=mode))
+    assert fa == ofa and tsv == otsv and vcf == ovcf
+    assert st.edits > 300
+    filt.free()
