@@ -160,6 +160,7 @@ struct CudaBackend
 	cudaStream_t stream = 0;
 	uint32_t* d_visit = nullptr;
 	Task* d_tasks = nullptr;
+	uint32_t* d_order = nullptr;
 	TaskResult* d_results = nullptr;
 	Event* d_events = nullptr;
 	Counters* d_ctr = nullptr;
@@ -201,6 +202,7 @@ struct CudaBackend
 	{
 		cudaFree(d_visit);
 		cudaFree(d_tasks);
+		cudaFree(d_order);
 		cudaFree(d_results);
 		cudaFree(d_events);
 		cudaFree(d_ctr);
@@ -263,8 +265,11 @@ struct CudaBackend
 		if (n > cap_tasks) {
 			cudaFree(d_tasks);
 			cudaFree(d_results);
+			cudaFree(d_order);
 			d_tasks = nullptr;
 			d_results = nullptr;
+			d_order = nullptr;
+			NTB_BE(cudaMalloc((void**)&d_order, n * sizeof(uint32_t)));
 			NTB_BE(cudaMalloc((void**)&d_tasks, n * sizeof(Task)));
 			NTB_BE(cudaMalloc((void**)&d_results, n * sizeof(TaskResult)));
 			cap_tasks = n;
@@ -285,9 +290,9 @@ struct CudaBackend
 		for (;;) {
 			NTB_BE(cudaMemsetAsync(d_ctr, 0, sizeof(Counters), stream));
 			NTB_BE(cudaEventRecord(ev0, stream));
-			NTB_BE(launch_walk(batch->d_text, d_visit, fb, fr, kp, d_tasks, d_results, (uint32_t)n, d_events,
+			NTB_BE(launch_walk(batch->d_text, d_visit, fb, fr, kp, d_tasks, d_order, d_results, (uint32_t)n, d_events,
 			                   (uint32_t)std::min<size_t>(cap_events, 0xFFFFFFF0u), d_ctr, sm_count(batch->device), stream));
-			launches++;
+			launches += 2; // order_tasks_kernel + walk_kernel
 			NTB_BE(cudaEventRecord(ev1, stream));
 			Counters ctr;
 			NTB_BE(cudaMemcpyAsync(&ctr, d_ctr, sizeof ctr, cudaMemcpyDeviceToHost, stream));
@@ -326,6 +331,23 @@ struct CudaBackend
 					tot += results[i].kcycles;
 				}
 				std::fprintf(stderr, "[ntb] walk launch: %zu tasks, %.2f ms, sum %.1f Mcycles\n", n, ms_walk, tot / 1024.0);
+				{
+					// cycles by number of sites in the task
+					const unsigned edges[7] = { 0, 1, 4, 8, 16, 32, 1u << 30 };
+					for (int b = 0; b < 6; b++) {
+						unsigned long long cyc = 0, cnt = 0, sites = 0, evs = 0;
+						for (size_t i = 0; i < n; i++) {
+							if (results[i].n_sites >= edges[b] && results[i].n_sites < edges[b + 1]) {
+								cyc += results[i].kcycles;
+								cnt++;
+								sites += results[i].n_sites;
+								evs += results[i].n_events;
+							}
+						}
+						std::fprintf(stderr, "[ntb]   sites in [%u,%u): %llu tasks, %llu sites, %llu events, %.1f Mcycles\n", edges[b], edges[b + 1], cnt,
+						             sites, evs, cyc / 1024.0);
+					}
+				}
 				for (size_t q = 0; q < top; q++) {
 					const TaskResult& r = results[idx[q]];
 					const Task& t = tasks[idx[q]];

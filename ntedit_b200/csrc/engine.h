@@ -145,6 +145,7 @@ struct WalkerIO
 	Event* events;
 	uint32_t ev_cap;
 	Counters* ctr;
+	const uint64_t* rot;       // ROT_WORDS entries, see rot_entry()
 };
 
 #if defined(__CUDACC__)
@@ -159,6 +160,17 @@ constexpr int PROBE_G = 10;               // sampled k-mers whose probes are in 
 constexpr int PROBE_HU = 4;               // hash functions probed per pass (hash_num <= HMAX takes ceil(h/4) passes)
 constexpr uint32_t TEXT_CACHE = 256;      // bytes of contig text kept in the shared state around the window
 constexpr uint32_t LOOKAHEAD = 32;        // dirty-window positions whose site test is evaluated in one pass
+constexpr uint32_t ROT_STRIDE = KMAX + 8; // rotation amounts tabulated per seed: srol^d(seed), d < ROT_STRIDE
+constexpr uint32_t ROT_ROWS = 5;          // A C G T none
+constexpr uint32_t ROT_WORDS = ROT_ROWS * ROT_STRIDE;
+
+// rot[code * ROT_STRIDE + d] = srol^d(seed of code); one copy per CTA (per process in the host build)
+NTB_FN inline uint64_t
+rot_entry(uint32_t idx)
+{
+	const uint32_t code = idx / ROT_STRIDE, d = idx % ROT_STRIDE;
+	return code < 4 ? sroln(seed_of_code(code), d) : 0ULL;
+}
 
 // One candidate k-mer series: "change the window's last base to X, then roll Q times; the first `c` incoming bases
 // are synthetic (an insertion string), the rest come from the linearised rope starting at offset `d`; sample the
@@ -255,6 +267,19 @@ struct WalkerState
 	uint32_t sup[4];
 	uint8_t ins_sup[MAX_INS_TRIES];
 	uint8_t del_sup[MAX_DELETIONS + 2];
+	// hash state after R plain rolls from the current window (R = 0 is the window itself), R <= n_plain: every k-mer of
+	// the check-missing subset, of the substitution trials and of the dirty-run look-ahead is one of these, or one of
+	// these plus the rotation-table terms of the changed last base
+	static constexpr int PLAIN_CAP = (NCAP <= 160 ? 48 : (int)KMAX) + (int)LOOKAHEAD + 2;
+	uint64_t plain_f[PLAIN_CAP], plain_r[PLAIN_CAP];
+	uint32_t n_plain;
+	uint8_t tflag[4][KMAX + 1]; // substitution trial: sampled k-mer present && solid
+	// insertion candidates without rolling: hash state after q+1 rolls of an insertion of length L whose inserted chars
+	// contribute nothing (ins_base_*[L-1][sample]); the candidates add their chars' terms from the rotation table
+	static constexpr int NSMAX = NCAP <= 160 ? 16 : 32;
+	uint64_t ins_base_f[5][NSMAX], ins_base_r[5][NSMAX];
+	uint8_t ins_nvalid[5];
+	bool bases_ready, ins_fast;
 	// tryIndels bookkeeping across chunks
 	uint32_t ti_i0, ti_i1, ti_nd0, ti_ndel;
 	uint32_t tb_support, ta_support, tb_type, tb_len;
@@ -521,10 +546,10 @@ struct Walker
 	// of the aligned filter word into the lane's slot of S.pv (cp.async: no register is tied up while the load is in
 	// flight, so all ng x PROBE_HU loads of a lane overlap without unrolling anything); S.psh keeps the bit offset of the
 	// probed byte / bit inside that word.
-	NTB_FN void probe_issue(const FilterView& F, uint32_t ng, uint32_t want, uint32_t i0)
+	NTB_FN void probe_issue(const FilterView& F, uint32_t ng, uint32_t want, uint32_t i0, uint32_t hu)
 	{
 		const uint32_t ln = lane_id();
-		const uint32_t hn = F.hash_num - i0 < (uint32_t)PROBE_HU ? F.hash_num - i0 : (uint32_t)PROBE_HU;
+		const uint32_t hn = F.hash_num - i0 < hu ? F.hash_num - i0 : hu;
 		for (uint32_t g = 0; g < ng; g++) {
 			if (!((want >> g) & 1u)) {
 				continue;
@@ -553,10 +578,10 @@ struct Walker
 
 	// value of sampled k-mer g after probe_issue(F, .., i0): folds hash functions [i0, i0 + PROBE_HU) into `val`
 	// (bit filter: AND of the probed bits; counting filter: min of the probed counters)
-	NTB_FN uint32_t probe_fold(const FilterView& F, uint32_t g, uint32_t i0, uint32_t val) const
+	NTB_FN uint32_t probe_fold(const FilterView& F, uint32_t g, uint32_t i0, uint32_t hu, uint32_t val) const
 	{
 		const uint32_t ln = lane_id();
-		const uint32_t hn = F.hash_num - i0 < (uint32_t)PROBE_HU ? F.hash_num - i0 : (uint32_t)PROBE_HU;
+		const uint32_t hn = F.hash_num - i0 < hu ? F.hash_num - i0 : hu;
 		for (uint32_t u = 0; u < hn; u++) {
 			const uint32_t w = S.pv[g][u][ln] >> S.psh[g][u][ln];
 			if (F.counting) {
@@ -569,18 +594,67 @@ struct Walker
 		return val;
 	}
 
-	// values of the first ng sampled k-mers of this lane in filter F -> S.pval[g][lane] (only those in `want`)
-	NTB_FN_NOINLINE void probe_values(const FilterView& F, uint32_t ng, uint32_t want)
+	// values of the first ng sampled k-mers of this lane in filter F -> S.pval[g][lane] (only those in `want`), `hu` hash
+	// functions per pass.  A k-mer whose value reached 0 (a probed bit is clear / a counter is 0) is dropped from the later
+	// passes -- the value cannot change any more -- which is btllib's early exit (ntedit.cpp:368-371) done per pass.
+	NTB_FN_NOINLINE void probe_values(const FilterView& F, uint32_t ng, uint32_t want, uint32_t hu)
 	{
 		const uint32_t ln = lane_id();
-		for (uint32_t i0 = 0; i0 < F.hash_num; i0 += PROBE_HU) {
-			probe_issue(F, ng, want, i0);
+		for (uint32_t i0 = 0; i0 < F.hash_num && want; i0 += hu) {
+			probe_issue(F, ng, want, i0, hu);
 			for (uint32_t g = 0; g < ng; g++) {
 				if ((want >> g) & 1u) {
 					const uint32_t start = i0 == 0 ? (F.counting ? 255u : 1u) : (uint32_t)S.pval[g][ln];
-					S.pval[g][ln] = (uint8_t)probe_fold(F, g, i0, start);
+					const uint32_t v = probe_fold(F, g, i0, hu, start);
+					S.pval[g][ln] = (uint8_t)v;
+					if (v == 0) {
+						want &= ~(1u << g);
+					}
 				}
 			}
+		}
+	}
+
+	// probes the ng sampled k-mers of this lane (S.hb[0..ng)[lane]) and classifies them
+	NTB_FN void finish_group(uint32_t kind, uint32_t ng, uint32_t premask, uint32_t hu, uint32_t& pre_ok, uint32_t& count, uint32_t& nchk)
+	{
+		const uint32_t ln = lane_id();
+		const uint32_t valid = (1u << ng) - 1u;
+		probe_values(S.io.bloom, ng, valid, hu);
+		if (kind == CK_CHECK) {
+			for (uint32_t g = 0; g < ng; g++) {
+				S.chk[nchk++] = S.pval[g][ln];
+			}
+		} else if (kind == CK_SITE) {
+			for (uint32_t g = 0; g < ng; g++) {
+				if (is_site_value(S.pval[g][ln])) {
+					count = 1;
+				}
+			}
+		} else {
+			uint32_t solid = 0;
+			for (uint32_t g = 0; g < ng; g++) {
+				if (solid_value(S.pval[g][ln])) {
+					solid |= 1u << g;
+				}
+			}
+			if (P.h_rep && solid) {
+				// secondary filter (-e): a k-mer found there is not solid, ntedit.cpp:467-468
+				probe_values(S.io.rep, ng, solid, hu);
+				for (uint32_t g = 0; g < ng; g++) {
+					if (((solid >> g) & 1u) && S.pval[g][ln] != 0) {
+						solid &= ~(1u << g);
+					}
+				}
+			}
+			if (solid & premask) {
+				pre_ok = 1;
+			}
+#if defined(__CUDA_ARCH__)
+			count += (uint32_t)__popc(solid & ~premask);
+#else
+			count += (uint32_t)__builtin_popcount(solid & ~premask);
+#endif
 		}
 	}
 
@@ -638,43 +712,7 @@ struct Walker
 			if (ng == 0) {
 				break;
 			}
-			const uint32_t valid = (1u << ng) - 1u;
-			probe_values(S.io.bloom, ng, valid);
-			if (kind == CK_CHECK) {
-				for (uint32_t g = 0; g < ng; g++) {
-					S.chk[nchk++] = S.pval[g][ln];
-				}
-			} else if (kind == CK_SITE) {
-				for (uint32_t g = 0; g < ng; g++) {
-					if (is_site_value(S.pval[g][ln])) {
-						count = 1;
-					}
-				}
-			} else {
-				uint32_t solid = 0;
-				for (uint32_t g = 0; g < ng; g++) {
-					if (solid_value(S.pval[g][ln])) {
-						solid |= 1u << g;
-					}
-				}
-				if (P.h_rep && solid) {
-					// secondary filter (-e): a k-mer found there is not solid, ntedit.cpp:467-468
-					probe_values(S.io.rep, ng, solid);
-					for (uint32_t g = 0; g < ng; g++) {
-						if (((solid >> g) & 1u) && S.pval[g][ln] != 0) {
-							solid &= ~(1u << g);
-						}
-					}
-				}
-				if (solid & premask) {
-					pre_ok = 1;
-				}
-#if defined(__CUDA_ARCH__)
-				count += (uint32_t)__popc(solid & ~premask);
-#else
-				count += (uint32_t)__builtin_popcount(solid & ~premask);
-#endif
-			}
+			finish_group(kind, ng, premask, PROBE_HU, pre_ok, count, nchk);
 		}
 		if (kind == CK_CHECK) {
 			S.chk_n = nchk;
@@ -957,6 +995,136 @@ struct Walker
 		}
 	}
 
+	// ---------------------------------------------------------------- plain rolls
+	// plain_f[R] / plain_r[R] = forward / reverse hash after R calls of roll() from the current state (no edit applied),
+	// R = 0 .. min(n_rolls, cap).  The two strands are independent chains: lane 0 rolls the forward one, lane 1 the reverse.
+	NTB_FN void compute_plain(uint32_t want)
+	{
+		const uint32_t cap = (uint32_t)WalkerState<NCAP>::PLAIN_CAP - 1;
+		uint32_t n = S.n_rolls < want ? S.n_rolls : want;
+		if (n > cap) {
+			n = cap;
+		}
+		warp_sync();
+		const uint32_t ln = lane_id();
+		if (ln == 0) {
+			uint64_t f = S.hs.fh;
+			S.plain_f[0] = f;
+			for (uint32_t r = 0; r < n; r++) {
+				f = srol1(f) ^ S.seed_tab[S.lin_in_c[r] & 7u] ^ S.rotk_tab[S.lin_out_c[r] & 7u];
+				S.plain_f[r + 1] = f;
+			}
+			S.n_plain = n;
+		}
+		if (ln == (lane_count() > 1 ? 1u : 0u)) {
+			uint64_t rv = S.hs.rh;
+			S.plain_r[0] = rv;
+			for (uint32_t r = 0; r < n; r++) {
+				rv = sror1(rv ^ S.rotk_tab[(S.lin_in_c[r] >> 3) & 7u] ^ S.seed_tab[(S.lin_out_c[r] >> 3) & 7u]);
+				S.plain_r[r + 1] = rv;
+			}
+		}
+		warp_sync();
+	}
+
+	// phase 1 without rolling: every k-mer of the check-missing subset (ntedit.cpp:1826-1858), of the substitution gates
+	// (ntedit.cpp:1923-1928) and of the substitution trials (ntedit.cpp:1936-1981) as one job, jobs dealt round-robin to
+	// the lanes.  A trial k-mer after R rolls is the plain k-mer plus the NTMC64_changelast terms rotated R times; after
+	// k rolls the substituted base has left the window and the k-mer is the plain one.
+	// Requires patch_idx == k-1 (the tail's slot leaves the window with the k-th roll), which every consistent rope gives.
+	NTB_FN void phase_check_and_subs_fast()
+	{
+		const uint32_t k = P.k, jump = P.jump, ln = lane_id();
+		const uint32_t n_sub = S.n_rolls < k ? S.n_rolls : k;
+		const uint32_t nC = S.n_check ? (S.n_check - 1) / jump + 1 : 0;   // samples q = 0, jump, .. < n_check
+		const uint32_t nT = n_sub ? (n_sub - 1) / jump + 1 : 0;           // samples q = 0, jump, .. < n_sub
+		uint32_t ncand = 0;
+		while (ncand < 4 && ((S.cands >> (8 * ncand)) & 0xFF) != 0) {
+			ncand++;
+		}
+		const uint32_t per_cand = 1 + nT; // gate + trial samples
+		const uint32_t njobs = nC + ncand * per_cand;
+		const uint32_t df = base_code(S.draft), dr = rev_code(S.draft);
+		const uint64_t* rot = S.io.rot;
+		warp_sync();
+		for (uint32_t j0 = 0; j0 < njobs; j0 += lane_count() * PROBE_G) {
+			// this lane's jobs of the round: j0 + ln, j0 + ln + lanes, ...
+			uint32_t ng = 0;
+			for (uint32_t j = j0 + ln; j < njobs && ng < (uint32_t)PROBE_G; j += lane_count()) {
+				uint64_t f, r;
+				if (j < nC) {
+					const uint32_t R = j * jump + 1;
+					f = S.plain_f[R];
+					r = S.plain_r[R];
+				} else {
+					const uint32_t c = (j - nC) / per_cand, w = (j - nC) % per_cand;
+					const unsigned char X = (unsigned char)((S.cands >> (8 * c)) & 0xFF);
+					const uint32_t R = w == 0 ? 0 : (w - 1) * jump + 1;
+					f = S.plain_f[R];
+					r = S.plain_r[R];
+					if (R < k) {
+						f ^= rot[df * ROT_STRIDE + R] ^ rot[base_code(X) * ROT_STRIDE + R];
+						r ^= rot[dr * ROT_STRIDE + (k - 1 - R)] ^ rot[rev_code(X) * ROT_STRIDE + (k - 1 - R)];
+					}
+				}
+				S.hb[ng][ln] = f + r;
+				ng++;
+			}
+			if (ng) {
+				probe_values(S.io.bloom, ng, (1u << ng) - 1u, PROBE_HU);
+				// solid k-mers additionally must be absent from the secondary filter (-e), ntedit.cpp:467-468
+				uint32_t solid = 0;
+				uint32_t g = 0;
+				for (uint32_t j = j0 + ln; j < njobs && g < ng; j += lane_count(), g++) {
+					if (j >= nC && solid_value(S.pval[g][ln])) {
+						solid |= 1u << g;
+					}
+				}
+				uint32_t raw[PROBE_G];
+				for (uint32_t q = 0; q < ng; q++) {
+					raw[q] = S.pval[q][ln];
+				}
+				if (P.h_rep && solid) {
+					probe_values(S.io.rep, ng, solid, PROBE_HU);
+					for (uint32_t q = 0; q < ng; q++) {
+						if (((solid >> q) & 1u) && S.pval[q][ln] != 0) {
+							solid &= ~(1u << q);
+						}
+					}
+				}
+				g = 0;
+				for (uint32_t j = j0 + ln; j < njobs && g < ng; j += lane_count(), g++) {
+					if (j < nC) {
+						S.chk[j] = (uint8_t)raw[g];
+					} else {
+						const uint32_t c = (j - nC) / per_cand, w = (j - nC) % per_cand;
+						const uint8_t ok = (uint8_t)((solid >> g) & 1u);
+						if (w == 0) {
+							S.gate[c] = ok;
+						} else {
+							S.tflag[c][w - 1] = ok;
+						}
+					}
+				}
+			}
+		}
+		warp_sync();
+		NTB_LEADER_BEGIN
+		S.chk_n = nC;
+		for (uint32_t c = 0; c < 4; c++) {
+			uint32_t cnt = 0;
+			if (c < ncand) {
+				for (uint32_t w = 0; w < nT; w++) {
+					cnt += S.tflag[c][w];
+				}
+			} else {
+				S.gate[c] = 0;
+			}
+			S.sup[c] = cnt;
+		}
+		NTB_LEADER_END
+	}
+
 	// ---------------------------------------------------------------- phases: one candidate per lane
 	// phase 1: job 0 = the check-missing subset, job 1+ci = substitution candidate ci (gate + trial)
 	NTB_FN void phase_check_and_subs()
@@ -1004,50 +1172,143 @@ struct Walker
 		warp_sync();
 	}
 
-	// phase 2: insertion candidates [i0, i1) of tryIndels for S.index_char and the deletions its iterations would try
-	NTB_FN void phase_indels()
+	// ---- tryIndels candidates (ntedit.cpp:1548-1744)
+	// All insertion candidates of a site roll the same outgoing and (after their inserted chars) the same incoming bases;
+	// ntHash is GF(2)-linear in the seeds, so the hash of candidate (string, sample) is
+	//     base(L, sample)  ^  terms of the index char / draft char (NTMC64_changelast)  ^  terms of the inserted chars,
+	// where base(L, .) is the hash state of "an insertion of length L whose chars have no seed" and every term is one
+	// entry of the rotation table.  Lanes 0..4 roll the five bases once per site; the 341 x 3 candidates then cost a few
+	// table look-ups per sampled k-mer instead of k-1 rolls each.
+	NTB_FN void compute_ins_bases()
 	{
-		const uint32_t n_ins = S.ti_i1 - S.ti_i0;
-		const uint32_t njobs = n_ins + S.ti_ndel;
+		const uint32_t k = P.k, jump = P.jump;
+		const uint32_t ns = (k - 1 + jump - 1) / jump; // samples after rolls q = 0, jump, 2 jump, ... < k-1
+		NTB_LEADER_BEGIN
+		S.ins_fast = ns <= (uint32_t)WalkerState<NCAP>::NSMAX && k + 4 < ROT_STRIDE;
+		S.bases_ready = true;
+		NTB_LEADER_END
+		if (!S.ins_fast) {
+			return;
+		}
+		for (uint32_t L = 1 + lane_id(); L <= 5; L += lane_count()) {
+			HashState st = S.hs;
+			uint32_t jc = 0, nv = 0;
+			for (uint32_t r = 0; r + 1 < k; r++) {
+				uint32_t ci = 0x24; // no seed on either strand
+				if (r >= L) {
+					const uint32_t j = r - L;
+					if (j >= S.n_rolls) {
+						break;
+					}
+					ci = S.lin_in_c[j];
+				}
+				roll_cls(st, S.lin_out_c[r], ci);
+				if (jc == 0) {
+					S.ins_base_f[L - 1][nv] = st.fh;
+					S.ins_base_r[L - 1][nv] = st.rh;
+					nv++;
+					jc = jump;
+				}
+				jc--;
+			}
+			S.ins_nvalid[L - 1] = (uint8_t)nv;
+		}
 		warp_sync();
-		for (uint32_t j = lane_id(); j < njobs; j += lane_count()) {
+	}
+
+	// support of insertion candidate i for S.index_char from the bases (this lane)
+	NTB_FN uint32_t eval_insertion_fast(uint32_t i)
+	{
+		const uint32_t ln = lane_id();
+		const uint32_t k = P.k, jump = P.jump;
+		uint64_t packed;
+		const uint32_t L = indel_string(S.index_char, i, packed);
+		// incoming chars of the synthetic rolls: string[1..L-1] then the draft char (ntedit.cpp:1583-1606)
+		uint32_t fcode[5], rcode[5];
+		for (uint32_t q = 0; q < L; q++) {
+			const unsigned char c = q + 1 < L ? (unsigned char)((packed >> (8 * (q + 1))) & 0xFF) : S.draft;
+			fcode[q] = base_code(c);
+			rcode[q] = rev_code(c);
+		}
+		const uint32_t xf = base_code(S.index_char), xr = rev_code(S.index_char);
+		const uint32_t df = base_code(S.draft), dr = rev_code(S.draft);
+		const uint64_t* rot = S.io.rot;
+		const uint32_t nv = S.ins_nvalid[L - 1];
+		uint32_t pre_ok = 0, count = 0, nchk = 0;
+		for (uint32_t s0 = 0; s0 < nv; s0 += PROBE_G) {
+			const uint32_t ng = nv - s0 < (uint32_t)PROBE_G ? nv - s0 : (uint32_t)PROBE_G;
+			for (uint32_t g = 0; g < ng; g++) {
+				const uint32_t R = (s0 + g) * jump + 1; // rolls done when the sample is taken
+				uint64_t f = S.ins_base_f[L - 1][s0 + g] ^ rot[df * ROT_STRIDE + R] ^ rot[xf * ROT_STRIDE + R];
+				uint64_t r = S.ins_base_r[L - 1][s0 + g] ^ rot[dr * ROT_STRIDE + (k - 1 - R)] ^ rot[xr * ROT_STRIDE + (k - 1 - R)];
+				const uint32_t m = L < R ? L : R;
+				for (uint32_t q = 0; q < m; q++) {
+					f ^= rot[fcode[q] * ROT_STRIDE + (R - 1 - q)];
+					r ^= rot[rcode[q] * ROT_STRIDE + (k - R + q)];
+				}
+				S.hb[g][ln] = f + r;
+			}
+			finish_group(CK_SOLID, ng, 0, 1, pre_ok, count, nchk);
+		}
+		return count;
+	}
+
+	// insertion candidates [i0, i1) of tryIndels for S.index_char: one per lane, 32 at a time
+	NTB_FN void phase_insertions(uint32_t i0, uint32_t i1)
+	{
+		warp_sync();
+		for (uint32_t i = i0 + lane_id(); i < i1; i += lane_count()) {
+			if (S.ins_fast) {
+				S.ins_sup[i] = (uint8_t)eval_insertion_fast(i);
+				continue;
+			}
+			// insertion string + the draft char, rolled base by base (ntedit.cpp:1583-1645)
 			Cand cd;
 			cd.kind = CK_SOLID;
 			cd.change = 1;
 			cd.patch = 0;
 			cd.period = P.jump;
 			uint32_t pre_ok = 0, count = 0;
-			if (j < n_ins) {
-				// insertion string + the draft char, ntedit.cpp:1583-1645
-				const uint32_t i = S.ti_i0 + j;
-				uint64_t packed;
-				const uint32_t len = indel_string(S.index_char, i, packed);
-				cd.X = S.index_char;
-				uint64_t sc = 0;
-				for (uint32_t q = 1; q < len; q++) {
-					sc |= (uint64_t)cls_of((unsigned char)((packed >> (8 * q)) & 0xFF)) << (8 * (q - 1));
-				}
-				cd.syn_cls = sc | ((uint64_t)cls_of(S.draft) << (8 * (len - 1)));
-				cd.c = len;
-				cd.d = 0;
-				cd.pre = 0;
-				cd.first = 0;
-				cd.Q = P.k - 1;
-				eval_cand(cd, pre_ok, count);
-				S.ins_sup[i] = (uint8_t)count;
-			} else {
-				// tryDeletion, ntedit.cpp:1451-1545
-				const uint32_t n = S.ti_nd0 + (j - n_ins);
-				cd.X = n >= 1 && n - 1 < S.n_rolls ? S.lin_in[n - 1] : 0;
-				cd.syn_cls = 0;
-				cd.c = 0;
-				cd.d = n;
-				cd.pre = 1;
-				cd.first = P.jump - 1;
-				cd.Q = P.k - 2;
-				eval_cand(cd, pre_ok, count);
-				S.del_sup[n] = (uint8_t)(pre_ok + count);
+			uint64_t packed;
+			const uint32_t len = indel_string(S.index_char, i, packed);
+			cd.X = S.index_char;
+			uint64_t sc = 0;
+			for (uint32_t q = 1; q < len; q++) {
+				sc |= (uint64_t)cls_of((unsigned char)((packed >> (8 * q)) & 0xFF)) << (8 * (q - 1));
 			}
+			cd.syn_cls = sc | ((uint64_t)cls_of(S.draft) << (8 * (len - 1)));
+			cd.c = len;
+			cd.d = 0;
+			cd.pre = 0;
+			cd.first = 0;
+			cd.Q = P.k - 1;
+			eval_cand(cd, pre_ok, count);
+			S.ins_sup[i] = (uint8_t)count;
+		}
+		warp_sync();
+	}
+
+	// tryDeletion (ntedit.cpp:1451-1545) for n = nd0 .. nd0 + ndel - 1: one per lane
+	NTB_FN void phase_deletions(uint32_t nd0, uint32_t ndel)
+	{
+		warp_sync();
+		for (uint32_t j = lane_id(); j < ndel; j += lane_count()) {
+			const uint32_t n = nd0 + j;
+			Cand cd;
+			cd.kind = CK_SOLID;
+			cd.change = 1;
+			cd.patch = 0;
+			cd.period = P.jump;
+			cd.X = n >= 1 && n - 1 < S.n_rolls ? S.lin_in[n - 1] : 0;
+			cd.syn_cls = 0;
+			cd.c = 0;
+			cd.d = n;
+			cd.pre = 1;
+			cd.first = P.jump - 1;
+			cd.Q = P.k - 2;
+			uint32_t pre_ok = 0, count = 0;
+			eval_cand(cd, pre_ok, count);
+			S.del_sup[n] = (uint8_t)(pre_ok + count);
 		}
 		warp_sync();
 	}
@@ -1058,36 +1319,40 @@ struct Walker
 	NTB_FN bool try_indels()
 	{
 		const uint32_t T = P.max_ins_tries;
+		if (T == 0) {
+			return false;
+		}
+		if (!S.bases_ready) {
+			compute_ins_bases();
+		}
 		NTB_LEADER_BEGIN
 		S.tb_support = S.ta_support = S.tb_type = S.tb_len = 0;
 		S.ti_done = false;
 		S.ti_ret = false;
 		S.ti_i0 = 0;
+		// deletions this call can reach: one per iteration while num_deletions <= max_deletions
+		S.ti_nd0 = S.num_deletions;
+		uint32_t nd = 0;
+		if (S.num_deletions <= P.max_deletions) {
+			nd = P.max_deletions - S.num_deletions + 1;
+			if (nd > T) {
+				nd = T;
+			}
+		}
+		S.ti_ndel = nd;
 		NTB_LEADER_END
+		if (S.ti_ndel) {
+			phase_deletions(S.ti_nd0, S.ti_ndel);
+		}
 		while (S.ti_i0 < T) {
+			// first hit wins in mode 0: evaluate one warp's worth of candidates at a time
+			const uint32_t i0 = S.ti_i0;
+			const uint32_t i1 = (P.mode == 0 && i0 + lane_count() * 1u < T && lane_count() > 1) ? i0 + lane_count()
+			                    : (P.mode == 0 && lane_count() == 1 && i0 + 32 < T)            ? i0 + 32
+			                                                                                   : T;
+			phase_insertions(i0, i1);
 			NTB_LEADER_BEGIN
-			uint32_t i1 = T;
-			if (P.mode == 0) {
-				// first hit wins: evaluate a small chunk first
-				i1 = S.ti_i0 == 0 ? 24 : S.ti_i0 == 24 ? 88 : T;
-				if (i1 > T) {
-					i1 = T;
-				}
-			}
-			S.ti_i1 = i1;
-			S.ti_nd0 = S.num_deletions;
-			uint32_t nd = 0;
-			if (S.num_deletions <= P.max_deletions) {
-				nd = P.max_deletions - S.num_deletions + 1;
-				if (nd > i1 - S.ti_i0) {
-					nd = i1 - S.ti_i0;
-				}
-			}
-			S.ti_ndel = nd;
-			NTB_LEADER_END
-			phase_indels();
-			NTB_LEADER_BEGIN
-			for (uint32_t i = S.ti_i0; i < S.ti_i1; i++) {
+			for (uint32_t i = i0; i < i1; i++) {
 				const uint32_t present = S.ins_sup[i];
 				if (meets_edit(present)) {
 					uint64_t packed;
@@ -1139,7 +1404,7 @@ struct Walker
 					S.num_deletions++;
 				}
 			}
-			S.ti_i0 = S.ti_i1;
+			S.ti_i0 = i1;
 			NTB_LEADER_END
 			if (S.ti_done) {
 				return S.ti_ret;
@@ -1177,6 +1442,7 @@ struct Walker
 		S.cands = candidates(S.draft);
 		S.site_ok = true;
 		S.chk_n = 0;
+		S.bases_ready = false;
 	}
 
 	// leader: check-missing verdict (ntedit.cpp:1859-1873) and the site locals (ntedit.cpp:1876-1914)
@@ -1393,7 +1659,12 @@ struct Walker
 		if (!P.snv && S.dnf) {
 			return true; // no attempt is possible (ntedit.cpp:1865): the subset counts are not needed
 		}
-		phase_check_and_subs();
+		if (S.patch_idx == P.k - 1 && P.k + 1 < ROT_STRIDE) {
+			compute_plain(P.k);
+			phase_check_and_subs_fast();
+		} else {
+			phase_check_and_subs();
+		}
 		NTB_LEADER_BEGIN
 		S.next = site_after_check() ? NEXT_CAND : NEXT_STOP;
 		NTB_LEADER_END
@@ -1705,24 +1976,38 @@ struct Walker
 	{
 		linearise(LOOKAHEAD - 1, false);
 		const uint32_t n = S.n_rolls + 1 < LOOKAHEAD ? S.n_rolls + 1 : LOOKAHEAD;
+		compute_plain(LOOKAHEAD - 1);
 		uint32_t bits = 0;
-		for (uint32_t j = lane_id(); j < n; j += lane_count()) {
-			Cand cd;
-			cd.syn_cls = 0;
-			cd.c = 0;
-			cd.d = 0;
-			cd.X = 0;
-			cd.change = 0;
-			cd.patch = 0;
-			cd.kind = CK_SITE;
-			cd.Q = j;
-			cd.pre = j == 0;
-			cd.first = j == 0 ? 0 : j - 1;
-			cd.period = LOOKAHEAD + 1;
-			uint32_t pre_ok = 0, count = 0;
-			eval_cand(cd, pre_ok, count);
-			if (count) {
-				bits |= 1u << j;
+		{
+			// lane j: the k-mer after j plain rolls (LOOKAHEAD <= lanes * PROBE_G)
+			const uint32_t ln = lane_id();
+			uint32_t ng = 0;
+			for (uint32_t j = ln; j < n && ng < (uint32_t)PROBE_G; j += lane_count()) {
+				S.hb[ng][ln] = S.plain_f[j] + S.plain_r[j];
+				ng++;
+			}
+			for (uint32_t g0 = 0; g0 < ng || (lane_count() == 1 && g0 < n); g0 += PROBE_G) {
+				if (lane_count() == 1 && g0 > 0) {
+					// one-lane build: refill the group
+					ng = 0;
+					for (uint32_t j = g0; j < n && ng < (uint32_t)PROBE_G; j++) {
+						S.hb[ng][ln] = S.plain_f[j] + S.plain_r[j];
+						ng++;
+					}
+				}
+				if (ng == 0) {
+					break;
+				}
+				probe_values(S.io.bloom, ng, (1u << ng) - 1u, PROBE_HU);
+				for (uint32_t g = 0; g < ng; g++) {
+					const uint32_t j = lane_count() == 1 ? g0 + g : ln + g * lane_count();
+					if (is_site_value(S.pval[g][ln])) {
+						bits |= 1u << j;
+					}
+				}
+				if (lane_count() > 1) {
+					break;
+				}
 			}
 		}
 		bits = warp_or(bits); // lane j holds bit j only
@@ -1764,87 +2049,102 @@ struct Walker
 		NTB_LEADER_END
 	}
 
-	// Walks one task.  Called by every lane of the warp with the same arguments.
-	NTB_FN void run(const Task& task, TaskResult& res)
+	// One iteration of the main loop (ntedit.cpp:1797-2139).  Called by every lane of the warp; returns false when the
+	// task is finished.  The CUDA kernel aligns the warps of a CTA at the top of every iteration (they then run the same
+	// instructions at about the same time, which is what keeps the instruction cache effective); the iteration itself has
+	// no CTA-level synchronisation.
+	NTB_FN bool step(const Task& task)
+	{
+		if (S.act == ACT_STOP) {
+			return false;
+		}
+		NTB_LEADER_BEGIN
+		loop_head(task);
+		NTB_LEADER_END
+		if (S.act == ACT_STOP) {
+			return false;
+		}
+		if (S.act == ACT_CLEAN) {
+			const uint32_t nv = next_visit(S.t.pos, task.end);
+			NTB_LEADER_BEGIN
+			if (nv == NONE32) {
+				S.end_pos = task.end;
+				S.act = ACT_STOP;
+			} else {
+				S.do_seed = nv != S.t.pos || S.need_seed;
+				S.visit_hit = nv;
+				if (S.do_seed) {
+					S.t.pos = nv;
+					S.h.pos = nv + 1 - P.k;
+				}
+				S.need_seed = false;
+			}
+			NTB_LEADER_END
+			if (S.act == ACT_STOP) {
+				return false;
+			}
+			if (!cache_covers_window()) {
+				fill_cache(S.h.pos);
+			}
+			NTB_LEADER_BEGIN
+			if (S.do_seed) {
+				seed_at(S.visit_hit);
+				reset_rope(S.h.pos);
+				S.site_now = true; // K1 flagged this very window
+			} else if (P.snv) {
+				S.site_now = true;
+			} else if (P.counting) {
+				S.site_now = is_site_value(q_count(S.hs));
+			} else {
+				S.site_now = !q_contains(S.hs);
+			}
+			NTB_LEADER_END
+		} else {
+			if (!cache_covers_window()) {
+				fill_cache(S.h.pos);
+			}
+			if (P.snv) {
+				NTB_LEADER_BEGIN
+				S.site_now = true;
+				NTB_LEADER_END
+			} else {
+				if (S.la_used >= S.la_n) {
+					lookahead();
+					if (S.jumped) {
+						return true; // now on a clean window: back to the top of the main loop
+					}
+				}
+				NTB_LEADER_BEGIN
+				S.site_now = ((S.la_bits >> S.la_used) & 1u) != 0;
+				NTB_LEADER_END
+			}
+		}
+		if (S.site_now) {
+			if (!evaluate_site()) {
+				NTB_LEADER_BEGIN
+				S.status |= ST_CONTIG_END;
+				S.act = ACT_STOP;
+				NTB_LEADER_END
+				return false;
+			}
+		}
+		NTB_LEADER_BEGIN
+		advance();
+		NTB_LEADER_END
+		return S.act != ACT_STOP;
+	}
+
+	// every lane: start a task
+	NTB_FN void begin(const Task& task)
 	{
 		NTB_LEADER_BEGIN
 		task_begin(task);
 		NTB_LEADER_END
-		while (S.act != ACT_STOP) {
-			NTB_LEADER_BEGIN
-			loop_head(task);
-			NTB_LEADER_END
-			if (S.act == ACT_STOP) {
-				break;
-			}
-			if (S.act == ACT_CLEAN) {
-				const uint32_t nv = next_visit(S.t.pos, task.end);
-				NTB_LEADER_BEGIN
-				if (nv == NONE32) {
-					S.end_pos = task.end;
-					S.act = ACT_STOP;
-				} else {
-					S.do_seed = nv != S.t.pos || S.need_seed;
-					S.visit_hit = nv;
-					if (S.do_seed) {
-						S.t.pos = nv;
-						S.h.pos = nv + 1 - P.k;
-					}
-					S.need_seed = false;
-				}
-				NTB_LEADER_END
-				if (S.act == ACT_STOP) {
-					break;
-				}
-				if (!cache_covers_window()) {
-					fill_cache(S.h.pos);
-				}
-				NTB_LEADER_BEGIN
-				if (S.do_seed) {
-					seed_at(S.visit_hit);
-					reset_rope(S.h.pos);
-					S.site_now = true; // K1 flagged this very window
-				} else if (P.snv) {
-					S.site_now = true;
-				} else if (P.counting) {
-					S.site_now = is_site_value(q_count(S.hs));
-				} else {
-					S.site_now = !q_contains(S.hs);
-				}
-				NTB_LEADER_END
-			} else {
-				if (!cache_covers_window()) {
-					fill_cache(S.h.pos);
-				}
-				if (P.snv) {
-					NTB_LEADER_BEGIN
-					S.site_now = true;
-					NTB_LEADER_END
-				} else {
-					if (S.la_used >= S.la_n) {
-						lookahead();
-						if (S.jumped) {
-							continue; // now on a clean window: back to the top of the main loop
-						}
-					}
-					NTB_LEADER_BEGIN
-					S.site_now = ((S.la_bits >> S.la_used) & 1u) != 0;
-					NTB_LEADER_END
-				}
-			}
-			if (S.site_now) {
-				if (!evaluate_site()) {
-					NTB_LEADER_BEGIN
-					S.status |= ST_CONTIG_END;
-					S.act = ACT_STOP;
-					NTB_LEADER_END
-					break;
-				}
-			}
-			NTB_LEADER_BEGIN
-			advance();
-			NTB_LEADER_END
-		}
+	}
+
+	// every lane: the result of a finished task (valid in the leader lane)
+	NTB_FN void finish(TaskResult& res)
+	{
 		NTB_LEADER_BEGIN
 		S.status |= ST_DONE;
 		res.end_pos = (S.status & ST_CONTIG_END) ? S.io.len : S.end_pos;
@@ -1859,6 +2159,15 @@ struct Walker
 		res.stale[3] = S.stale_alt3;
 		res.kcycles = 0;
 		NTB_LEADER_END
+	}
+
+	// Walks one task.  Called by every lane of the warp with the same arguments.
+	NTB_FN void run(const Task& task, TaskResult& res)
+	{
+		begin(task);
+		while (step(task)) {
+		}
+		finish(res);
 	}
 };
 

@@ -1,6 +1,8 @@
 // sm_100a kernels of the ntEdit hot path -- see kernels.cuh for the map to the reference.
 #include "kernels.cuh"
 
+#include <cstdlib>
+
 namespace ntb {
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -325,65 +327,125 @@ launch_scan(const ScanArgs& a, bool counting, bool extra, int grid, cudaStream_t
 // K2
 // K2: persistent warps, one task (contig segment) per warp at a time, tasks handed out through an atomic counter.
 // The walker state of every warp lives in shared memory (engine.h: WalkerState); lane 0 is the leader.
+// NCAP (capacity of the local rope copy) is 2.5 k + 32 rounded up: 160 serves k <= 48, 352 serves k <= KMAX.
+template<int NCAP>
 __global__ void __launch_bounds__(WALK_THREADS)
 walk_kernel(const uint8_t* text, const uint32_t* visit, FilterView bloom, FilterView rep, const __grid_constant__ KParams kp,
-            const Task* tasks, TaskResult* results, uint32_t n_tasks, Event* events, uint32_t ev_cap, Counters* ctr)
+            const Task* tasks, const uint32_t* order, TaskResult* results, uint32_t n_tasks, Event* events, uint32_t ev_cap, Counters* ctr)
 {
 	extern __shared__ __align__(16) uint8_t walk_smem[];
-	WalkState* states = reinterpret_cast<WalkState*>(walk_smem);
-	WalkState& S = states[threadIdx.x >> 5];
+	WalkerState<NCAP>* states = reinterpret_cast<WalkerState<NCAP>*>(walk_smem);
+	WalkerState<NCAP>& S = states[threadIdx.x >> 5];
+	uint64_t* rot = reinterpret_cast<uint64_t*>(walk_smem + (size_t)WALK_WARPS * sizeof(WalkerState<NCAP>));
+	for (uint32_t q = threadIdx.x; q < ROT_WORDS; q += WALK_THREADS) {
+		rot[q] = rot_entry(q);
+	}
+	__syncthreads();
 	const uint32_t lane = threadIdx.x & 31u;
-	Walker<WALK_NCAP> w(S, kp);
+	Walker<NCAP> w(S, kp);
+	bool have = false;
+	uint32_t i = 0;
+	Task task;
+	long long c0 = 0;
 	for (;;) {
-		uint32_t i = 0;
-		if (lane == 0) {
-			i = atomicAdd(&ctr->next_task, 1u);
+		if (!have) {
+			if (lane == 0) {
+				i = atomicAdd(&ctr->next_task, 1u);
+			}
+			i = __shfl_sync(0xFFFFFFFFu, i, 0);
+			if (i < n_tasks) {
+				if (order) {
+					i = order[i];
+				}
+				task = tasks[i];
+				__syncwarp();
+				if (lane == 0) {
+					S.io.text = text + task.text_off;
+					S.io.len = task.len;
+					S.io.visit = visit;
+					S.io.goff = task.text_off;
+					S.io.bloom = bloom;
+					S.io.rep = rep;
+					S.io.events = events;
+					S.io.ev_cap = ev_cap;
+					S.io.ctr = ctr;
+					S.io.rot = rot;
+				}
+				__syncwarp();
+				c0 = clock64();
+				w.begin(task);
+				have = true;
+			}
 		}
-		i = __shfl_sync(0xFFFFFFFFu, i, 0);
-		if (i >= n_tasks) {
+		if (!have) {
 			break;
 		}
-		const Task task = tasks[i];
-		__syncwarp();
-		if (lane == 0) {
-			S.io.text = text + task.text_off;
-			S.io.len = task.len;
-			S.io.visit = visit;
-			S.io.goff = task.text_off;
-			S.io.bloom = bloom;
-			S.io.rep = rep;
-			S.io.events = events;
-			S.io.ev_cap = ev_cap;
-			S.io.ctr = ctr;
-		}
-		__syncwarp();
-		TaskResult res;
-		const long long c0 = clock64();
-		w.run(task, res);
-		if (lane == 0) {
-			res.kcycles = (uint32_t)((clock64() - c0) >> 10);
-			results[i] = res;
+		if (!w.step(task)) {
+			TaskResult res;
+			w.finish(res);
+			if (lane == 0) {
+				res.kcycles = (uint32_t)((clock64() - c0) >> 10);
+				results[i] = res;
+			}
+			have = false;
 		}
 	}
 }
 
-cudaError_t
-launch_walk(const uint8_t* text, const uint32_t* visit, const FilterView& bloom, const FilterView& rep, const KParams& kp, const Task* tasks,
-            TaskResult* results, uint32_t n_tasks, Event* events, uint32_t ev_cap, Counters* ctr, int sm_count, cudaStream_t stream)
+// Puts the tasks with many flagged positions at the front of the work queue (they take the longest: every flagged
+// position in an unfixable stretch can cost a full insertion / deletion enumeration), the rest behind them.
+__global__ void __launch_bounds__(256)
+order_tasks_kernel(const uint32_t* visit, const Task* tasks, uint32_t n_tasks, uint32_t dense_threshold, uint32_t* order, Counters* ctr)
+{
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n_tasks) {
+		return;
+	}
+	const Task t = tasks[i];
+	const uint64_t g0 = t.text_off + t.start, g1 = t.text_off + t.end;
+	uint32_t cnt = 0;
+	for (uint64_t w = g0 >> 5; (w << 5) < g1 && cnt < dense_threshold; w++) {
+		uint32_t bits = visit[w];
+		if (w == (g0 >> 5)) {
+			bits &= 0xFFFFFFFFu << (g0 & 31);
+		}
+		if (((w + 1) << 5) > g1) {
+			bits &= 0xFFFFFFFFu >> (32 - (g1 & 31));
+		}
+		cnt += __popc(bits);
+	}
+	if (cnt >= dense_threshold) {
+		order[atomicAdd(&ctr->n_front, 1u)] = i;
+	} else {
+		order[n_tasks - 1 - atomicAdd(&ctr->n_back, 1u)] = i;
+	}
+}
+
+template<int NCAP>
+static cudaError_t
+launch_walk_n(const uint8_t* text, const uint32_t* visit, const FilterView& bloom, const FilterView& rep, const KParams& kp, const Task* tasks,
+              const uint32_t* order, TaskResult* results, uint32_t n_tasks, Event* events, uint32_t ev_cap, Counters* ctr, int sm_count,
+              cudaStream_t stream)
 {
 	static int blocks_per_sm = 0;
-	const size_t smem = walk_smem_bytes();
+	const size_t smem = (size_t)WALK_WARPS * sizeof(WalkerState<NCAP>) + ROT_WORDS * sizeof(uint64_t);
 	if (blocks_per_sm == 0) {
-		cudaError_t e = cudaFuncSetAttribute(walk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+		cudaError_t e = cudaFuncSetAttribute(walk_kernel<NCAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 		if (e != cudaSuccess) {
 			return e;
 		}
 		int n = 0;
-		e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, walk_kernel, WALK_THREADS, smem);
+		e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, walk_kernel<NCAP>, WALK_THREADS, smem);
 		if (e != cudaSuccess) {
 			return e;
 		}
 		blocks_per_sm = n > 0 ? n : 1;
+		if (const char* cap = std::getenv("NTB_WALK_BLOCKS_PER_SM")) { // tuning aid
+			const int c = std::atoi(cap);
+			if (c > 0 && c < blocks_per_sm) {
+				blocks_per_sm = c;
+			}
+		}
 	}
 	const uint64_t want = ((uint64_t)n_tasks + WALK_WARPS - 1) / WALK_WARPS;
 	const uint64_t cap = (uint64_t)sm_count * (uint64_t)blocks_per_sm;
@@ -391,8 +453,26 @@ launch_walk(const uint8_t* text, const uint32_t* visit, const FilterView& bloom,
 	if (grid == 0) {
 		return cudaSuccess;
 	}
-	walk_kernel<<<grid, WALK_THREADS, smem, stream>>>(text, visit, bloom, rep, kp, tasks, results, n_tasks, events, ev_cap, ctr);
+	walk_kernel<NCAP><<<grid, WALK_THREADS, smem, stream>>>(text, visit, bloom, rep, kp, tasks, order, results, n_tasks, events, ev_cap, ctr);
 	return cudaGetLastError();
+}
+
+cudaError_t
+launch_walk(const uint8_t* text, const uint32_t* visit, const FilterView& bloom, const FilterView& rep, const KParams& kp, const Task* tasks,
+            uint32_t* order, TaskResult* results, uint32_t n_tasks, Event* events, uint32_t ev_cap, Counters* ctr, int sm_count,
+            cudaStream_t stream)
+{
+	if (order && n_tasks) {
+		order_tasks_kernel<<<(n_tasks + 255) / 256, 256, 0, stream>>>(visit, tasks, n_tasks, 24u, order, ctr);
+		cudaError_t e = cudaGetLastError();
+		if (e != cudaSuccess) {
+			return e;
+		}
+	}
+	if (kp.k <= 48) {
+		return launch_walk_n<160>(text, visit, bloom, rep, kp, tasks, order, results, n_tasks, events, ev_cap, ctr, sm_count, stream);
+	}
+	return launch_walk_n<352>(text, visit, bloom, rep, kp, tasks, order, results, n_tasks, events, ev_cap, ctr, sm_count, stream);
 }
 
 // ------------------------------------------------------------------------------------------------------------------

@@ -52,20 +52,14 @@ struct ScanArgs
 cudaError_t launch_scan(const ScanArgs& a, bool counting, bool extra, int grid, cudaStream_t stream);
 
 // K2 geometry: WALK_WARPS walkers per CTA, each with its own WalkerState in dynamic shared memory
-constexpr int WALK_NCAP = 352;
-constexpr int WALK_WARPS = 8;
+constexpr int WALK_WARPS = 4;
 constexpr int WALK_THREADS = WALK_WARPS * 32;
-using WalkState = WalkerState<WALK_NCAP>;
-inline size_t
-walk_smem_bytes()
-{
-	return (size_t)WALK_WARPS * sizeof(WalkState);
-}
 
-// launches walk_kernel on a persistent grid sized from the occupancy of the kernel
+// orders the tasks (dense ones first) into `order` (n_tasks entries, may be NULL = queue order) and launches the walker
+// kernel on a persistent grid sized from its occupancy; 2 launches
 cudaError_t launch_walk(const uint8_t* text, const uint32_t* visit, const FilterView& bloom, const FilterView& rep, const KParams& kp,
-                        const Task* tasks, TaskResult* results, uint32_t n_tasks, Event* events, uint32_t ev_cap, Counters* ctr, int sm_count,
-                        cudaStream_t stream);
+                        const Task* tasks, uint32_t* order, TaskResult* results, uint32_t n_tasks, Event* events, uint32_t ev_cap,
+                        Counters* ctr, int sm_count, cudaStream_t stream);
 
 __global__ void insert_kernel(const uint8_t* text, uint64_t total, uint8_t* data, FilterView f, const __grid_constant__ KParams kp);
 

@@ -114,6 +114,8 @@ struct Counters
 	uint32_t n_events;   // arena fill
 	uint32_t overflow;
 	uint32_t next_task;  // work queue of the persistent walker warps
+	uint32_t n_front;    // order_tasks_kernel: dense tasks placed so far (from the front of the queue)
+	uint32_t n_back;     // ... the others (from the back)
 	uint32_t pad_;
 };
 

@@ -75,8 +75,12 @@ struct HostBackend
 		results.resize(tasks.size());
 		events.assign(1u << 16, Event());
 		for (;;) {
-			Counters ctr = { 0, 0, 0, 0 };
+			Counters ctr = { 0, 0, 0, 0, 0, 0 };
 			WalkerState<352>* st = new WalkerState<352>();
+			std::vector<uint64_t> rot(ROT_WORDS);
+			for (uint32_t q = 0; q < ROT_WORDS; q++) {
+				rot[q] = rot_entry(q);
+			}
 			for (size_t i = 0; i < tasks.size(); i++) {
 				WalkerIO& io = st->io;
 				io.text = bases + tasks[i].text_off;
@@ -88,6 +92,7 @@ struct HostBackend
 				io.events = events.data();
 				io.ev_cap = (uint32_t)events.size();
 				io.ctr = &ctr;
+				io.rot = rot.data();
 				Walker<352> w(*st, kp);
 				w.run(tasks[i], results[i]);
 			}
