@@ -332,6 +332,16 @@ struct CudaBackend
 				}
 				std::fprintf(stderr, "[ntb] walk launch: %zu tasks, %.2f ms, sum %.1f Mcycles\n", n, ms_walk, tot / 1024.0);
 				{
+					static const char* names[16] = { "loop_head", "next_visit", "fill_cache", "seed", "lookahead", "dirty_misc", "evaluate_site",
+						                             "advance", "site_begin+linearise", "compute_plain", "phase1", "candidates", "try_indels",
+						                             "commit", "-", "-" };
+					for (int q = 0; q < 14; q++) {
+						if (ctr.prof[q]) {
+							std::fprintf(stderr, "[ntb]   phase %-22s %10.1f Mcycles\n", names[q], ctr.prof[q] / 1048576.0);
+						}
+					}
+				}
+				{
 					// cycles by number of sites in the task
 					const unsigned edges[7] = { 0, 1, 4, 8, 16, 32, 1u << 30 };
 					for (int b = 0; b < 6; b++) {

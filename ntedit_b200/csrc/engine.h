@@ -35,12 +35,25 @@ namespace ntb {
 #endif
 
 // ------------------------------------------------------------------------------------------------------------------
-// warp execution model (host build: a warp of one lane)
+// Execution model: a walker is run by a TEAM of NTB_TEAM consecutive lanes of a warp (NTB_TEAM = 32: the whole warp).
+// Several teams share a warp: their leader sections then execute as one SIMT instruction stream wherever the teams
+// take the same path, which divides the instruction-fetch and issue cost of the serial control code by the number of
+// teams.  Host build: a team of one lane.
+#if defined(__CUDACC__)
+#ifndef NTB_TEAM
+#define NTB_TEAM 32
+#endif
+#else
+#undef NTB_TEAM
+#define NTB_TEAM 1
+#endif
+static_assert(NTB_TEAM == 1 || NTB_TEAM == 2 || NTB_TEAM == 4 || NTB_TEAM == 8 || NTB_TEAM == 16 || NTB_TEAM == 32, "team size");
+
 NTB_FN inline uint32_t
 lane_id()
 {
 #if defined(__CUDA_ARCH__)
-	return threadIdx.x & 31u;
+	return threadIdx.x & (NTB_TEAM - 1u);
 #else
 	return 0;
 #endif
@@ -49,27 +62,37 @@ lane_id()
 NTB_FN inline uint32_t
 lane_count()
 {
-#if defined(__CUDA_ARCH__)
-	return 32u;
-#else
-	return 1u;
-#endif
+	return NTB_TEAM;
 }
+
+#if defined(__CUDACC__)
+// first lane of the team inside its warp, and the team's lane mask
+__device__ inline uint32_t
+team_base()
+{
+	return threadIdx.x & 31u & ~(NTB_TEAM - 1u);
+}
+__device__ inline uint32_t
+team_mask()
+{
+	return NTB_TEAM == 32 ? 0xFFFFFFFFu : (((1u << (NTB_TEAM & 31)) - 1u) << team_base());
+}
+#endif
 
 NTB_FN inline void
 warp_sync()
 {
 #if defined(__CUDA_ARCH__)
-	__syncwarp();
+	__syncwarp(team_mask());
 #endif
 }
 
-// smallest value of v over the lanes of the warp
+// smallest value of v over the lanes of the team
 NTB_FN inline uint32_t
 warp_min(uint32_t v)
 {
 #if defined(__CUDA_ARCH__)
-	return __reduce_min_sync(0xFFFFFFFFu, v);
+	return __reduce_min_sync(team_mask(), v);
 #else
 	return v;
 #endif
@@ -79,9 +102,8 @@ NTB_FN inline uint64_t
 warp_xor64(uint64_t v)
 {
 #if defined(__CUDA_ARCH__)
-	uint32_t lo = (uint32_t)v, hi = (uint32_t)(v >> 32);
-	lo = __reduce_xor_sync(0xFFFFFFFFu, lo);
-	hi = __reduce_xor_sync(0xFFFFFFFFu, hi);
+	const uint32_t lo = __reduce_xor_sync(team_mask(), (uint32_t)v);
+	const uint32_t hi = __reduce_xor_sync(team_mask(), (uint32_t)(v >> 32));
 	return ((uint64_t)hi << 32) | lo;
 #else
 	return v;
@@ -92,11 +114,27 @@ NTB_FN inline uint32_t
 warp_or(uint32_t v)
 {
 #if defined(__CUDA_ARCH__)
-	return __reduce_or_sync(0xFFFFFFFFu, v);
+	return __reduce_or_sync(team_mask(), v);
 #else
 	return v;
 #endif
 }
+
+// optional per-phase cycle accounting (tuning aid, -DNTB_PHASE_PROF): S.prof[p] accumulates the leader's clock
+#if defined(NTB_PHASE_PROF) && defined(__CUDA_ARCH__)
+#define NTB_PROF_T0 long long prof_t0_ = clock64();
+#define NTB_PROF(p)                                   \
+	do {                                              \
+		const long long prof_t1_ = clock64();         \
+		if (lane_id() == 0) {                         \
+			S.prof[p] += (uint32_t)(prof_t1_ - prof_t0_); \
+		}                                             \
+		prof_t0_ = prof_t1_;                          \
+	} while (0)
+#else
+#define NTB_PROF_T0
+#define NTB_PROF(p)
+#endif
 
 #define NTB_LEADER_BEGIN \
 	warp_sync();         \
@@ -147,12 +185,6 @@ struct WalkerIO
 	Counters* ctr;
 	const uint64_t* rot;       // ROT_WORDS entries, see rot_entry()
 };
-
-#if defined(__CUDACC__)
-#define NTB_LANES 32
-#else
-#define NTB_LANES 1
-#endif
 
 constexpr uint32_t MAX_INS_TRIES = 341;   // num_tries[5], ntedit.cpp:172
 constexpr uint32_t MAX_DELETIONS = 10;    // ntedit.cpp:2489-2493
@@ -242,10 +274,10 @@ struct WalkerState
 	uint8_t lin_in_c[KMAX + LOOKAHEAD + 2];
 	uint64_t seed_tab[8];                    // forward seeds by code (A C G T, none)
 	uint64_t rotk_tab[8];                    // srol^k of the same
-	uint64_t hb[PROBE_G][NTB_LANES];         // sampled k-mer hashes of every lane, waiting to be probed
-	uint32_t pv[PROBE_G][PROBE_HU][NTB_LANES]; // probed filter words (cp.async destinations)
-	uint8_t psh[PROBE_G][PROBE_HU][NTB_LANES]; // bit offset of the probed bit / counter inside the word
-	uint8_t pval[PROBE_G][NTB_LANES];        // filter value of each sampled k-mer
+	uint64_t hb[PROBE_G][NTB_TEAM];         // sampled k-mer hashes of every lane, waiting to be probed
+	uint32_t pv[PROBE_G][PROBE_HU][NTB_TEAM]; // probed filter words (cp.async destinations)
+	uint8_t psh[PROBE_G][PROBE_HU][NTB_TEAM]; // bit offset of the probed bit / counter inside the word
+	uint8_t pval[PROBE_G][NTB_TEAM];        // filter value of each sampled k-mer
 	uint32_t n_rolls;     // successful simulated rolls
 	uint32_t n_check;     // completed iterations of the check-missing loop
 	uint32_t patch_idx;   // index into lin_out[] that reads the tail's own slot
@@ -256,6 +288,7 @@ struct WalkerState
 	uint32_t cands;       // substitution candidates, packed
 	bool tail_is_pos, tail_is_chr, touched;
 	uint32_t next;        // what the candidate loop does next
+	uint32_t ci;          // substitution candidate being processed
 	unsigned char index_char;
 	Site s;
 	uint32_t num_deletions;
@@ -273,7 +306,10 @@ struct WalkerState
 	static constexpr int PLAIN_CAP = (NCAP <= 160 ? 48 : (int)KMAX) + (int)LOOKAHEAD + 2;
 	uint64_t plain_f[PLAIN_CAP], plain_r[PLAIN_CAP];
 	uint32_t n_plain;
-	uint8_t tflag[4][KMAX + 1]; // substitution trial: sampled k-mer present && solid
+	uint8_t tsolid[4][KMAX + 1]; // substitution trial, k-mer after R rolls (index R-1): present && solid
+	uint8_t tsite[4][KMAX + 1];  // ... the main loop would enter its edit block at that k-mer
+	bool p1_fast;                // phase 1 took the table path (tsolid / tsite are filled for every roll)
+	bool skip_advance;           // site_commit already moved the window to the next clean position
 	// insertion candidates without rolling: hash state after q+1 rolls of an insertion of length L whose inserted chars
 	// contribute nothing (ins_base_*[L-1][sample]); the candidates add their chars' terms from the rotation table
 	static constexpr int NSMAX = NCAP <= 160 ? 16 : 32;
@@ -287,6 +323,7 @@ struct WalkerState
 	bool ti_done, ti_ret;
 	// dirty-window lookahead: bit j = the main loop would enter its edit block after j more plain rolls
 	uint32_t la_bits, la_n, la_used, la_J;
+	uint32_t prof[16];
 };
 
 constexpr uint32_t ACT_STOP = 0, ACT_CLEAN = 1, ACT_DIRTY = 2;
@@ -1001,28 +1038,55 @@ struct Walker
 	NTB_FN void compute_plain(uint32_t want)
 	{
 		const uint32_t cap = (uint32_t)WalkerState<NCAP>::PLAIN_CAP - 1;
+		const uint32_t k = P.k;
 		uint32_t n = S.n_rolls < want ? S.n_rolls : want;
 		if (n > cap) {
 			n = cap;
 		}
 		warp_sync();
 		const uint32_t ln = lane_id();
-		if (ln == 0) {
-			uint64_t f = S.hs.fh;
-			S.plain_f[0] = f;
-			for (uint32_t r = 0; r < n; r++) {
-				f = srol1(f) ^ S.seed_tab[S.lin_in_c[r] & 7u] ^ S.rotk_tab[S.lin_out_c[r] & 7u];
-				S.plain_f[r + 1] = f;
+		bool direct = S.n_rolls >= k && k <= ROT_STRIDE;
+		if (direct) {
+			// the window after R rolls is lin_out[R..k) ++ lin_in[0..R): hash it from the rotation table, one window per lane
+			const uint64_t* rot = S.io.rot;
+			uint32_t bad = 0;
+			for (uint32_t R = ln; R <= n; R += lane_count()) {
+				uint64_t f = 0, r = 0;
+				for (uint32_t i = 0; i < k; i++) {
+					const uint32_t m = R + i;
+					const uint32_t c = m < k ? S.lin_out_c[m] : S.lin_in_c[m - k];
+					f ^= rot[(c & 7u) * ROT_STRIDE + (k - 1 - i)];
+					r ^= rot[((c >> 3) & 7u) * ROT_STRIDE + i];
+				}
+				S.plain_f[R] = f;
+				S.plain_r[R] = r;
+				if (R == 0 && (f != S.hs.fh || r != S.hs.rh)) {
+					bad = 1; // the rolled state is not the hash of the window's chars: roll instead
+				}
 			}
-			S.n_plain = n;
+			direct = warp_or(bad) == 0;
 		}
-		if (ln == (lane_count() > 1 ? 1u : 0u)) {
-			uint64_t rv = S.hs.rh;
-			S.plain_r[0] = rv;
-			for (uint32_t r = 0; r < n; r++) {
-				rv = sror1(rv ^ S.rotk_tab[(S.lin_in_c[r] >> 3) & 7u] ^ S.seed_tab[(S.lin_out_c[r] >> 3) & 7u]);
-				S.plain_r[r + 1] = rv;
+		if (!direct) {
+			warp_sync();
+			if (ln == 0) {
+				uint64_t f = S.hs.fh;
+				S.plain_f[0] = f;
+				for (uint32_t r = 0; r < n; r++) {
+					f = srol1(f) ^ S.seed_tab[S.lin_in_c[r] & 7u] ^ S.rotk_tab[S.lin_out_c[r] & 7u];
+					S.plain_f[r + 1] = f;
+				}
 			}
+			if (ln == (lane_count() > 1 ? 1u : 0u)) {
+				uint64_t rv = S.hs.rh;
+				S.plain_r[0] = rv;
+				for (uint32_t r = 0; r < n; r++) {
+					rv = sror1(rv ^ S.rotk_tab[(S.lin_in_c[r] >> 3) & 7u] ^ S.seed_tab[(S.lin_out_c[r] >> 3) & 7u]);
+					S.plain_r[r + 1] = rv;
+				}
+			}
+		}
+		if (ln == 0) {
+			S.n_plain = n;
 		}
 		warp_sync();
 	}
@@ -1037,12 +1101,13 @@ struct Walker
 		const uint32_t k = P.k, jump = P.jump, ln = lane_id();
 		const uint32_t n_sub = S.n_rolls < k ? S.n_rolls : k;
 		const uint32_t nC = S.n_check ? (S.n_check - 1) / jump + 1 : 0;   // samples q = 0, jump, .. < n_check
-		const uint32_t nT = n_sub ? (n_sub - 1) / jump + 1 : 0;           // samples q = 0, jump, .. < n_sub
 		uint32_t ncand = 0;
 		while (ncand < 4 && ((S.cands >> (8 * ncand)) & 0xFF) != 0) {
 			ncand++;
 		}
-		const uint32_t per_cand = 1 + nT; // gate + trial samples
+		// per candidate: the gate (R = 0) and the k-mer after every roll R = 1 .. n_sub -- the sampled ones are the trial
+		// (ntedit.cpp:1960-1968), all of them are the windows the main loop visits next if the candidate is accepted
+		const uint32_t per_cand = 1 + n_sub;
 		const uint32_t njobs = nC + ncand * per_cand;
 		const uint32_t df = base_code(S.draft), dr = rev_code(S.draft);
 		const uint64_t* rot = S.io.rot;
@@ -1057,9 +1122,8 @@ struct Walker
 					f = S.plain_f[R];
 					r = S.plain_r[R];
 				} else {
-					const uint32_t c = (j - nC) / per_cand, w = (j - nC) % per_cand;
+					const uint32_t c = (j - nC) / per_cand, R = (j - nC) % per_cand;
 					const unsigned char X = (unsigned char)((S.cands >> (8 * c)) & 0xFF);
-					const uint32_t R = w == 0 ? 0 : (w - 1) * jump + 1;
 					f = S.plain_f[R];
 					r = S.plain_r[R];
 					if (R < k) {
@@ -1073,16 +1137,18 @@ struct Walker
 			if (ng) {
 				probe_values(S.io.bloom, ng, (1u << ng) - 1u, PROBE_HU);
 				// solid k-mers additionally must be absent from the secondary filter (-e), ntedit.cpp:467-468
-				uint32_t solid = 0;
+				uint32_t solid = 0, site = 0;
 				uint32_t g = 0;
+				uint32_t raw[PROBE_G];
 				for (uint32_t j = j0 + ln; j < njobs && g < ng; j += lane_count(), g++) {
-					if (j >= nC && solid_value(S.pval[g][ln])) {
+					const uint32_t v = S.pval[g][ln];
+					raw[g] = v;
+					if (j >= nC && solid_value(v)) {
 						solid |= 1u << g;
 					}
-				}
-				uint32_t raw[PROBE_G];
-				for (uint32_t q = 0; q < ng; q++) {
-					raw[q] = S.pval[q][ln];
+					if (is_site_value(v)) {
+						site |= 1u << g;
+					}
 				}
 				if (P.h_rep && solid) {
 					probe_values(S.io.rep, ng, solid, PROBE_HU);
@@ -1097,12 +1163,13 @@ struct Walker
 					if (j < nC) {
 						S.chk[j] = (uint8_t)raw[g];
 					} else {
-						const uint32_t c = (j - nC) / per_cand, w = (j - nC) % per_cand;
+						const uint32_t c = (j - nC) / per_cand, R = (j - nC) % per_cand;
 						const uint8_t ok = (uint8_t)((solid >> g) & 1u);
-						if (w == 0) {
+						if (R == 0) {
 							S.gate[c] = ok;
 						} else {
-							S.tflag[c][w - 1] = ok;
+							S.tsolid[c][R - 1] = ok;
+							S.tsite[c][R - 1] = (uint8_t)((site >> g) & 1u);
 						}
 					}
 				}
@@ -1111,11 +1178,12 @@ struct Walker
 		warp_sync();
 		NTB_LEADER_BEGIN
 		S.chk_n = nC;
+		S.p1_fast = true;
 		for (uint32_t c = 0; c < 4; c++) {
 			uint32_t cnt = 0;
 			if (c < ncand) {
-				for (uint32_t w = 0; w < nT; w++) {
-					cnt += S.tflag[c][w];
+				for (uint32_t q = 0; q < n_sub; q += jump) {
+					cnt += S.tsolid[c][q];
 				}
 			} else {
 				S.gate[c] = 0;
@@ -1347,12 +1415,30 @@ struct Walker
 		while (S.ti_i0 < T) {
 			// first hit wins in mode 0: evaluate one warp's worth of candidates at a time
 			const uint32_t i0 = S.ti_i0;
-			const uint32_t i1 = (P.mode == 0 && i0 + lane_count() * 1u < T && lane_count() > 1) ? i0 + lane_count()
-			                    : (P.mode == 0 && lane_count() == 1 && i0 + 32 < T)            ? i0 + 32
-			                                                                                   : T;
+			const uint32_t i1 = (P.mode == 0 && i0 + 32 < T) ? i0 + 32 : T;
 			phase_insertions(i0, i1);
+			// does any candidate of the chunk reach its threshold?  (usually none does)
+			uint32_t any = 0;
+			for (uint32_t i = i0 + lane_id(); i < i1; i += lane_count()) {
+				if (meets_edit(S.ins_sup[i])) {
+					any = 1;
+				}
+			}
+			for (uint32_t n = S.num_deletions + lane_id(); n <= P.max_deletions && n - S.num_deletions < i1 - i0; n += lane_count()) {
+				if (S.del_sup[n] >= P.thr_edit_del && S.del_sup[n] > 0) {
+					any = 1;
+				}
+			}
+			any = warp_or(any);
 			NTB_LEADER_BEGIN
-			for (uint32_t i = i0; i < i1; i++) {
+			if (!any) {
+				// nothing to select: only the shared deletion counter advances, once per iteration (ntedit.cpp:1692-1729)
+				if (S.num_deletions <= P.max_deletions) {
+					const uint32_t left = P.max_deletions + 1 - S.num_deletions;
+					S.num_deletions += left < i1 - i0 ? left : i1 - i0;
+				}
+			}
+			for (uint32_t i = any ? i0 : i1; i < i1; i++) {
 				const uint32_t present = S.ins_sup[i];
 				if (meets_edit(present)) {
 					uint64_t packed;
@@ -1443,6 +1529,8 @@ struct Walker
 		S.site_ok = true;
 		S.chk_n = 0;
 		S.bases_ready = false;
+		S.p1_fast = false;
+		S.skip_advance = false;
 	}
 
 	// leader: check-missing verdict (ntedit.cpp:1859-1873) and the site locals (ntedit.cpp:1876-1914)
@@ -1622,6 +1710,28 @@ struct Walker
 			}
 			hash_changelast(S.hs, draft, s.best_sub, P);
 			S.la_n = 0;
+			if (S.p1_fast && !P.snv && S.lin_simple && S.tail_is_pos && !S.dnf && S.n_check == P.k && S.n_rolls >= P.k) {
+				// The next k-1 windows contain the substituted base, the k-th is clean again.  Phase 1 probed all of them
+				// for every candidate: when none is a site for the accepted base (and the k incoming bases are accepted --
+				// n_check == k), rolling through them one by one (ntedit.cpp:2118-2138) has no observable effect: jump.
+				uint32_t c = 0;
+				while (c < 4 && ((S.cands >> (8 * c)) & 0xFF) != s.best_sub) {
+					c++;
+				}
+				bool quiet = c < 4;
+				for (uint32_t R = 1; quiet && R + 1 <= P.k; R++) {
+					if (S.tsite[c][R - 1]) {
+						quiet = false;
+					}
+				}
+				if (quiet) {
+					S.h.pos += P.k;
+					S.t.pos += P.k;
+					S.adv += P.k;
+					S.need_seed = true; // the window is clean: the hash is re-seeded at the next flagged position
+					S.skip_advance = true;
+				}
+			}
 			break;
 		case 2: {
 			emit(2, fl, draft, s);
@@ -1652,41 +1762,62 @@ struct Walker
 	// returns false when the contig is finished (insertion guard fired)
 	NTB_FN bool evaluate_site()
 	{
+		NTB_PROF_T0
 		NTB_LEADER_BEGIN
 		site_begin();
 		NTB_LEADER_END
 		linearise(P.k + MAX_DELETIONS + 1, true);
+		NTB_PROF(8);
 		if (!P.snv && S.dnf) {
 			return true; // no attempt is possible (ntedit.cpp:1865): the subset counts are not needed
 		}
 		if (S.patch_idx == P.k - 1 && P.k + 1 < ROT_STRIDE) {
 			compute_plain(P.k);
+			NTB_PROF(9);
 			phase_check_and_subs_fast();
 		} else {
 			phase_check_and_subs();
 		}
+		NTB_PROF(10);
 		NTB_LEADER_BEGIN
 		S.next = site_after_check() ? NEXT_CAND : NEXT_STOP;
 		NTB_LEADER_END
 		if (S.next == NEXT_STOP) {
 			return true;
 		}
-		for (uint32_t ci = 0; ci < 4; ci++) {
+		NTB_LEADER_BEGIN
+		S.ci = 0;
+		NTB_LEADER_END
+		for (;;) {
+			// the leader walks the substitution candidates until one needs tryIndels (a warp-wide phase)
 			NTB_LEADER_BEGIN
-			site_candidate(ci);
-			NTB_LEADER_END
-			if (S.next == NEXT_STOP) {
-				break;
-			}
-			if (S.next == NEXT_INDELS) {
-				if (try_indels() && (P.mode == 0 || P.mode == 1)) {
+			S.next = NEXT_STOP;
+			for (; S.ci < 4; S.ci++) {
+				site_candidate(S.ci);
+				if (S.next != NEXT_CAND) {
 					break;
 				}
+				S.next = NEXT_STOP;
 			}
+			NTB_LEADER_END
+			if (S.next != NEXT_INDELS) {
+				break;
+			}
+			NTB_PROF(11);
+			const bool hit = try_indels();
+			NTB_PROF(12);
+			if (hit && (P.mode == 0 || P.mode == 1)) {
+				break;
+			}
+			NTB_LEADER_BEGIN
+			S.ci++;
+			NTB_LEADER_END
 		}
+		NTB_PROF(11);
 		NTB_LEADER_BEGIN
 		site_commit();
 		NTB_LEADER_END
+		NTB_PROF(13);
 		return S.site_ok;
 	}
 
@@ -1731,10 +1862,10 @@ struct Walker
 				bits &= 0xFFFFFFFFu << (g & 31);
 			}
 #if defined(__CUDA_ARCH__)
-			const uint32_t any = __ballot_sync(0xFFFFFFFFu, bits != 0);
+			const uint32_t any = __ballot_sync(team_mask(), bits != 0) >> team_base();
 			if (any) {
 				const int src = __ffs((int)any) - 1;
-				const uint32_t b = __shfl_sync(0xFFFFFFFFu, bits, src);
+				const uint32_t b = __shfl_sync(team_mask(), bits, (int)team_base() + src);
 				const uint64_t hit = ((w0 + (uint64_t)src) << 5) + (uint32_t)(__ffs((int)b) - 1);
 				return hit < gend ? (uint32_t)(hit - S.io.goff) : NONE32;
 			}
@@ -2058,14 +2189,17 @@ struct Walker
 		if (S.act == ACT_STOP) {
 			return false;
 		}
+		NTB_PROF_T0
 		NTB_LEADER_BEGIN
 		loop_head(task);
 		NTB_LEADER_END
+		NTB_PROF(0);
 		if (S.act == ACT_STOP) {
 			return false;
 		}
 		if (S.act == ACT_CLEAN) {
 			const uint32_t nv = next_visit(S.t.pos, task.end);
+			NTB_PROF(1);
 			NTB_LEADER_BEGIN
 			if (nv == NONE32) {
 				S.end_pos = task.end;
@@ -2086,9 +2220,28 @@ struct Walker
 			if (!cache_covers_window()) {
 				fill_cache(S.h.pos);
 			}
+			NTB_PROF(2);
+			uint64_t seed_f = 0, seed_r = 0;
+			if (S.do_seed) {
+				// NTMC64 seeding form (ntedit.cpp:403-416) of the unedited window that ends at the flagged position:
+				// every lane contributes its bases' terms from the rotation table
+				const uint32_t k = P.k, head = S.visit_hit + 1 - k;
+				const uint64_t* rot = S.io.rot;
+				for (uint32_t i = lane_id(); i < k; i += lane_count()) {
+					const unsigned char c = text_at(head + i);
+					seed_f ^= rot[base_code(c) * ROT_STRIDE + (k - 1 - i)];
+					seed_r ^= rot[rev_code(c) * ROT_STRIDE + i];
+				}
+				seed_f = warp_xor64(seed_f);
+				seed_r = warp_xor64(seed_r);
+			}
 			NTB_LEADER_BEGIN
 			if (S.do_seed) {
-				seed_at(S.visit_hit);
+				S.h.pos = S.visit_hit + 1 - P.k;
+				S.t.pos = S.visit_hit;
+				S.hs.fh = seed_f;
+				S.hs.rh = seed_r;
+				S.char_in = text_at(S.visit_hit);
 				reset_rope(S.h.pos);
 				S.site_now = true; // K1 flagged this very window
 			} else if (P.snv) {
@@ -2099,6 +2252,7 @@ struct Walker
 				S.site_now = !q_contains(S.hs);
 			}
 			NTB_LEADER_END
+			NTB_PROF(3);
 		} else {
 			if (!cache_covers_window()) {
 				fill_cache(S.h.pos);
@@ -2110,6 +2264,7 @@ struct Walker
 			} else {
 				if (S.la_used >= S.la_n) {
 					lookahead();
+					NTB_PROF(4);
 					if (S.jumped) {
 						return true; // now on a clean window: back to the top of the main loop
 					}
@@ -2119,6 +2274,7 @@ struct Walker
 				NTB_LEADER_END
 			}
 		}
+		NTB_PROF(5);
 		if (S.site_now) {
 			if (!evaluate_site()) {
 				NTB_LEADER_BEGIN
@@ -2128,9 +2284,15 @@ struct Walker
 				return false;
 			}
 		}
+		NTB_PROF(6);
 		NTB_LEADER_BEGIN
-		advance();
+		if (S.site_now && S.skip_advance) {
+			S.skip_advance = false;
+		} else {
+			advance();
+		}
 		NTB_LEADER_END
+		NTB_PROF(7);
 		return S.act != ACT_STOP;
 	}
 

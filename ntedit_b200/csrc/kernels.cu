@@ -335,30 +335,31 @@ walk_kernel(const uint8_t* text, const uint32_t* visit, FilterView bloom, Filter
 {
 	extern __shared__ __align__(16) uint8_t walk_smem[];
 	WalkerState<NCAP>* states = reinterpret_cast<WalkerState<NCAP>*>(walk_smem);
-	WalkerState<NCAP>& S = states[threadIdx.x >> 5];
-	uint64_t* rot = reinterpret_cast<uint64_t*>(walk_smem + (size_t)WALK_WARPS * sizeof(WalkerState<NCAP>));
+	WalkerState<NCAP>& S = states[threadIdx.x / NTB_TEAM];
+	uint64_t* rot = reinterpret_cast<uint64_t*>(walk_smem + (size_t)WALK_TEAMS * sizeof(WalkerState<NCAP>));
 	for (uint32_t q = threadIdx.x; q < ROT_WORDS; q += WALK_THREADS) {
 		rot[q] = rot_entry(q);
 	}
 	__syncthreads();
-	const uint32_t lane = threadIdx.x & 31u;
+	const uint32_t lane = lane_id();
 	Walker<NCAP> w(S, kp);
 	bool have = false;
 	uint32_t i = 0;
 	Task task;
 	long long c0 = 0;
+	// every team runs its own task; the teams of a warp re-converge at the top of each iteration
 	for (;;) {
 		if (!have) {
 			if (lane == 0) {
 				i = atomicAdd(&ctr->next_task, 1u);
 			}
-			i = __shfl_sync(0xFFFFFFFFu, i, 0);
+			i = __shfl_sync(team_mask(), i, (int)team_base());
 			if (i < n_tasks) {
 				if (order) {
 					i = order[i];
 				}
 				task = tasks[i];
-				__syncwarp();
+				warp_sync();
 				if (lane == 0) {
 					S.io.text = text + task.text_off;
 					S.io.len = task.len;
@@ -371,8 +372,15 @@ walk_kernel(const uint8_t* text, const uint32_t* visit, FilterView bloom, Filter
 					S.io.ctr = ctr;
 					S.io.rot = rot;
 				}
-				__syncwarp();
+				warp_sync();
 				c0 = clock64();
+#if defined(NTB_PHASE_PROF)
+				if (lane == 0) {
+					for (int q = 0; q < 16; q++) {
+						S.prof[q] = 0;
+					}
+				}
+#endif
 				w.begin(task);
 				have = true;
 			}
@@ -386,6 +394,11 @@ walk_kernel(const uint8_t* text, const uint32_t* visit, FilterView bloom, Filter
 			if (lane == 0) {
 				res.kcycles = (uint32_t)((clock64() - c0) >> 10);
 				results[i] = res;
+#if defined(NTB_PHASE_PROF)
+				for (int q = 0; q < 16; q++) {
+					atomicAdd(&ctr->prof[q], (unsigned long long)S.prof[q]);
+				}
+#endif
 			}
 			have = false;
 		}
@@ -428,7 +441,7 @@ launch_walk_n(const uint8_t* text, const uint32_t* visit, const FilterView& bloo
               cudaStream_t stream)
 {
 	static int blocks_per_sm = 0;
-	const size_t smem = (size_t)WALK_WARPS * sizeof(WalkerState<NCAP>) + ROT_WORDS * sizeof(uint64_t);
+	const size_t smem = (size_t)WALK_TEAMS * sizeof(WalkerState<NCAP>) + ROT_WORDS * sizeof(uint64_t);
 	if (blocks_per_sm == 0) {
 		cudaError_t e = cudaFuncSetAttribute(walk_kernel<NCAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 		if (e != cudaSuccess) {
@@ -447,7 +460,7 @@ launch_walk_n(const uint8_t* text, const uint32_t* visit, const FilterView& bloo
 			}
 		}
 	}
-	const uint64_t want = ((uint64_t)n_tasks + WALK_WARPS - 1) / WALK_WARPS;
+	const uint64_t want = ((uint64_t)n_tasks + WALK_TEAMS - 1) / WALK_TEAMS;
 	const uint64_t cap = (uint64_t)sm_count * (uint64_t)blocks_per_sm;
 	const unsigned grid = (unsigned)(want < cap ? want : cap);
 	if (grid == 0) {

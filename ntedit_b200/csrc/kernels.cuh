@@ -51,9 +51,13 @@ struct ScanArgs
 // launches scan_kernel<hash_num, counting, extra> on `grid` persistent CTAs
 cudaError_t launch_scan(const ScanArgs& a, bool counting, bool extra, int grid, cudaStream_t stream);
 
-// K2 geometry: WALK_WARPS walkers per CTA, each with its own WalkerState in dynamic shared memory
-constexpr int WALK_WARPS = 4;
+// K2 geometry: WALK_TEAMS walkers per CTA, each with its own WalkerState in dynamic shared memory
+#ifndef NTB_WALK_WARPS
+#define NTB_WALK_WARPS 2
+#endif
+constexpr int WALK_WARPS = NTB_WALK_WARPS;
 constexpr int WALK_THREADS = WALK_WARPS * 32;
+constexpr int WALK_TEAMS = WALK_THREADS / NTB_TEAM;   // walkers per CTA (engine.h: a team of NTB_TEAM lanes runs one walker)
 
 // orders the tasks (dense ones first) into `order` (n_tasks entries, may be NULL = queue order) and launches the walker
 // kernel on a persistent grid sized from its occupancy; 2 launches

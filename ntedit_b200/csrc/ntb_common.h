@@ -117,6 +117,7 @@ struct Counters
 	uint32_t n_front;    // order_tasks_kernel: dense tasks placed so far (from the front of the queue)
 	uint32_t n_back;     // ... the others (from the back)
 	uint32_t pad_;
+	unsigned long long prof[16]; // -DNTB_PHASE_PROF: leader cycles per phase of the walker
 };
 
 } // namespace ntb

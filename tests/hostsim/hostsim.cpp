@@ -75,7 +75,7 @@ struct HostBackend
 		results.resize(tasks.size());
 		events.assign(1u << 16, Event());
 		for (;;) {
-			Counters ctr = { 0, 0, 0, 0, 0, 0 };
+			Counters ctr = {};
 			WalkerState<352>* st = new WalkerState<352>();
 			std::vector<uint64_t> rot(ROT_WORDS);
 			for (uint32_t q = 0; q < ROT_WORDS; q++) {
