@@ -151,22 +151,101 @@ fill_scan_tables(ScanArgs& a, uint32_t k)
 	}
 }
 
+// Device + pinned-host scratch of one polishing call.  Grow-only and cached per device in a small pool so that
+// back-to-back calls (the reference's OpenMP loop makes one per contig batch) do not pay cudaMalloc / cudaFree /
+// cudaHostAlloc again; concurrent calls from different host threads each check out their own workspace.
+struct Workspace
+{
+	int device = 0;
+	cudaStream_t stream = nullptr;
+	cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+	uint32_t* d_visit = nullptr;
+	size_t cap_visit = 0; // words
+	Task* d_tasks = nullptr;
+	uint32_t* d_order = nullptr;
+	TaskResult* d_results = nullptr;
+	size_t cap_tasks = 0;
+	Event* d_events = nullptr;
+	size_t cap_events = 0;
+	Counters* d_ctr = nullptr;
+	// pinned host mirrors
+	Task* h_tasks = nullptr;
+	TaskResult* h_results = nullptr;
+	size_t cap_h_tasks = 0;
+	Event* h_events = nullptr;
+	size_t cap_h_events = 0;
+	Counters* h_ctr = nullptr;
+
+	~Workspace()
+	{
+		cudaSetDevice(device);
+		cudaFree(d_visit);
+		cudaFree(d_tasks);
+		cudaFree(d_order);
+		cudaFree(d_results);
+		cudaFree(d_events);
+		cudaFree(d_ctr);
+		cudaFreeHost(h_tasks);
+		cudaFreeHost(h_results);
+		cudaFreeHost(h_events);
+		cudaFreeHost(h_ctr);
+		if (ev0) {
+			cudaEventDestroy(ev0);
+		}
+		if (ev1) {
+			cudaEventDestroy(ev1);
+		}
+		if (stream) {
+			cudaStreamDestroy(stream);
+		}
+	}
+};
+
+std::mutex g_pool_mutex;
+std::vector<Workspace*> g_pool;
+
+Workspace*
+workspace_acquire(int device)
+{
+	{
+		std::lock_guard<std::mutex> lock(g_pool_mutex);
+		for (size_t i = 0; i < g_pool.size(); i++) {
+			if (g_pool[i]->device == device) {
+				Workspace* w = g_pool[i];
+				g_pool.erase(g_pool.begin() + (long)i);
+				return w;
+			}
+		}
+	}
+	Workspace* w = new (std::nothrow) Workspace();
+	if (w) {
+		w->device = device;
+	}
+	return w;
+}
+
+void
+workspace_release(Workspace* w)
+{
+	if (!w) {
+		return;
+	}
+	std::lock_guard<std::mutex> lock(g_pool_mutex);
+	if (g_pool.size() >= 8) {
+		delete w;
+	} else {
+		g_pool.push_back(w);
+	}
+}
+
 // CUDA implementation of the Backend concept of polish_driver.hpp
 struct CudaBackend
 {
 	ntb_filter* bloom;
 	ntb_filter* rep;
 	ntb_batch* batch;
-	cudaStream_t stream = 0;
-	uint32_t* d_visit = nullptr;
-	Task* d_tasks = nullptr;
-	uint32_t* d_order = nullptr;
-	TaskResult* d_results = nullptr;
-	Event* d_events = nullptr;
-	Counters* d_ctr = nullptr;
-	size_t cap_tasks = 0;
-	size_t cap_events = 0;
-	cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+	Workspace* ws = nullptr;
+	size_t ev_used = 0; // events of earlier rounds kept in ws->h_events
 	float ms_scan = 0, ms_walk = 0, ms_d2h = 0;
 	uint32_t launches = 0;
 	std::string err;
@@ -191,28 +270,32 @@ struct CudaBackend
 
 	int init()
 	{
-		NTB_BE(cudaEventCreate(&ev0));
-		NTB_BE(cudaEventCreate(&ev1));
-		NTB_BE(cudaMalloc((void**)&d_visit, batch->n_tiles * SCAN_BITWORDS * 4 + 64));
-		NTB_BE(cudaMalloc((void**)&d_ctr, sizeof(Counters)));
+		ws = workspace_acquire(batch->device);
+		if (!ws) {
+			err = "out of memory";
+			return rc = NTB_ENOMEM;
+		}
+		if (!ws->stream) {
+			NTB_BE(cudaStreamCreateWithFlags(&ws->stream, cudaStreamNonBlocking));
+			NTB_BE(cudaEventCreate(&ws->ev0));
+			NTB_BE(cudaEventCreate(&ws->ev1));
+			NTB_BE(cudaMalloc((void**)&ws->d_ctr, sizeof(Counters)));
+			NTB_BE(cudaHostAlloc((void**)&ws->h_ctr, sizeof(Counters), cudaHostAllocDefault));
+		}
+		const size_t words = batch->n_tiles * SCAN_BITWORDS + 16;
+		if (words > ws->cap_visit) {
+			cudaFree(ws->d_visit);
+			ws->d_visit = nullptr;
+			ws->cap_visit = 0;
+			NTB_BE(cudaMalloc((void**)&ws->d_visit, words * 4));
+			ws->cap_visit = words;
+		}
+		// the batch was uploaded on the default stream
+		NTB_BE(cudaStreamSynchronize(0));
 		return NTB_OK;
 	}
 
-	~CudaBackend()
-	{
-		cudaFree(d_visit);
-		cudaFree(d_tasks);
-		cudaFree(d_order);
-		cudaFree(d_results);
-		cudaFree(d_events);
-		cudaFree(d_ctr);
-		if (ev0) {
-			cudaEventDestroy(ev0);
-		}
-		if (ev1) {
-			cudaEventDestroy(ev1);
-		}
-	}
+	~CudaBackend() { workspace_release(ws); }
 
 	int scan_impl(const KParams& kp)
 	{
@@ -224,37 +307,72 @@ struct CudaBackend
 		a.k = kp.k;
 		a.min_threshold = kp.min_threshold;
 		a.snv = (uint32_t)kp.snv;
-		a.visit = d_visit;
+		a.visit = ws->d_visit;
 		fill_scan_tables(a, kp.k);
 		const int grid = (int)std::min<uint64_t>(batch->n_tiles, (uint64_t)sm_count(batch->device) * 3);
-		NTB_BE(cudaEventRecord(ev0, stream));
+		NTB_BE(cudaEventRecord(ws->ev0, ws->stream));
 		if (grid > 0) {
-			NTB_BE(launch_scan(a, bloom->counting != 0, false, grid, stream));
+			NTB_BE(launch_scan(a, bloom->counting != 0, false, grid, ws->stream));
 			launches++;
 		}
-		NTB_BE(cudaEventRecord(ev1, stream));
-		NTB_BE(cudaEventSynchronize(ev1));
+		NTB_BE(cudaEventRecord(ws->ev1, ws->stream));
+		return NTB_OK;
+	}
+
+	int scan_wait()
+	{
+		NTB_BE(cudaEventSynchronize(ws->ev1));
 		float ms = 0;
-		NTB_BE(cudaEventElapsedTime(&ms, ev0, ev1));
+		NTB_BE(cudaEventElapsedTime(&ms, ws->ev0, ws->ev1));
 		ms_scan += ms;
 		return NTB_OK;
 	}
 
-	void scan_visit(const KParams& kp)
+	void scan_begin(const KParams& kp)
 	{
 		if (rc == NTB_OK) {
 			scan_impl(kp);
 		}
 	}
 
-	int walk(const KParams& kp, const std::vector<Task>& tasks, std::vector<TaskResult>& results, std::vector<Event>& events)
+	void scan_end()
+	{
+		if (rc == NTB_OK) {
+			scan_wait();
+		}
+	}
+
+	Task* task_buffer(size_t n)
+	{
+		if (rc != NTB_OK) {
+			return nullptr;
+		}
+		if (n > ws->cap_h_tasks) {
+			cudaFreeHost(ws->h_tasks);
+			cudaFreeHost(ws->h_results);
+			ws->h_tasks = nullptr;
+			ws->h_results = nullptr;
+			ws->cap_h_tasks = 0;
+			const size_t want = n + n / 8 + 1024;
+			if (cudaHostAlloc((void**)&ws->h_tasks, want * sizeof(Task), cudaHostAllocDefault) != cudaSuccess ||
+			    cudaHostAlloc((void**)&ws->h_results, want * sizeof(TaskResult), cudaHostAllocDefault) != cudaSuccess) {
+				err = "cudaHostAlloc(tasks) failed";
+				rc = NTB_ENOMEM;
+				return nullptr;
+			}
+			ws->cap_h_tasks = want;
+		}
+		return ws->h_tasks;
+	}
+
+	int walk(const KParams& kp, size_t n, const TaskResult** res_out, const Event** ev_out, size_t* n_ev_out)
 	{
 		if (rc != NTB_OK) {
 			return rc;
 		}
-		const size_t n = tasks.size();
-		results.resize(n);
-		events.clear();
+		*res_out = ws->h_results;
+		*ev_out = ws->h_events + ev_used;
+		*n_ev_out = 0;
 		if (n == 0) {
 			return NTB_OK;
 		}
@@ -262,25 +380,28 @@ struct CudaBackend
 			err = "too many segments in one batch";
 			return rc = NTB_EINVAL;
 		}
-		if (n > cap_tasks) {
-			cudaFree(d_tasks);
-			cudaFree(d_results);
-			cudaFree(d_order);
-			d_tasks = nullptr;
-			d_results = nullptr;
-			d_order = nullptr;
-			NTB_BE(cudaMalloc((void**)&d_order, n * sizeof(uint32_t)));
-			NTB_BE(cudaMalloc((void**)&d_tasks, n * sizeof(Task)));
-			NTB_BE(cudaMalloc((void**)&d_results, n * sizeof(TaskResult)));
-			cap_tasks = n;
+		cudaStream_t stream = ws->stream;
+		if (n > ws->cap_tasks) {
+			cudaFree(ws->d_tasks);
+			cudaFree(ws->d_results);
+			cudaFree(ws->d_order);
+			ws->d_tasks = nullptr;
+			ws->d_results = nullptr;
+			ws->d_order = nullptr;
+			ws->cap_tasks = 0;
+			const size_t want = n + n / 8 + 1024;
+			NTB_BE(cudaMalloc((void**)&ws->d_order, want * sizeof(uint32_t)));
+			NTB_BE(cudaMalloc((void**)&ws->d_tasks, want * sizeof(Task)));
+			NTB_BE(cudaMalloc((void**)&ws->d_results, want * sizeof(TaskResult)));
+			ws->cap_tasks = want;
 		}
-		if (cap_events == 0) {
+		if (ws->cap_events == 0) {
 			// sized for the recipe's ~1.1e-3 edits per base with headroom; grown on overflow
-			size_t want = std::max<size_t>(1u << 16, (size_t)(batch->total / 96));
-			NTB_BE(cudaMalloc((void**)&d_events, want * sizeof(Event)));
-			cap_events = want;
+			const size_t want = std::max<size_t>(1u << 16, (size_t)(batch->total / 256));
+			NTB_BE(cudaMalloc((void**)&ws->d_events, want * sizeof(Event)));
+			ws->cap_events = want;
 		}
-		NTB_BE(cudaMemcpyAsync(d_tasks, tasks.data(), n * sizeof(Task), cudaMemcpyHostToDevice, stream));
+		NTB_BE(cudaMemcpyAsync(ws->d_tasks, ws->h_tasks, n * sizeof(Task), cudaMemcpyHostToDevice, stream));
 		const FilterView fb = bloom->view();
 		FilterView fr;
 		std::memset(&fr, 0, sizeof fr);
@@ -288,84 +409,102 @@ struct CudaBackend
 			fr = rep->view();
 		}
 		for (;;) {
-			NTB_BE(cudaMemsetAsync(d_ctr, 0, sizeof(Counters), stream));
-			NTB_BE(cudaEventRecord(ev0, stream));
-			NTB_BE(launch_walk(batch->d_text, d_visit, fb, fr, kp, d_tasks, d_order, d_results, (uint32_t)n, d_events,
-			                   (uint32_t)std::min<size_t>(cap_events, 0xFFFFFFF0u), d_ctr, sm_count(batch->device), stream));
+			NTB_BE(cudaMemsetAsync(ws->d_ctr, 0, sizeof(Counters), stream));
+			NTB_BE(cudaEventRecord(ws->ev0, stream));
+			NTB_BE(launch_walk(batch->d_text, ws->d_visit, fb, fr, kp, ws->d_tasks, ws->d_order, ws->d_results, (uint32_t)n, ws->d_events,
+			                   (uint32_t)std::min<size_t>(ws->cap_events, 0xFFFFFFF0u), ws->d_ctr, sm_count(batch->device), stream));
 			launches += 2; // order_tasks_kernel + walk_kernel
-			NTB_BE(cudaEventRecord(ev1, stream));
-			Counters ctr;
-			NTB_BE(cudaMemcpyAsync(&ctr, d_ctr, sizeof ctr, cudaMemcpyDeviceToHost, stream));
+			NTB_BE(cudaEventRecord(ws->ev1, stream));
+			NTB_BE(cudaMemcpyAsync(ws->h_ctr, ws->d_ctr, sizeof(Counters), cudaMemcpyDeviceToHost, stream));
 			NTB_BE(cudaStreamSynchronize(stream));
+			const Counters ctr = *ws->h_ctr;
 			float ms = 0;
-			NTB_BE(cudaEventElapsedTime(&ms, ev0, ev1));
+			NTB_BE(cudaEventElapsedTime(&ms, ws->ev0, ws->ev1));
 			ms_walk += ms;
 			if (ctr.overflow) {
-				cudaFree(d_events);
-				d_events = nullptr;
-				cap_events *= 4;
-				NTB_BE(cudaMalloc((void**)&d_events, cap_events * sizeof(Event)));
+				cudaFree(ws->d_events);
+				ws->d_events = nullptr;
+				const size_t want = ws->cap_events * 4;
+				ws->cap_events = 0;
+				NTB_BE(cudaMalloc((void**)&ws->d_events, want * sizeof(Event)));
+				ws->cap_events = want;
 				continue;
 			}
-			NTB_BE(cudaEventRecord(ev0, stream));
-			events.resize(ctr.n_events);
-			if (ctr.n_events) {
-				NTB_BE(cudaMemcpyAsync(events.data(), d_events, (size_t)ctr.n_events * sizeof(Event), cudaMemcpyDeviceToHost, stream));
+			// the events of this round go behind those of the earlier rounds in the pinned arena
+			if (ev_used + ctr.n_events > ws->cap_h_events) {
+				const size_t want = std::max<size_t>((ev_used + ctr.n_events) * 5 / 4 + 4096, ws->cap_events / 2);
+				Event* grown = nullptr;
+				NTB_BE(cudaHostAlloc((void**)&grown, want * sizeof(Event), cudaHostAllocDefault));
+				if (ev_used) {
+					std::memcpy(grown, ws->h_events, ev_used * sizeof(Event));
+				}
+				cudaFreeHost(ws->h_events);
+				ws->h_events = grown;
+				ws->cap_h_events = want;
 			}
-			NTB_BE(cudaMemcpyAsync(results.data(), d_results, n * sizeof(TaskResult), cudaMemcpyDeviceToHost, stream));
-			NTB_BE(cudaEventRecord(ev1, stream));
+			NTB_BE(cudaEventRecord(ws->ev0, stream));
+			if (ctr.n_events) {
+				NTB_BE(cudaMemcpyAsync(ws->h_events + ev_used, ws->d_events, (size_t)ctr.n_events * sizeof(Event), cudaMemcpyDeviceToHost, stream));
+			}
+			NTB_BE(cudaMemcpyAsync(ws->h_results, ws->d_results, n * sizeof(TaskResult), cudaMemcpyDeviceToHost, stream));
+			NTB_BE(cudaEventRecord(ws->ev1, stream));
 			NTB_BE(cudaStreamSynchronize(stream));
-			NTB_BE(cudaEventElapsedTime(&ms, ev0, ev1));
+			NTB_BE(cudaEventElapsedTime(&ms, ws->ev0, ws->ev1));
 			ms_d2h += ms;
+			*res_out = ws->h_results;
+			*ev_out = ws->h_events + ev_used;
+			*n_ev_out = ctr.n_events;
+			ev_used += ctr.n_events;
 			if (std::getenv("NTB_DEBUG_TASKS")) {
-				// diagnostics: the slowest walkers of this launch
-				std::vector<size_t> idx(n);
-				for (size_t i = 0; i < n; i++) {
-					idx[i] = i;
-				}
-				const size_t top = std::min<size_t>(12, n);
-				std::partial_sort(idx.begin(), idx.begin() + top, idx.end(),
-				                  [&](size_t a, size_t b) { return results[a].kcycles > results[b].kcycles; });
-				unsigned long long tot = 0;
-				for (size_t i = 0; i < n; i++) {
-					tot += results[i].kcycles;
-				}
-				std::fprintf(stderr, "[ntb] walk launch: %zu tasks, %.2f ms, sum %.1f Mcycles\n", n, ms_walk, tot / 1024.0);
-				{
-					static const char* names[16] = { "loop_head", "next_visit", "fill_cache", "seed", "lookahead", "dirty_misc", "evaluate_site",
-						                             "advance", "site_begin+linearise", "compute_plain", "phase1", "candidates", "try_indels",
-						                             "commit", "-", "-" };
-					for (int q = 0; q < 14; q++) {
-						if (ctr.prof[q]) {
-							std::fprintf(stderr, "[ntb]   phase %-22s %10.1f Mcycles\n", names[q], ctr.prof[q] / 1048576.0);
-						}
-					}
-				}
-				{
-					// cycles by number of sites in the task
-					const unsigned edges[7] = { 0, 1, 4, 8, 16, 32, 1u << 30 };
-					for (int b = 0; b < 6; b++) {
-						unsigned long long cyc = 0, cnt = 0, sites = 0, evs = 0;
-						for (size_t i = 0; i < n; i++) {
-							if (results[i].n_sites >= edges[b] && results[i].n_sites < edges[b + 1]) {
-								cyc += results[i].kcycles;
-								cnt++;
-								sites += results[i].n_sites;
-								evs += results[i].n_events;
-							}
-						}
-						std::fprintf(stderr, "[ntb]   sites in [%u,%u): %llu tasks, %llu sites, %llu events, %.1f Mcycles\n", edges[b], edges[b + 1], cnt,
-						             sites, evs, cyc / 1024.0);
-					}
-				}
-				for (size_t q = 0; q < top; q++) {
-					const TaskResult& r = results[idx[q]];
-					const Task& t = tasks[idx[q]];
-					std::fprintf(stderr, "[ntb]   task %zu contig %u [%u,%u) kcycles %u sites %u events %u end %u status %u\n", idx[q], t.contig,
-					             t.start, t.end, r.kcycles, r.n_sites, r.n_events, r.end_pos, r.status);
-				}
+				debug_tasks(n, ctr);
 			}
 			return NTB_OK;
+		}
+	}
+
+	// diagnostics: the slowest walkers of this launch and the cycles by number of sites
+	void debug_tasks(size_t n, const Counters& ctr)
+	{
+		const TaskResult* results = ws->h_results;
+		const Task* tasks = ws->h_tasks;
+		std::vector<size_t> idx(n);
+		for (size_t i = 0; i < n; i++) {
+			idx[i] = i;
+		}
+		const size_t top = std::min<size_t>(6, n);
+		std::partial_sort(idx.begin(), idx.begin() + (long)top, idx.end(),
+		                  [&](size_t a, size_t b) { return results[a].kcycles > results[b].kcycles; });
+		unsigned long long tot = 0;
+		for (size_t i = 0; i < n; i++) {
+			tot += results[i].kcycles;
+		}
+		std::fprintf(stderr, "[ntb] walk launch: %zu tasks, %.2f ms, sum %.1f Mcycles\n", n, ms_walk, tot / 1024.0);
+		static const char* names[16] = { "loop_head", "next_visit", "fill_cache", "seed", "lookahead", "dirty_misc", "evaluate_site", "advance",
+			                             "site_begin+linearise", "compute_plain", "phase1", "candidates", "try_indels", "commit", "-", "-" };
+		for (int q = 0; q < 14; q++) {
+			if (ctr.prof[q]) {
+				std::fprintf(stderr, "[ntb]   phase %-22s %10.1f Mcycles\n", names[q], ctr.prof[q] / 1048576.0);
+			}
+		}
+		const unsigned edges[7] = { 0, 1, 4, 8, 16, 32, 1u << 30 };
+		for (int b = 0; b < 6; b++) {
+			unsigned long long cyc = 0, cnt = 0, sites = 0, evs = 0;
+			for (size_t i = 0; i < n; i++) {
+				if (results[i].n_sites >= edges[b] && results[i].n_sites < edges[b + 1]) {
+					cyc += results[i].kcycles;
+					cnt++;
+					sites += results[i].n_sites;
+					evs += results[i].n_events;
+				}
+			}
+			std::fprintf(stderr, "[ntb]   sites in [%u,%u): %llu tasks, %llu sites, %llu events, %.1f Mcycles\n", edges[b], edges[b + 1], cnt, sites, evs,
+			             cyc / 1024.0);
+		}
+		for (size_t q = 0; q < top; q++) {
+			const TaskResult& r = results[idx[q]];
+			const Task& t = tasks[idx[q]];
+			std::fprintf(stderr, "[ntb]   task %zu contig %u [%u,%u) kcycles %u sites %u events %u end %u status %u\n", idx[q], t.contig, t.start, t.end,
+			             r.kcycles, r.n_sites, r.n_events, r.end_pos, r.status);
 		}
 	}
 #undef NTB_BE

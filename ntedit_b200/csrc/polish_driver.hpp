@@ -4,8 +4,12 @@
 // speculative clean start turned out to be wrong, then replay the accepted events into ropes (replay.hpp).
 //
 // Backend concept:
-//   void scan_visit(const KParams&);                       -- K1: build the visit bitmap for the whole batch
-//   int  walk(const KParams&, const std::vector<Task>&, std::vector<TaskResult>&, std::vector<Event>&);
+//   void  scan_begin(const KParams&);                      -- K1: start building the visit bitmap of the whole batch
+//   void  scan_end();                                      -- ... wait for it
+//   Task* task_buffer(size_t n);                           -- host buffer (pinned in the CUDA backend) for n tasks
+//   int   walk(const KParams&, size_t n_tasks, const TaskResult** results, const Event** events, size_t* n_events);
+//         -- K2 over the tasks in task_buffer(); results stay valid until the next walk(), the events of every
+//            round until the backend is destroyed
 // The product instantiates this with the CUDA backend (capi.cu); tests/hostsim instantiates it with a CPU
 // simulator of the same engine so the stitch/replay logic can be fuzzed without a GPU.
 #pragma once
@@ -15,6 +19,8 @@
 #include <atomic>
 #include <chrono>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <memory>
 #include <thread>
 
@@ -132,12 +138,18 @@ polish_run(Backend& be, const KParams& kp, const ntb_params& up, char* host_base
            ResultImpl& out, std::string& err)
 {
 	using clk = std::chrono::steady_clock;
+	const bool dbg = std::getenv("NTB_DEBUG_TASKS") != nullptr;
+	const auto t_begin = clk::now();
+	auto since = [&](clk::time_point t) { return std::chrono::duration<double, std::milli>(clk::now() - t).count(); };
 	out.contigs.assign(n_contigs, ContigResult());
 	std::memset(&out.stats, 0, sizeof out.stats);
 	uint32_t seg_len = up.segment_len ? up.segment_len : (kp.snv ? 1024u : 4096u);
 	if (seg_len < 4 * kp.k) {
 		seg_len = 4 * kp.k;
 	}
+
+	// K1 runs while the host cuts the contigs into segments
+	be.scan_begin(kp);
 
 	// ---- segments
 	std::vector<Segment> segs;
@@ -175,20 +187,29 @@ polish_run(Backend& be, const KParams& kp, const ntb_params& up, char* host_base
 	}
 	first_seg[n_contigs] = segs.size();
 
-	be.scan_visit(kp);
+	if (dbg) {
+		std::fprintf(stderr, "[ntb] host: %zu segments built in %.1f ms\n", segs.size(), since(t_begin));
+	}
+	const auto t_scan = clk::now();
+	be.scan_end();
+	if (dbg) {
+		std::fprintf(stderr, "[ntb] host: scan returned after %.1f ms\n", since(t_scan));
+	}
 
 	// ---- rounds of walkers + stitching
-	std::vector<std::unique_ptr<std::vector<Event>>> arenas;
+	std::vector<const Event*> arenas; // events of each round (owned by the backend)
 	std::vector<uint64_t> pending; // segment indices to (re)run
 	pending.reserve(segs.size());
 	for (uint64_t i = 0; i < segs.size(); i++) {
 		pending.push_back(i);
 	}
-	std::vector<Task> tasks;
-	std::vector<TaskResult> results;
 	double host_ms = 0;
 	while (!pending.empty()) {
-		tasks.resize(pending.size());
+		Task* tasks = be.task_buffer(pending.size());
+		if (!tasks) {
+			err = be.error();
+			return NTB_ENOMEM;
+		}
 		for (size_t i = 0; i < pending.size(); i++) {
 			const Segment& s = segs[pending[i]];
 			Task& t = tasks[i];
@@ -200,16 +221,24 @@ polish_run(Backend& be, const KParams& kp, const ntb_params& up, char* host_base
 			t.flags = (s.p0 == 0 && s.run_start == 0) ? TASK_CONTIG_START : 0;
 			t.pad_ = 0;
 		}
-		arenas.emplace_back(new std::vector<Event>());
-		const int rc = be.walk(kp, tasks, results, *arenas.back());
+		const TaskResult* results = nullptr;
+		const Event* round_events = nullptr;
+		size_t n_round_events = 0;
+		const auto t_walk = clk::now();
+		const int rc = be.walk(kp, pending.size(), &results, &round_events, &n_round_events);
+		if (dbg) {
+			std::fprintf(stderr, "[ntb] host: walk round (%zu tasks, %zu events) returned after %.1f ms\n", pending.size(), n_round_events,
+			             since(t_walk));
+		}
 		if (rc != NTB_OK) {
 			err = be.error();
 			return rc;
 		}
+		arenas.push_back(round_events);
 		out.stats.rounds++;
-		out.stats.segments += tasks.size();
+		out.stats.segments += pending.size();
 		if (out.stats.rounds > 1) {
-			out.stats.reruns += tasks.size();
+			out.stats.reruns += pending.size();
 		}
 		const auto t0 = clk::now();
 		for (size_t i = 0; i < pending.size(); i++) {
@@ -290,7 +319,7 @@ polish_run(Backend& be, const KParams& kp, const ntb_params& up, char* host_base
 				if (need >= s.p1) {
 					continue;
 				}
-				const std::vector<Event>& arena = *arenas[(size_t)s.arena];
+				const Event* arena = arenas[(size_t)s.arena];
 				chain.clear();
 				for (uint32_t e = s.res.last_event; e != NONE32; e = arena[e].prev) {
 					chain.push_back(&arena[e]);
@@ -355,6 +384,9 @@ polish_run(Backend& be, const KParams& kp, const ntb_params& up, char* host_base
 		return NTB_EINTERNAL;
 	}
 	host_ms += std::chrono::duration<double, std::milli>(clk::now() - t1).count();
+	if (dbg) {
+		std::fprintf(stderr, "[ntb] host: replay %.1f ms, whole call %.1f ms\n", since(t1), since(t_begin));
+	}
 	out.stats.edits = n_edits;
 	out.stats.ms_host = (float)host_ms;
 	return NTB_OK;

@@ -41,7 +41,9 @@ struct HostBackend
 	const std::string& error() const { return err; }
 
 	// CPU stand-in for the scan kernel K1
-	void scan_visit(const KParams& kp)
+	void scan_end() {}
+
+	void scan_begin(const KParams& kp)
 	{
 		visit.assign((total + 63) / 32 + 2, 0u);
 		uint64_t run = 0;
@@ -70,18 +72,29 @@ struct HostBackend
 		}
 	}
 
-	int walk(const KParams& kp, const std::vector<Task>& tasks, std::vector<TaskResult>& results, std::vector<Event>& events)
+	std::vector<Task> tasks;
+	std::vector<TaskResult> results;
+	std::vector<std::unique_ptr<std::vector<Event>>> rounds;
+
+	Task* task_buffer(size_t n)
 	{
-		results.resize(tasks.size());
-		events.assign(1u << 16, Event());
+		tasks.resize(n);
+		return tasks.data();
+	}
+
+	int walk(const KParams& kp, size_t n_tasks, const TaskResult** res_out, const Event** ev_out, size_t* n_ev_out)
+	{
+		results.resize(n_tasks);
+		rounds.emplace_back(new std::vector<Event>(1u << 16));
+		std::vector<Event>& events = *rounds.back();
+		std::vector<uint64_t> rot(ROT_WORDS);
+		for (uint32_t q = 0; q < ROT_WORDS; q++) {
+			rot[q] = rot_entry(q);
+		}
 		for (;;) {
 			Counters ctr = {};
 			WalkerState<352>* st = new WalkerState<352>();
-			std::vector<uint64_t> rot(ROT_WORDS);
-			for (uint32_t q = 0; q < ROT_WORDS; q++) {
-				rot[q] = rot_entry(q);
-			}
-			for (size_t i = 0; i < tasks.size(); i++) {
+			for (size_t i = 0; i < n_tasks; i++) {
 				WalkerIO& io = st->io;
 				io.text = bases + tasks[i].text_off;
 				io.len = tasks[i].len;
@@ -99,6 +112,9 @@ struct HostBackend
 			delete st;
 			if (!ctr.overflow) {
 				events.resize(ctr.n_events);
+				*res_out = results.data();
+				*ev_out = events.data();
+				*n_ev_out = events.size();
 				return NTB_OK;
 			}
 			events.assign(events.size() * 4, Event());
