@@ -486,6 +486,9 @@ struct CudaBackend
 				std::fprintf(stderr, "[ntb]   phase %-22s %10.1f Mcycles\n", names[q], ctr.prof[q] / 1048576.0);
 			}
 		}
+		if (ctr.prof[14]) {
+			std::fprintf(stderr, "[ntb]   filter probes issued %llu, tryIndels calls %llu\n", ctr.prof[14], ctr.prof[15]);
+		}
 		const unsigned edges[7] = { 0, 1, 4, 8, 16, 32, 1u << 30 };
 		for (int b = 0; b < 6; b++) {
 			unsigned long long cyc = 0, cnt = 0, sites = 0, evs = 0;

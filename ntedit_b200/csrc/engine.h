@@ -600,6 +600,9 @@ struct Walker
 #if defined(__CUDA_ARCH__)
 				const uint32_t dst = (uint32_t)__cvta_generic_to_shared(&S.pv[g][u][ln]);
 				asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+#if defined(NTB_PHASE_PROF)
+				atomicAdd(&S.prof[14], 1u); // filter probes issued by this walker
+#endif
 #else
 				uint32_t w;
 				std::memcpy(&w, src, 4);
@@ -1804,6 +1807,11 @@ struct Walker
 				break;
 			}
 			NTB_PROF(11);
+#if defined(NTB_PHASE_PROF) && defined(__CUDA_ARCH__)
+			if (lane_id() == 0) {
+				S.prof[15]++; // tryIndels calls
+			}
+#endif
 			const bool hit = try_indels();
 			NTB_PROF(12);
 			if (hit && (P.mode == 0 || P.mode == 1)) {

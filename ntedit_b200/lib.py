@@ -136,10 +136,11 @@ def load():
     """Load the in-tree CUDA library; raises if it has not been built (no fallback)."""
     global _lib
     if _lib is None:
-        if not os.path.exists(SO):
+        so = os.environ.get("NTB_LIB", SO)  # tuning aid: load a differently compiled build of the same library
+        if not os.path.exists(so):
             raise ImportError("libntedit_b200.so is not built: run `python -c 'import __graft_entry__ as g; g.build()'` "
                               "(ntedit_b200 has no CPU fallback)")
-        L = C.CDLL(SO)
+        L = C.CDLL(so)
         for name, (res, args) in SYMBOLS.items():
             fn = getattr(L, name)
             fn.restype = res
