@@ -1,0 +1,665 @@
+// ntedit-b200: the host driver of the B200 path with ntEdit's command line and file formats.
+//
+// Plays the roles of the reference's main() (ntedit.cpp:2276-2600: option parsing, parameter clamps, filter load,
+// banners) and readAndCorrect() (ntedit.cpp:2154-2259: gz/plain FASTA in through a kseq-compatible reader, the three
+// output files with their headers).  Where the reference hands one contig at a time to an OpenMP thread
+// (ntedit.cpp:2213-2252), this driver packs contigs into batches and hands each batch to the GPU through the C ABI
+// (ntb_polish_batch); with --gpus N batches go round-robin to N devices, the filter replicated on each.  Output is
+// always in input order (= the reference's `-t 1` order).  No hashing and no filter probe happens in this file.
+#include "../../include/ntedit_b200.h"
+#include "writer.hpp"
+
+#include <getopt.h>
+#include <zlib.h>
+
+#include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <ctime>
+#include <fstream>
+#include <future>
+#include <iostream>
+#include <memory>
+#include <sstream>
+#include <string>
+#include <thread>
+#include <vector>
+
+#define PROGRAM "ntedit-b200"
+
+namespace {
+
+const char VERSION_MESSAGE[] = PROGRAM " (ntEdit v2.1.1 hot path on B200)\n";
+
+const char USAGE_MESSAGE[] =
+    "Usage: " PROGRAM " -f DRAFT -r BLOOM [options]\n"
+    "  drop-in for `ntedit` (bcgsc/ntEdit v2.1.1); same options, same output files\n"
+    " -t,  number of host threads (formatting / replay) [4]\n"
+    " -f,  draft genome assembly (FASTA, Multi-FASTA, and/or gzipped compatible), REQUIRED\n"
+    " -r,  Bloom filter file (btllib KmerBloomFilter / KmerCountingBloomFilter8), REQUIRED\n"
+    " -e,  secondary Bloom filter with k-mers to reject (optional)\n"
+    " -b,  output file prefix (optional)\n"
+    " -z,  minimum contig length [100]\n"
+    " -i,  maximum number of insertion bases to try, range 0-5 [5]\n"
+    " -d,  maximum number of deletions bases to try, range 0-10 [5]\n"
+    " -x,  k/x ratio for the number of k-mers that should be missing [5.000]\n"
+    " -y,  k/y ratio for the number of edited k-mers that should be present [9.000]\n"
+    " -X,  ratio of number of k-mers in the k subset that should be missing in order to attempt fix (higher=stringent)\n"
+    " -Y,  ratio of number of k-mers in the k subset that should be present to accept an edit (higher=stringent)\n"
+    " -c,  cap for the number of base insertions that can be made at one position (accepted, overridden by k*1.5 as in ntedit)\n"
+    " -j,  controls size of k-mer subset [3]\n"
+    " -m,  mode of editing, range 0-2 [0]\n"
+    " -s,  SNV mode (-s 1 = yes, default = 0, no)\n"
+    " -l,  input VCF file with annotated variants (e.g., clinvar.vcf, optional)\n"
+    " -a,  soft masks missing k-mer positions having no fix (-a 1 = yes, default = 0, no)\n"
+    " -p,  minimum k-mer coverage threshold (CBF only) [1]\n"
+    " -q,  maximum k-mer coverage threshold (CBF only) [255]\n"
+    " -k,  k-mer size (optional; taken from the Bloom filter header, checked when given)\n"
+    " -v,  verbose (accepted; per-site tracing is not reproduced)\n"
+    "      --gpus N          shard batches of contigs over the first N GPUs [1]\n"
+    "      --batch_bases N   bases per device batch [1073741824]\n"
+    "      --help, --version\n";
+
+struct Opt
+{
+	unsigned nthreads = 4;
+	std::string draft, vcf, bloom, bloomrep, prefix;
+	ntb_params p;
+	unsigned insertion_cap = 0;
+	int verbose = 0;
+	unsigned k_given = 0;
+	int gpus = 1;
+	uint64_t batch_bases = 1ull << 30;
+};
+
+enum
+{
+	OPT_HELP = 1,
+	OPT_VERSION,
+	OPT_GPUS,
+	OPT_BATCH
+};
+
+const char shortopts[] = "t:f:s:k:z:b:r:v:d:i:X:Y:x:y:m:c:j:s:e:a:l:p:q:";
+
+const struct option longopts[] = { { "threads", required_argument, nullptr, 't' },
+	                               { "draft_file", required_argument, nullptr, 'f' },
+	                               { "k", required_argument, nullptr, 'k' },
+	                               { "minimum_contig_length", required_argument, nullptr, 'z' },
+	                               { "maximum_insertions", required_argument, nullptr, 'i' },
+	                               { "maximum_deletions", required_argument, nullptr, 'd' },
+	                               { "insertion_cap", required_argument, nullptr, 'c' },
+	                               { "edit_threshold", required_argument, nullptr, 'y' },
+	                               { "missing_threshold", required_argument, nullptr, 'x' },
+	                               { "edit_ratio", required_argument, nullptr, 'Y' },
+	                               { "missing_ratio", required_argument, nullptr, 'X' },
+	                               { "jump", required_argument, nullptr, 'j' },
+	                               { "bloom_filename", required_argument, nullptr, 'r' },
+	                               { "bloomrep_filename", required_argument, nullptr, 'e' },
+	                               { "outfile_prefix", required_argument, nullptr, 'b' },
+	                               { "mode", required_argument, nullptr, 'm' },
+	                               { "snv", required_argument, nullptr, 's' },
+	                               { "vcf_file", required_argument, nullptr, 'l' },
+	                               { "mask", required_argument, nullptr, 'a' },
+	                               { "verbose", required_argument, nullptr, 'v' },
+	                               { "minimum_kmer_coverage", required_argument, nullptr, 'p' },
+	                               { "maximum_kmer_coverage", required_argument, nullptr, 'q' },
+	                               { "gpus", required_argument, nullptr, OPT_GPUS },
+	                               { "batch_bases", required_argument, nullptr, OPT_BATCH },
+	                               { "help", no_argument, nullptr, OPT_HELP },
+	                               { "version", no_argument, nullptr, OPT_VERSION },
+	                               { nullptr, 0, nullptr, 0 } };
+
+void
+assert_readable(const std::string& path)
+{
+	std::ifstream f(path);
+	if (!f.good()) {
+		std::cerr << PROGRAM ": error: cannot read `" << path << "'\n";
+		std::exit(EXIT_FAILURE);
+	}
+}
+
+std::string
+basename_of(const std::string& p)
+{
+	return p.substr(p.find_last_of("/\\") + 1);
+}
+
+std::string
+now_str()
+{
+	time_t raw;
+	time(&raw);
+	return ctime(&raw);
+}
+
+[[noreturn]] void
+die_ntb(const char* what)
+{
+	std::cerr << PROGRAM ": error: " << what << ": " << ntb_last_error() << "\n";
+	std::exit(EXIT_FAILURE);
+}
+
+// ---------------------------------------------------------------- kseq-compatible FASTA/FASTQ reader over zlib
+// Same record semantics as lib/kseq.h:175-215: name = up to the first whitespace, comment = rest of the header line,
+// sequence lines concatenated with every character kept except newlines / carriage returns... (kseq keeps all
+// printable characters of a sequence line; it drops only the line terminator and isgraph-failing bytes)
+class FastxReader
+{
+  public:
+	explicit FastxReader(const std::string& path) : buf_(1 << 20)
+	{
+		fp_ = gzopen(path.c_str(), "r");
+		if (fp_) {
+			gzbuffer(fp_, 1 << 20);
+		}
+	}
+	~FastxReader()
+	{
+		if (fp_) {
+			gzclose(fp_);
+		}
+	}
+	bool ok() const { return fp_ != nullptr; }
+
+	// reads the next record; sequence is appended to `seq`.  Returns false at end of file.
+	bool next(std::string& name, std::string& comment, std::string& seq)
+	{
+		int c;
+		if (last_char_ == 0) { // jump to the next header line
+			while ((c = getc_()) != -1 && c != '>' && c != '@') {
+			}
+			if (c == -1) {
+				return false;
+			}
+			last_char_ = c;
+		}
+		name.clear();
+		comment.clear();
+		// name: up to the first whitespace
+		while ((c = getc_()) != -1 && !isspace_(c)) {
+			name.push_back((char)c);
+		}
+		if (c == -1 && name.empty()) {
+			return false;
+		}
+		if (c != '\n' && c != -1) { // comment: the rest of the line
+			while ((c = getc_()) != -1 && c != '\n') {
+				comment.push_back((char)c);
+			}
+			if (!comment.empty() && comment.back() == '\r') {
+				comment.pop_back();
+			}
+		}
+		const size_t seq0 = seq.size();
+		while ((c = getc_()) != -1 && c != '>' && c != '+' && c != '@') {
+			if (c == '\n') {
+				continue;
+			}
+			seq.push_back((char)c);
+			append_line_(seq); // rest of the line
+		}
+		if (c == '>' || c == '@') {
+			last_char_ = c;
+		} else {
+			last_char_ = 0;
+		}
+		if (c != '+') {
+			return true;
+		}
+		// FASTQ: skip the rest of the '+' line, then as many quality characters as there are bases
+		while ((c = getc_()) != -1 && c != '\n') {
+		}
+		if (c == -1) {
+			return true;
+		}
+		const size_t want = seq.size() - seq0;
+		size_t have = 0;
+		std::string q;
+		while (have < want && (c = getc_()) != -1) {
+			if (c == '\n') {
+				continue;
+			}
+			q.clear();
+			q.push_back((char)c);
+			append_line_(q);
+			have += q.size();
+		}
+		last_char_ = 0;
+		return true;
+	}
+
+  private:
+	static bool isspace_(int c) { return c == ' ' || c == '\t' || c == '\n' || c == '\r' || c == '\v' || c == '\f'; }
+
+	int getc_()
+	{
+		if (pos_ >= len_) {
+			if (eof_) {
+				return -1;
+			}
+			const int n = gzread(fp_, buf_.data(), (unsigned)buf_.size());
+			if (n <= 0) {
+				eof_ = true;
+				return -1;
+			}
+			len_ = (size_t)n;
+			pos_ = 0;
+		}
+		return (unsigned char)buf_[pos_++];
+	}
+
+	// appends the rest of the current line (without its terminator) to s
+	void append_line_(std::string& s)
+	{
+		for (;;) {
+			if (pos_ >= len_) {
+				const int c = getc_();
+				if (c == -1) {
+					break;
+				}
+				pos_--;
+			}
+			const char* b = buf_.data() + pos_;
+			const char* nl = (const char*)std::memchr(b, '\n', len_ - pos_);
+			const size_t n = nl ? (size_t)(nl - b) : len_ - pos_;
+			s.append(b, n);
+			pos_ += n;
+			if (nl) {
+				pos_++; // consume the newline
+				break;
+			}
+		}
+		if (!s.empty() && s.back() == '\r') {
+			s.pop_back();
+		}
+	}
+
+	gzFile fp_ = nullptr;
+	std::vector<char> buf_;
+	size_t pos_ = 0, len_ = 0;
+	bool eof_ = false;
+	int last_char_ = 0;
+};
+
+// vcf_entry_to_map, ntedit.cpp:2261-2274
+void
+vcf_entry_to_map(const std::string& line, ntb::ClinvarMap& m)
+{
+	std::vector<std::string> tok;
+	size_t s = 0;
+	for (;;) {
+		const size_t e = line.find('\t', s);
+		tok.push_back(line.substr(s, e == std::string::npos ? std::string::npos : e - s));
+		if (e == std::string::npos) {
+			break;
+		}
+		s = e + 1;
+	}
+	// std::sregex_token_iterator drops trailing empty fields
+	while (!tok.empty() && tok.back().empty()) {
+		tok.pop_back();
+	}
+	if (tok.size() >= 8) {
+		m[tok[0] + ">" + tok[3] + tok[1] + tok[4]] = tok[7];
+	}
+}
+
+void
+load_clinvar(const std::string& path, ntb::ClinvarMap& m)
+{
+	gzFile fp = gzopen(path.c_str(), "r"); // transparently reads plain and gzipped files
+	if (!fp) {
+		std::cerr << "Unable to open file" << std::endl;
+		return;
+	}
+	std::string line;
+	char buf[1 << 16];
+	while (gzgets(fp, buf, sizeof buf)) {
+		line += buf;
+		if (!line.empty() && line.back() == '\n') {
+			line.pop_back();
+			vcf_entry_to_map(line, m);
+			line.clear();
+		}
+	}
+	if (!line.empty()) {
+		vcf_entry_to_map(line, m);
+	}
+	gzclose(fp);
+}
+
+struct Batch
+{
+	std::vector<std::string> names;
+	std::string bases; // contigs end to end, each followed by its NUL
+	std::vector<uint64_t> offsets{ 0 };
+};
+
+struct BatchOut
+{
+	std::string fa, tsv, vcf;
+	uint64_t contigs = 0, bases = 0, edits = 0;
+};
+
+// polish one batch on `device` and format it (contigs formatted in parallel, concatenated in input order)
+BatchOut
+process_batch(std::unique_ptr<Batch> b, ntb_filter* bloom, ntb_filter* rep, const Opt& opt, const ntb::ClinvarMap* cv)
+{
+	BatchOut out;
+	ntb_result* res = nullptr;
+	if (ntb_polish_batch(bloom, rep, &opt.p, &b->bases[0], b->offsets.data(), b->names.size(), &res) != NTB_OK) {
+		die_ntb("ntb_polish_batch");
+	}
+	const size_t n = b->names.size();
+	std::vector<std::string> fa(n), tsv(n), vcf(n);
+	std::atomic<size_t> next(0);
+	auto work = [&]() {
+		for (;;) {
+			const size_t c = next.fetch_add(1);
+			if (c >= n) {
+				break;
+			}
+			int polished = 0;
+			const ntb_node* nodes = nullptr;
+			const ntb_srec* recs = nullptr;
+			uint64_t nn = 0, nr = 0;
+			ntb_result_contig(res, c, &polished, &nodes, &nn, &recs, &nr);
+			if (!polished) {
+				continue; // shorter than -z: dropped from all outputs, ntedit.cpp:2242-2245
+			}
+			ntb::format_contig(b->names[c], &b->bases[b->offsets[c]], nodes, (size_t)nn, recs, (size_t)nr, opt.p.snv != 0, cv, &fa[c], &tsv[c],
+			                   &vcf[c]);
+		}
+	};
+	const unsigned nt = (unsigned)std::max<size_t>(1, std::min<size_t>(opt.nthreads, n));
+	std::vector<std::thread> pool;
+	for (unsigned i = 1; i < nt; i++) {
+		pool.emplace_back(work);
+	}
+	work();
+	for (auto& t : pool) {
+		t.join();
+	}
+	for (size_t c = 0; c < n; c++) {
+		out.fa += fa[c];
+		out.tsv += tsv[c];
+		out.vcf += vcf[c];
+	}
+	ntb_stats st;
+	ntb_result_stats(res, &st);
+	out.contigs = st.contigs;
+	out.bases = st.bases;
+	out.edits = st.edits;
+	ntb_result_free(res);
+	return out;
+}
+
+template<class T>
+bool
+parse(const char* s, T& v)
+{
+	std::istringstream arg(s ? s : "");
+	arg >> v;
+	return arg.eof() && !arg.fail();
+}
+
+} // namespace
+
+int
+main(int argc, char** argv)
+{
+	Opt opt;
+	ntb_params_init(&opt.p);
+	bool die = false;
+	for (int c; (c = getopt_long(argc, argv, shortopts, longopts, nullptr)) != -1;) {
+		bool ok = true;
+		switch (c) {
+		case '?': die = true; break;
+		case 't': ok = parse(optarg, opt.nthreads); break;
+		case 'f': ok = parse(optarg, opt.draft); break;
+		case 'z': ok = parse(optarg, opt.p.min_contig_len); break;
+		case 'b': ok = parse(optarg, opt.prefix); break;
+		case 'r': ok = parse(optarg, opt.bloom); break;
+		case 'e': ok = parse(optarg, opt.bloomrep); break;
+		case 'd': ok = parse(optarg, opt.p.max_deletions); break;
+		case 'i': ok = parse(optarg, opt.p.max_insertions); break;
+		case 'x': ok = parse(optarg, opt.p.missing_threshold); break;
+		case 'y': ok = parse(optarg, opt.p.edit_threshold); break;
+		case 'X':
+			ok = parse(optarg, opt.p.missing_ratio);
+			opt.p.use_ratio = 1;
+			break;
+		case 'Y':
+			ok = parse(optarg, opt.p.edit_ratio);
+			opt.p.use_ratio = 1;
+			break;
+		case 'c': ok = parse(optarg, opt.insertion_cap); break;
+		case 'j': ok = parse(optarg, opt.p.jump); break;
+		case 'm': ok = parse(optarg, opt.p.mode); break;
+		case 's': ok = parse(optarg, opt.p.snv); break;
+		case 'l': ok = parse(optarg, opt.vcf); break;
+		case 'a': ok = parse(optarg, opt.p.mask); break;
+		case 'v': ok = parse(optarg, opt.verbose); break;
+		case 'p': ok = parse(optarg, opt.p.min_threshold); break;
+		case 'q': ok = parse(optarg, opt.p.max_threshold); break;
+		case 'k': ok = parse(optarg, opt.k_given); break; // the reference rejects -k (no case for it); we check it against the filter
+		case OPT_GPUS: ok = parse(optarg, opt.gpus); break;
+		case OPT_BATCH: ok = parse(optarg, opt.batch_bases); break;
+		case OPT_HELP: std::cerr << USAGE_MESSAGE; return EXIT_SUCCESS;
+		case OPT_VERSION: std::cerr << VERSION_MESSAGE; return EXIT_SUCCESS;
+		default: break;
+		}
+		if (!ok) {
+			std::cerr << PROGRAM ": invalid option: `-" << (char)c << (optarg ? optarg : "") << "'\n";
+			return EXIT_FAILURE;
+		}
+	}
+
+	std::cout << "---------- initializing                             : " << now_str();
+	if (opt.draft.empty()) {
+		std::cerr << PROGRAM ": error: need to specify assembly draft file (-f)\n";
+		die = true;
+	} else {
+		assert_readable(opt.draft);
+	}
+	if (opt.bloom.empty()) {
+		std::cerr << PROGRAM ": error: need to specify the Bloom filter file (-r)\n";
+		die = true;
+	} else {
+		assert_readable(opt.bloom);
+	}
+	if (!opt.bloomrep.empty()) {
+		assert_readable(opt.bloomrep);
+	}
+	if (die) {
+		std::cerr << "Try `" << PROGRAM << " --help' for more information.\n";
+		return EXIT_FAILURE;
+	}
+	if (opt.p.snv) { // ntedit.cpp:2411-2420
+		opt.p.max_insertions = 0;
+		opt.p.max_deletions = 0;
+		std::cerr << "\nSNV mode ON\nTracking all single-base variants\nNote: -i and -d both set to 0 when -s is set to 1\n\n";
+	}
+	const int ndev_avail = ntb_device_count();
+	if (ndev_avail <= 0) {
+		std::cerr << PROGRAM ": error: no CUDA device available (this build has no CPU fallback)\n";
+		return EXIT_FAILURE;
+	}
+	if (opt.gpus < 1 || opt.gpus > ndev_avail) {
+		std::cerr << PROGRAM ": error: --gpus " << opt.gpus << " but " << ndev_avail << " device(s) present\n";
+		return EXIT_FAILURE;
+	}
+	if (opt.batch_bases < 1024) {
+		opt.batch_bases = 1024;
+	}
+
+	// ---- filters: one replica per device (ntedit.cpp:2438-2461)
+	std::cout << "---------- loading Bloom filter from file           : " << now_str() << "\n";
+	std::vector<ntb_filter*> bloom((size_t)opt.gpus, nullptr), rep((size_t)opt.gpus, nullptr);
+	for (int d = 0; d < opt.gpus; d++) {
+		if (ntb_filter_load(opt.bloom.c_str(), d, &bloom[(size_t)d]) != NTB_OK) {
+			std::cerr << PROGRAM ": error: Bloom filter file supplied (-r) is incorrect: " << ntb_last_error() << "\n";
+			return EXIT_FAILURE;
+		}
+	}
+	ntb_filter_info fi;
+	if (ntb_filter_get_info(bloom[0], &fi) != NTB_OK) {
+		die_ntb("ntb_filter_get_info");
+	}
+	if (fi.hash_num == 0) {
+		std::cerr << PROGRAM ": error: Bloom filter file supplied (-r) is incorrect.\n";
+		return EXIT_FAILURE;
+	}
+	if (opt.k_given && opt.k_given != fi.k) {
+		std::cerr << PROGRAM ": error: -k " << opt.k_given << " does not match the Bloom filter's k-mer size (" << fi.k << ")\n";
+		return EXIT_FAILURE;
+	}
+	if (!fi.counting && opt.p.min_threshold != 1) { // ntedit.cpp:2453-2458
+		std::cerr << PROGRAM ": warning: Bloom filter is not counting, min k-mer presence threshold will be set to 1.\n";
+		opt.p.min_threshold = 1;
+	}
+	auto print_details = [](const ntb_filter_info& f) { // BFWrapper::print_details, ntedit.cpp:387-395
+		std::cout << "BLOOM::\tcounting: " << (f.counting ? "YES" : "NO") << "\tsize: " << f.bytes << "\tnumber hash functions: " << f.hash_num
+		          << "\tkmer size: " << f.k << "\tFPR: " << f.fpr << std::endl;
+	};
+	print_details(fi);
+
+	std::cout << "\n---------- verifying parameters                     : " << now_str();
+	if ((opt.p.max_insertions == 0 && opt.p.max_deletions > 0) || (opt.p.max_insertions == 1 && opt.p.max_deletions > 1)) {
+		std::cerr << PROGRAM ": warning: i and d parameter combination is not possible; d was set to the value of i.\n";
+		opt.p.max_deletions = opt.p.max_insertions;
+	}
+	if (opt.p.max_insertions > 5) {
+		std::cerr << PROGRAM ": warning: i parameter too high, adjusting to maximum -i 5";
+		opt.p.max_insertions = 5;
+	}
+	if (opt.p.max_deletions > 10) {
+		std::cerr << PROGRAM ": warning: d parameter too high, adjusting to maximum -d 10";
+		opt.p.max_deletions = 10;
+	}
+	if (opt.prefix.empty()) { // ntedit.cpp:2496-2502
+		std::ostringstream o;
+		o << basename_of(opt.draft) << "_k" << fi.k << "_z" << opt.p.min_contig_len << "_r" << basename_of(opt.bloom) << "_i" << opt.p.max_insertions
+		  << "_d" << opt.p.max_deletions << "_m" << opt.p.mode;
+		opt.prefix = o.str();
+	}
+	std::cout << "\nrunning : " << PROGRAM << "\n -f " << basename_of(opt.draft) << "\n -k " << fi.k << "\n -z " << opt.p.min_contig_len << "\n -b "
+	          << opt.prefix << "\n -r " << basename_of(opt.bloom) << "\n -e " << basename_of(opt.bloomrep) << "\n -i " << opt.p.max_insertions << "\n -d "
+	          << opt.p.max_deletions;
+	if (opt.p.use_ratio) {
+		std::cout << "\n -X " << opt.p.missing_ratio << "\n -Y " << opt.p.edit_ratio;
+	} else {
+		std::cout << "\n -x " << opt.p.missing_threshold << "\n -y " << opt.p.edit_threshold;
+	}
+	std::cout << "\n -j " << opt.p.jump << "\n -m " << opt.p.mode << "\n -s " << opt.p.snv << "\n -l " << basename_of(opt.vcf) << "\n -a " << opt.p.mask
+	          << "\n -t " << opt.nthreads << "\n -v " << opt.verbose << "\n --gpus " << opt.gpus << "\n"
+	          << std::endl;
+	if (fi.counting) {
+		std::cout << " -p " << opt.p.min_threshold << "\n -q " << opt.p.max_threshold << "\n" << std::endl;
+	}
+
+	ntb::ClinvarMap clinvar;
+	if (!opt.vcf.empty()) {
+		assert_readable(opt.vcf);
+		load_clinvar(opt.vcf, clinvar);
+	}
+
+	if (!opt.bloomrep.empty()) { // ntedit.cpp:2566-2590
+		std::cout << "---------- loading secondary Bloom filter from file : " << now_str() << "\n";
+		for (int d = 0; d < opt.gpus; d++) {
+			if (ntb_filter_load(opt.bloomrep.c_str(), d, &rep[(size_t)d]) != NTB_OK) {
+				std::cerr << PROGRAM ": error: secondary Bloom filter file supplied (-e) is incorrect: " << ntb_last_error() << "\n";
+				return EXIT_FAILURE;
+			}
+		}
+		ntb_filter_info ri;
+		ntb_filter_get_info(rep[0], &ri);
+		if (ri.k != fi.k) {
+			std::cerr << PROGRAM ": error: secondary Bloom filter k size (" << ri.k << ") is different than main Bloom filter k size (" << fi.k << ")\n";
+			return EXIT_FAILURE;
+		}
+		print_details(ri);
+		std::cout << "\n";
+	}
+	std::cout << "---------- reading/processing input sequence        : " << now_str();
+
+	// ---- readAndCorrect, ntedit.cpp:2154-2259
+	FastxReader reader(opt.draft);
+	if (!reader.ok()) {
+		std::cerr << PROGRAM ": error: cannot open `" << opt.draft << "'\n";
+		return EXIT_FAILURE;
+	}
+	std::ofstream dfout(opt.prefix + "_edited.fa", std::ios::binary);
+	std::ofstream rfout(opt.prefix + "_changes.tsv", std::ios::binary);
+	std::ofstream vfout(opt.prefix + "_variants.vcf", std::ios::binary);
+	if (!dfout || !rfout || !vfout) {
+		std::cerr << PROGRAM ": error: cannot open output files with prefix `" << opt.prefix << "'\n";
+		return EXIT_FAILURE;
+	}
+	rfout << ntb::tsv_header(fi.k, opt.p.jump, fi.counting != 0);
+	vfout << ntb::vcf_header("ntEdit v2.1.1", opt.draft); // the reference's PROGRAM string (ntedit.cpp:1), kept for byte-compatible headers
+
+	const ntb::ClinvarMap* cv = &clinvar;
+	std::vector<std::future<BatchOut>> inflight; // in input order
+	uint64_t tot_contigs = 0, tot_bases = 0, tot_edits = 0, n_read = 0;
+	size_t next_dev = 0;
+	auto drain_one = [&]() {
+		BatchOut o = inflight.front().get();
+		inflight.erase(inflight.begin());
+		dfout.write(o.fa.data(), (std::streamsize)o.fa.size());
+		rfout.write(o.tsv.data(), (std::streamsize)o.tsv.size());
+		vfout.write(o.vcf.data(), (std::streamsize)o.vcf.size());
+		tot_contigs += o.contigs;
+		tot_bases += o.bases;
+		tot_edits += o.edits;
+	};
+	const auto t_begin = std::chrono::steady_clock::now();
+	bool more = true;
+	std::string name, comment;
+	while (more) {
+		std::unique_ptr<Batch> b(new Batch());
+		b->bases.reserve((size_t)std::min<uint64_t>(opt.batch_bases + (64u << 20), 1ull << 32));
+		while (b->bases.size() < opt.batch_bases) {
+			more = reader.next(name, comment, b->bases);
+			if (!more) {
+				break;
+			}
+			b->bases.push_back('\0');
+			b->offsets.push_back(b->bases.size());
+			b->names.push_back(comment.empty() ? name : name + " " + comment); // ntedit.cpp:2224-2229
+			n_read++;
+		}
+		if (b->names.empty()) {
+			break;
+		}
+		const size_t d = next_dev;
+		next_dev = (next_dev + 1) % (size_t)opt.gpus;
+		while (inflight.size() >= (size_t)opt.gpus) { // at most one batch per device in flight (+ the one being read)
+			drain_one();
+		}
+		Batch* raw = b.release();
+		inflight.push_back(std::async(std::launch::async, [raw, &bloom, &rep, &opt, cv, d]() {
+			return process_batch(std::unique_ptr<Batch>(raw), bloom[d], rep[d], opt, cv);
+		}));
+	}
+	while (!inflight.empty()) {
+		drain_one();
+	}
+	dfout.close();
+	rfout.close();
+	vfout.close();
+	const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_begin).count();
+	std::cout << "Processed " << n_read << " sequences: " << tot_contigs << " polished (" << tot_bases << " bases, " << tot_edits << " edits) in " << secs
+	          << " s" << std::endl;
+	std::cout << "---------- process complete                         : " << now_str();
+	for (int d = 0; d < opt.gpus; d++) {
+		ntb_filter_free(bloom[(size_t)d]);
+		ntb_filter_free(rep[(size_t)d]);
+	}
+	return 0;
+}

@@ -114,3 +114,24 @@ def test_writer_through_the_abi_matches_golden(L, oracle):
     for b in (fa, tsv, vcf):
         L.ntb_strbuf_free(C.byref(b))
     filt.free()
+
+
+def test_cli_builds_and_refuses_to_run_without_a_device(tmp_path):
+    """ntedit-b200 (cli.cpp) is built next to the library; without a CUDA device it stops with an error, it never
+    falls back to a CPU path."""
+    import subprocess
+    from ntedit_b200 import lib
+    lib.build()
+    assert os.path.exists(lib.CLI)
+    r = subprocess.run([lib.CLI, "--help"], stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    assert r.returncode == 0 and b"-f" in r.stderr and b"--gpus" in r.stderr
+    r = subprocess.run([lib.CLI], stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    assert r.returncode != 0 and b"need to specify assembly draft file" in r.stderr
+    import torch
+    if not torch.cuda.is_available():
+        d = tmp_path / "d.fa"
+        d.write_bytes(b">a\nACGT\n")
+        f = tmp_path / "f.bf"
+        f.write_bytes(b"[BTLKmerBloomFilter_v1]\n")
+        r = subprocess.run([lib.CLI, "-f", str(d), "-r", str(f)], stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+        assert r.returncode != 0 and b"no CUDA device" in r.stderr
