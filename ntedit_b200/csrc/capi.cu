@@ -168,6 +168,9 @@ struct Workspace
 	Event* d_events = nullptr;
 	size_t cap_events = 0;
 	Counters* d_ctr = nullptr;
+	uint64_t* d_records = nullptr; // K1b: probe records, n_buckets x bucket_cap
+	size_t cap_records = 0;
+	uint32_t* d_cursor = nullptr;  // K1b: BIN_MAX_BUCKETS record counters + the probe kernel's pacing counter
 	// pinned host mirrors
 	Task* h_tasks = nullptr;
 	TaskResult* h_results = nullptr;
@@ -185,6 +188,8 @@ struct Workspace
 		cudaFree(d_results);
 		cudaFree(d_events);
 		cudaFree(d_ctr);
+		cudaFree(d_records);
+		cudaFree(d_cursor);
 		cudaFreeHost(h_tasks);
 		cudaFreeHost(h_results);
 		cudaFreeHost(h_events);
@@ -297,8 +302,95 @@ struct CudaBackend
 
 	~CudaBackend() { workspace_release(ws); }
 
+	static uint64_t env_u64(const char* name, uint64_t dflt)
+	{
+		const char* v = std::getenv(name);
+		return (v && *v) ? std::strtoull(v, nullptr, 10) : dflt;
+	}
+
+	// K1b geometry for this filter: region size (log2 slots) and bucket count; false = use the direct scan
+	bool binned_geometry(const KParams& kp, uint32_t& rl, uint32_t& nb) const
+	{
+		if (kp.snv) {
+			return false; // every valid window is a site: nothing is probed
+		}
+		if (bloom->bytes < env_u64("NTB_BIN_MIN_BYTES", 96ull << 20)) {
+			return false; // the filter sits in L2 anyway
+		}
+		const FilterView fv = bloom->view();
+		rl = (uint32_t)env_u64("NTB_BIN_REGION_LOG2", bloom->counting ? 24 : 27); // 16 MB regions: two of them hot at a time
+		if (rl < 3) {
+			rl = 3;
+		}
+		while (rl <= 32 && ((fv.mod + (1ull << rl) - 1) >> rl) > (uint64_t)BIN_MAX_BUCKETS) {
+			rl++;
+		}
+		if (rl > 32) {
+			return false;
+		}
+		nb = (uint32_t)((fv.mod + (1ull << rl) - 1) >> rl);
+		return true;
+	}
+
+	int scan_binned(const KParams& kp, uint32_t rl, uint32_t nb)
+	{
+		const uint64_t H = bloom->h;
+		const uint64_t budget_records = (env_u64("NTB_BIN_SCRATCH_MB", 8192) << 20) / 8;
+		uint64_t chunk_tiles = budget_records / (uint64_t)((double)SCAN_TILE * (double)H * 1.06);
+		chunk_tiles = std::max<uint64_t>(1, std::min<uint64_t>(chunk_tiles, batch->n_tiles));
+		chunk_tiles = std::min<uint64_t>(chunk_tiles, (0xFFFFFFFFull / SCAN_TILE) - 1); // record positions are 32-bit
+		uint64_t cap = (uint64_t)((double)(chunk_tiles * SCAN_TILE * H) / (double)nb * 1.04) + 4096;
+		cap = env_u64("NTB_BIN_BUCKET_CAP", cap); // testing aid: small rows force the direct-probe overflow path
+		cap = (cap + 31) & ~31ull;
+		if (cap > 0xFFFFFFE0ull) {
+			cap = 0xFFFFFFE0ull;
+		}
+		const size_t need = (size_t)nb * cap;
+		if (need > ws->cap_records) {
+			cudaFree(ws->d_records);
+			ws->d_records = nullptr;
+			ws->cap_records = 0;
+			NTB_BE(cudaMalloc((void**)&ws->d_records, need * 8));
+			ws->cap_records = need;
+		}
+		if (!ws->d_cursor) {
+			NTB_BE(cudaMalloc((void**)&ws->d_cursor, (BIN_MAX_BUCKETS + 1) * sizeof(uint32_t)));
+		}
+		BinArgs A;
+		std::memset(&A, 0, sizeof A);
+		A.scan.filter = bloom->view();
+		A.scan.k = kp.k;
+		A.scan.min_threshold = kp.min_threshold;
+		fill_scan_tables(A.scan, kp.k);
+		A.records = ws->d_records;
+		A.cursor = ws->d_cursor;
+		A.bucket_cap = (uint32_t)cap;
+		A.n_buckets = nb;
+		A.region_log2 = rl;
+		const int sms = sm_count(batch->device);
+		NTB_BE(cudaEventRecord(ws->ev0, ws->stream));
+		NTB_BE(cudaMemsetAsync(ws->d_visit, 0, batch->n_tiles * SCAN_BITWORDS * 4, ws->stream));
+		for (uint64_t t0 = 0; t0 < batch->n_tiles; t0 += chunk_tiles) {
+			const uint64_t nt = std::min<uint64_t>(chunk_tiles, batch->n_tiles - t0);
+			A.scan.text = batch->d_text + t0 * SCAN_TILE;
+			A.scan.n_tiles = nt;
+			A.scan.visit = ws->d_visit + t0 * SCAN_BITWORDS;
+			A.chunk_base = t0 * SCAN_TILE;
+			NTB_BE(cudaMemsetAsync(ws->d_cursor, 0, (BIN_MAX_BUCKETS + 1) * sizeof(uint32_t), ws->stream));
+			NTB_BE(launch_scan_binned(A, bloom->counting != 0, (int)std::min<uint64_t>(nt, (uint64_t)sms * 2),
+			                          (int)env_u64("NTB_BIN_PROBE_CTAS_PER_SM", 4), ws->stream));
+			launches += 2;
+		}
+		NTB_BE(cudaEventRecord(ws->ev1, ws->stream));
+		return NTB_OK;
+	}
+
 	int scan_impl(const KParams& kp)
 	{
+		uint32_t rl = 0, nb = 0;
+		if (batch->n_tiles > 0 && binned_geometry(kp, rl, nb)) {
+			return scan_binned(kp, rl, nb);
+		}
 		ScanArgs a;
 		std::memset(&a, 0, sizeof a);
 		a.text = batch->d_text;

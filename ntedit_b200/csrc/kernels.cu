@@ -324,6 +324,400 @@ launch_scan(const ScanArgs& a, bool counting, bool extra, int grid, cudaStream_t
 }
 
 // ------------------------------------------------------------------------------------------------------------------
+// K1b: binned scan (see kernels.cuh)
+__device__ __forceinline__ uint64_t
+policy_evict_first()
+{
+	uint64_t p;
+	asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+	return p;
+}
+
+__device__ __forceinline__ uint64_t
+policy_evict_last()
+{
+	uint64_t p;
+	asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+	return p;
+}
+
+// the probe a record stands for, done on the spot: is the k-mer's bit clear / its counter below the threshold?
+template<bool COUNTING>
+__device__ __forceinline__ bool
+probe_misses(const uint8_t* data, uint64_t slot, uint32_t thr)
+{
+	if (COUNTING) {
+		return ld_filter_u8(data + slot) < thr;
+	}
+	return ((ld_filter_u8(data + (slot >> 3)) >> ((uint32_t)slot & 7u)) & 1u) == 0;
+}
+
+template<int H, bool COUNTING>
+__global__ void __launch_bounds__(SCAN_THREADS, 2)
+bin_kernel(const __grid_constant__ BinArgs A)
+{
+	const ScanArgs& a = A.scan;
+	constexpr int RR = SCAN_THREADS * BIN_POS_PER_ROUND * H; // records a round can produce
+	extern __shared__ __align__(128) uint8_t smem[];
+	uint8_t* stage_buf = smem;                                                // SCAN_STAGES * SCAN_STAGE_BYTES
+	uint64_t* sorted = (uint64_t*)(smem + SCAN_STAGES * SCAN_STAGE_BYTES);    // the round's records, grouped by bucket
+	uint16_t* sorted_b = (uint16_t*)(sorted + RR);                            // their buckets
+	uint32_t* cnt = (uint32_t*)(sorted_b + RR);                               // per bucket: records of this round
+	uint32_t* off = cnt + BIN_MAX_BUCKETS;                                    // per bucket: start inside sorted[]
+	uint32_t* gbase = off + BIN_MAX_BUCKETS;                                  // per bucket: start inside the bucket's global rows
+	uint32_t* wsum = gbase + BIN_MAX_BUCKETS;                                 // [0..8) warp totals, [8] round total
+	uint8_t* cls = (uint8_t*)(wsum + 16);                                     // 256
+	uint64_t* tab = (uint64_t*)(cls + 256);                                   // seed[8], rotk[8]
+	uint64_t* bars = tab + 16;                                                // SCAN_STAGES mbarriers
+
+	const int tid = threadIdx.x;
+	const int lane = tid & 31, warp = tid >> 5;
+	for (int i = tid; i < 256; i += SCAN_THREADS) {
+		cls[i] = class_of((unsigned)i);
+	}
+	for (int i = tid; i < BIN_MAX_BUCKETS; i += SCAN_THREADS) {
+		cnt[i] = 0;
+	}
+	if (tid < 8) {
+		tab[tid] = tid < 5 ? a.seed[tid] : 0;
+		tab[8 + tid] = tid < 5 ? a.rotk[tid] : 0;
+	}
+	if (tid == 0) {
+		for (int s = 0; s < SCAN_STAGES; s++) {
+			mbar_init(&bars[s], 1);
+		}
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+	}
+	__syncthreads();
+
+	const uint32_t k = a.k;
+	const int warm = (int)((k + 3) & ~3u);
+	const int oshift = 8 * (int)((0u - k) & 3u);
+	const int strip0 = SCAN_HALO + tid * SCAN_STRIP;
+	const FilterView& F = a.filter;
+	const uint32_t rl = A.region_log2;
+	const uint64_t rmask = (1ULL << rl) - 1ULL;
+	const uint32_t nb = A.n_buckets;
+	const uint32_t cap = A.bucket_cap;
+	const uint32_t thr = a.min_threshold > 1u ? a.min_threshold : 1u;
+
+	uint64_t tile = blockIdx.x;
+	uint32_t phase[SCAN_STAGES];
+	for (int s = 0; s < SCAN_STAGES; s++) {
+		phase[s] = 0;
+	}
+	int stage = 0;
+	if (tid == 0 && tile < a.n_tiles) {
+		mbar_expect_tx(&bars[0], SCAN_STAGE_BYTES);
+		bulk_copy_g2s(stage_buf, a.text + tile * SCAN_TILE - SCAN_HALO, SCAN_STAGE_BYTES, &bars[0]);
+	}
+	for (; tile < a.n_tiles; tile += gridDim.x) {
+		const uint64_t next = tile + gridDim.x;
+		if (tid == 0 && next < a.n_tiles) {
+			asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+			mbar_expect_tx(&bars[stage ^ 1], SCAN_STAGE_BYTES);
+			bulk_copy_g2s(stage_buf + (stage ^ 1) * SCAN_STAGE_BYTES, a.text + next * SCAN_TILE - SCAN_HALO, SCAN_STAGE_BYTES,
+			              &bars[stage ^ 1]);
+		}
+		mbar_wait(&bars[stage], phase[stage]);
+		phase[stage] ^= 1;
+		const uint8_t* st = stage_buf + stage * SCAN_STAGE_BYTES;
+
+		// ---- warm-up: hash of the window that ends just before the strip (as in scan_kernel)
+		uint64_t f = 0, r = 0;
+		uint32_t run = 0;
+		{
+			const int w0 = strip0 - warm;
+			const uint32_t first = *(const uint32_t*)(st + w0);
+			for (int j = 0; j < warm; j += 4) {
+				const uint32_t w = *(const uint32_t*)(st + w0 + j);
+#pragma unroll
+				for (int b = 0; b < 4; b++) {
+					const uint32_t ci = cls[(w >> (8 * b)) & 0xFF];
+					uint64_t fo = 0, ro = 0;
+					if ((uint32_t)(j + b) >= k) {
+						const uint32_t co = cls[(first >> (8 * (j + b - (int)k))) & 0xFF];
+						fo = tab[8 + (co & 7)];
+						ro = tab[(co >> 3) & 7];
+					}
+					f = srol1(f) ^ tab[ci & 7] ^ fo;
+					r = sror1(r ^ tab[8 + ((ci >> 3) & 7)] ^ ro);
+					run = (ci & 0x40) ? run + 1 : 0;
+				}
+			}
+		}
+
+		const int o0 = strip0 - (int)k;
+		uint32_t wlo = *(const uint32_t*)(st + (o0 & ~3));
+		const uint32_t pos0 = (uint32_t)(tile * SCAN_TILE) + (uint32_t)tid * SCAN_STRIP; // position inside the chunk
+		for (int wi = 0; wi < SCAN_STRIP / 4; wi++) {
+			const uint32_t win = *(const uint32_t*)(st + strip0 + 4 * wi);
+			const uint32_t whi = *(const uint32_t*)(st + (o0 & ~3) + 4 * wi + 4);
+			const uint32_t wout = __funnelshift_r(wlo, whi, oshift);
+			wlo = whi;
+			// ---- (a) the round's records: slot inside its region, bucket, rank inside the bucket (shared atomics)
+			uint32_t rsir[4 * H];
+			uint32_t rbr[4 * H]; // bucket << 16 | rank ; 0xFFFFFFFF = no record
+#pragma unroll
+			for (int b = 0; b < 4; b++) {
+				const uint32_t ci = cls[(win >> (8 * b)) & 0xFF];
+				const uint32_t co = cls[(wout >> (8 * b)) & 0xFF];
+				f = srol1(f) ^ tab[ci & 7] ^ tab[8 + (co & 7)];
+				r = sror1(r ^ tab[8 + ((ci >> 3) & 7)] ^ tab[(co >> 3) & 7]);
+				run = (ci & 0x40) ? run + 1 : 0;
+				const bool valid = run >= k;
+				const uint64_t base = f + r;
+#pragma unroll
+				for (int i = 0; i < H; i++) {
+					uint64_t hv = base;
+					if (i > 0) {
+						hv *= a.mult[i];
+						hv ^= hv >> MULTISHIFT;
+					}
+					const uint64_t slot = filter_slot(F, hv);
+					const uint32_t bucket = (uint32_t)(slot >> rl);
+					rsir[b * H + i] = (uint32_t)(slot & rmask);
+					rbr[b * H + i] = valid ? ((bucket << 16) | atomicAdd(&cnt[bucket], 1u)) : 0xFFFFFFFFu;
+				}
+			}
+			__syncthreads();
+			// ---- (b) one thread per bucket: reserve the global rows, scan the counts
+			uint32_t c = 0;
+			if ((uint32_t)tid < nb) {
+				c = cnt[tid];
+				cnt[tid] = 0;
+			}
+			uint32_t incl = c;
+#pragma unroll
+			for (int o = 1; o < 32; o <<= 1) {
+				const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+				if (lane >= o) {
+					incl += v;
+				}
+			}
+			if (lane == 31) {
+				wsum[warp] = incl;
+			}
+			uint32_t g = 0;
+			if (c) {
+				g = atomicAdd(&A.cursor[tid], c);
+			}
+			__syncthreads();
+			uint32_t woff = 0;
+#pragma unroll
+			for (int w = 0; w < SCAN_THREADS / 32; w++) {
+				woff += w < warp ? wsum[w] : 0u;
+			}
+			if ((uint32_t)tid < nb) {
+				off[tid] = woff + incl - c;
+				gbase[tid] = g;
+			}
+			if (tid == SCAN_THREADS - 1) {
+				wsum[8] = woff + incl;
+			}
+			__syncthreads();
+			// ---- (c) group the records by bucket
+#pragma unroll
+			for (int q = 0; q < 4 * H; q++) {
+				if (rbr[q] != 0xFFFFFFFFu) {
+					const uint32_t bucket = rbr[q] >> 16;
+					const uint32_t j = off[bucket] + (rbr[q] & 0xFFFFu);
+					sorted[j] = ((uint64_t)rsir[q] << 32) | (uint64_t)(pos0 + 4 * wi + q / H);
+					sorted_b[j] = (uint16_t)bucket;
+				}
+			}
+			__syncthreads();
+			// ---- (d) contiguous runs out to the buckets' rows
+			const uint32_t total = wsum[8];
+			for (uint32_t j = tid; j < total; j += SCAN_THREADS) {
+				const uint32_t bucket = sorted_b[j];
+				const uint64_t rec = sorted[j];
+				const uint32_t idx = gbase[bucket] + (j - off[bucket]);
+				if (idx < cap) {
+					A.records[(uint64_t)bucket * cap + idx] = rec;
+				} else {
+					// the bucket's rows are full (heavily repeated k-mers): probe directly
+					const uint64_t slot = ((uint64_t)bucket << rl) | (rec >> 32);
+					if (probe_misses<COUNTING>(F.data, slot, thr)) {
+						const uint32_t pos = (uint32_t)rec;
+						atomicOr(&a.visit[pos >> 5], 1u << (pos & 31));
+					}
+				}
+			}
+			// the next round's shared atomics may start: cnt[] was cleared in (b); sorted[] / off[] / gbase[] are only written
+			// again after the next round's first barrier, which every thread reaches after finishing (d)
+		}
+		__syncthreads(); // tile consumed: its stage may be refilled
+		stage ^= 1;
+	}
+}
+
+__device__ __forceinline__ ulonglong2
+ld_records_stream(const uint64_t* p, uint64_t policy)
+{
+	ulonglong2 v;
+	asm("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.u64 {%0, %1}, [%2], %3;" : "=l"(v.x), "=l"(v.y) : "l"(p), "l"(policy));
+	return v;
+}
+
+__device__ __forceinline__ uint32_t
+ld_filter_keep(const uint8_t* p, uint64_t policy)
+{
+	uint32_t v;
+	asm("ld.global.nc.L1::no_allocate.L2::cache_hint.u8 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(policy));
+	return v;
+}
+
+template<bool COUNTING>
+__global__ void __launch_bounds__(256)
+probe_bin_kernel(const __grid_constant__ BinArgs A)
+{
+	constexpr int U = 4; // 16-byte record loads in flight per thread
+	const uint64_t pol_stream = policy_evict_first();
+	const uint64_t pol_keep = policy_evict_last();
+	const uint32_t rl = A.region_log2;
+	const uint32_t cap = A.bucket_cap;
+	const uint32_t thr = A.scan.min_threshold > 1u ? A.scan.min_threshold : 1u;
+	uint32_t* visit = A.scan.visit;
+	const uint64_t gtid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	const uint64_t gstride = (uint64_t)gridDim.x * blockDim.x;
+	// pacing: the probes only hit L2 while every CTA works on (nearly) the same region, so a CTA may run at most one
+	// bucket ahead of the slowest one -- at most two regions are hot at any time.  A.cursor[BIN_MAX_BUCKETS] counts the
+	// (CTA, bucket) pairs that are done; the grid is launched cooperatively, so every CTA is resident and the wait ends.
+	unsigned int* done = A.cursor + BIN_MAX_BUCKETS;
+	for (uint32_t b = 0; b < A.n_buckets; b++) {
+		if (b >= 2) {
+			if (threadIdx.x == 0) {
+				const unsigned int target = (b - 1) * gridDim.x;
+				unsigned int seen;
+				do {
+					asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(done) : "memory");
+				} while (seen < target);
+			}
+			__syncthreads();
+		}
+		const uint32_t have = A.cursor[b];
+		const uint32_t n = have < cap ? have : cap;
+		const uint64_t* recs = A.records + (uint64_t)b * cap;
+		const uint8_t* region = A.scan.filter.data + (COUNTING ? ((uint64_t)b << rl) : ((uint64_t)b << (rl - 3)));
+		const uint64_t npair = n >> 1;
+		for (uint64_t p0 = gtid; p0 < npair; p0 += gstride * U) {
+			ulonglong2 rec[U];
+#pragma unroll
+			for (int u = 0; u < U; u++) {
+				const uint64_t p = p0 + (uint64_t)u * gstride;
+				rec[u] = make_ulonglong2(~0ULL, ~0ULL);
+				if (p < npair) {
+					rec[u] = ld_records_stream(recs + 2 * p, pol_stream);
+				}
+			}
+			uint32_t got[2 * U];
+#pragma unroll
+			for (int u = 0; u < U; u++) {
+				const uint64_t r0 = rec[u].x, r1 = rec[u].y;
+				const uint32_t s0 = (uint32_t)(r0 >> 32), s1 = (uint32_t)(r1 >> 32);
+				got[2 * u] = 0xFFu;
+				got[2 * u + 1] = 0xFFu;
+				if (r0 != ~0ULL) {
+					got[2 * u] = ld_filter_keep(region + (COUNTING ? s0 : (s0 >> 3)), pol_keep);
+				}
+				if (r1 != ~0ULL) {
+					got[2 * u + 1] = ld_filter_keep(region + (COUNTING ? s1 : (s1 >> 3)), pol_keep);
+				}
+			}
+#pragma unroll
+			for (int u = 0; u < U; u++) {
+#pragma unroll
+				for (int h = 0; h < 2; h++) {
+					const uint64_t rr = h ? rec[u].y : rec[u].x;
+					const uint32_t v = got[2 * u + h];
+					const bool miss = COUNTING ? (v < thr) : (((v >> ((uint32_t)(rr >> 32) & 7u)) & 1u) == 0);
+					if (rr != ~0ULL && miss) {
+						const uint32_t pos = (uint32_t)rr;
+						atomicOr(&visit[pos >> 5], 1u << (pos & 31));
+					}
+				}
+			}
+		}
+		if ((n & 1u) && gtid == 0) {
+			const uint64_t rr = recs[n - 1];
+			const uint64_t slot = ((uint64_t)b << rl) | (rr >> 32);
+			if (probe_misses<COUNTING>(A.scan.filter.data, slot, thr)) {
+				const uint32_t pos = (uint32_t)rr;
+				atomicOr(&visit[pos >> 5], 1u << (pos & 31));
+			}
+		}
+		__syncthreads();
+		if (threadIdx.x == 0) {
+			atomicAdd(done, 1u);
+		}
+	}
+}
+
+template<int H>
+static cudaError_t
+launch_bin_h(const BinArgs& a, bool counting, int grid, cudaStream_t stream)
+{
+	const size_t smem = bin_smem_bytes(H);
+	cudaError_t e;
+	if (counting) {
+		e = cudaFuncSetAttribute(bin_kernel<H, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+		if (e != cudaSuccess) {
+			return e;
+		}
+		bin_kernel<H, true><<<grid, SCAN_THREADS, smem, stream>>>(a);
+	} else {
+		e = cudaFuncSetAttribute(bin_kernel<H, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+		if (e != cudaSuccess) {
+			return e;
+		}
+		bin_kernel<H, false><<<grid, SCAN_THREADS, smem, stream>>>(a);
+	}
+	return cudaGetLastError();
+}
+
+cudaError_t
+launch_scan_binned(const BinArgs& a, bool counting, int grid_bin, int grid_probe, cudaStream_t stream)
+{
+	if (a.n_buckets == 0 || a.n_buckets > (uint32_t)BIN_MAX_BUCKETS || a.region_log2 < 3 || a.region_log2 > 32) {
+		return cudaErrorInvalidValue;
+	}
+	cudaError_t e;
+	switch (a.scan.filter.hash_num) {
+	case 1: e = launch_bin_h<1>(a, counting, grid_bin, stream); break;
+	case 2: e = launch_bin_h<2>(a, counting, grid_bin, stream); break;
+	case 3: e = launch_bin_h<3>(a, counting, grid_bin, stream); break;
+	case 4: e = launch_bin_h<4>(a, counting, grid_bin, stream); break;
+	case 5: e = launch_bin_h<5>(a, counting, grid_bin, stream); break;
+	case 6: e = launch_bin_h<6>(a, counting, grid_bin, stream); break;
+	case 7: e = launch_bin_h<7>(a, counting, grid_bin, stream); break;
+	case 8: e = launch_bin_h<8>(a, counting, grid_bin, stream); break;
+	default: return cudaErrorInvalidValue;
+	}
+	if (e != cudaSuccess) {
+		return e;
+	}
+	// cooperative launch: all CTAs resident (the kernel paces itself across CTAs); grid_probe = CTAs per SM wanted
+	static int per_sm[2] = { 0, 0 };
+	const void* fn = counting ? (const void*)probe_bin_kernel<true> : (const void*)probe_bin_kernel<false>;
+	if (per_sm[counting ? 1 : 0] == 0) {
+		int n = 0;
+		e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fn, 256, 0);
+		if (e != cudaSuccess) {
+			return e;
+		}
+		per_sm[counting ? 1 : 0] = n > 0 ? n : 1;
+	}
+	int dev = 0, sms = 148;
+	cudaGetDevice(&dev);
+	cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+	const int want = grid_probe > 0 && grid_probe < per_sm[counting ? 1 : 0] ? grid_probe : per_sm[counting ? 1 : 0];
+	BinArgs args = a;
+	void* params[1] = { (void*)&args };
+	return cudaLaunchCooperativeKernel(fn, dim3((unsigned)(sms * want)), dim3(256), params, 0, stream);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
 // K2
 // K2: persistent warps, one task (contig segment) per warp at a time, tasks handed out through an atomic counter.
 // The walker state of every warp lives in shared memory (engine.h: WalkerState); lane 0 is the leader.

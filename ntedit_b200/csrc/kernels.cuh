@@ -51,6 +51,41 @@ struct ScanArgs
 // launches scan_kernel<hash_num, counting, extra> on `grid` persistent CTAs
 cudaError_t launch_scan(const ScanArgs& a, bool counting, bool extra, int grid, cudaStream_t stream);
 
+// ------------------------------------------------------------------------------------------------------------------
+// K1b: binned scan.  B200's L2 fetches a whole 128-byte line from DRAM for every missed sector, so a random 1-bit probe
+// into a multi-GB filter costs 128 bytes of HBM traffic (profiles/r01_*).  The binned scan therefore does not load the
+// filter while it hashes: bin_kernel turns every probe into an 8-byte record
+//     (position within the text chunk : 32 | slot within the filter region : 32)
+// appended to the bucket of the filter REGION (2^region_log2 slots, sized to sit in L2) the probe falls into; records are
+// counting-sorted per round in shared memory and leave the SM as contiguous runs.  probe_bin_kernel then walks the buckets
+// one after the other, every CTA on the same bucket, so that the probes of a bucket hit the one region that is L2-resident;
+// a failed probe sets the visit bit of its position.  Same visit bitmap as scan_kernel, bit for bit.
+constexpr int BIN_POS_PER_ROUND = 4;                             // positions per thread and round (same step as K1)
+constexpr int BIN_MAX_BUCKETS = SCAN_THREADS;                    // one thread per bucket in the per-round scan
+constexpr int BIN_ROUND_RECORDS = SCAN_THREADS * BIN_POS_PER_ROUND * (int)HMAX; // upper bound for the template maximum
+inline size_t
+bin_smem_bytes(int hash_num)
+{
+	const size_t round_records = (size_t)SCAN_THREADS * BIN_POS_PER_ROUND * (size_t)hash_num;
+	return (size_t)SCAN_STAGES * SCAN_STAGE_BYTES + round_records * 8 + round_records * 2 + 3 * BIN_MAX_BUCKETS * 4 + 16 * 4 + 256 + 16 * 8 +
+	       SCAN_STAGES * 8 + 64;
+}
+
+struct BinArgs
+{
+	ScanArgs scan;          // text, filter, tables, visit (n_tiles = tiles of this chunk, text = chunk start)
+	uint64_t chunk_base;    // text position of the chunk's first tile (multiple of SCAN_TILE)
+	uint64_t* records;      // n_buckets x bucket_cap
+	uint32_t* cursor;       // records appended per bucket (may exceed bucket_cap: the excess was probed directly)
+	uint32_t bucket_cap;
+	uint32_t n_buckets;
+	uint32_t region_log2;   // slots per region = 1 << region_log2
+};
+
+// launches bin_kernel<hash_num, counting> on `grid_bin` persistent CTAs and probe_bin_kernel<counting> cooperatively on
+// min(grid_probe, occupancy) CTAs per SM; `cursor` has BIN_MAX_BUCKETS + 1 zeroed entries (the last one paces the probe CTAs)
+cudaError_t launch_scan_binned(const BinArgs& a, bool counting, int grid_bin, int grid_probe, cudaStream_t stream);
+
 // K2 geometry: WALK_TEAMS walkers per CTA, each with its own WalkerState in dynamic shared memory
 #ifndef NTB_WALK_WARPS
 #define NTB_WALK_WARPS 2

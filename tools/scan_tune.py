@@ -1,0 +1,50 @@
+#!/usr/bin/env python
+"""Tuning aid: builds bench.py's workload once, then times the scan stage (K1 / K1b) under several environment settings.
+usage: python tools/scan_tune.py [workload] 'NAME=VAL,NAME=VAL' 'NAME=VAL' ...   ('' = defaults)"""
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch  # noqa: E402
+
+import bench  # noqa: E402
+import ntedit_b200 as nb  # noqa: E402
+
+
+def main():
+    args = sys.argv[1:]
+    workload = "3Gbp_k25_4GiB_m1"
+    if args and args[0] in bench.WORKLOADS:
+        workload = args.pop(0)
+    w = bench.WORKLOADS[workload]
+    nb.lib.load()
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(0)
+    filt = torch.zeros(w["fbytes"] + 64, dtype=torch.uint8, device=dev)
+    bloom = nb.BloomFilter.wrap_device(filt.data_ptr(), w["fbytes"], bench.K, bench.H, counting=False, device=0)
+    buf, offs = bench.build_workload(w, dev, 0, bloom, nb)
+    torch.cuda.synchronize()
+    batch = nb.Batch.wrap_device(buf.data_ptr(), offs, device=0)
+    params = nb.default_params(mode=w["mode"])
+    base_env = dict(os.environ)
+    for cfg in (args or [""]):
+        os.environ.clear()
+        os.environ.update(base_env)
+        for kv in [x for x in cfg.split(",") if x]:
+            k, v = kv.split("=")
+            os.environ[k] = v
+        out = []
+        for _ in range(3):
+            res = nb.kmerize_and_correct_device(batch, bloom, params, host_buf=None)
+            st = res.stats().as_dict()
+            res.free()
+            out.append(st)
+        st = out[-1]
+        print(json.dumps({"env": cfg, "ms_scan": [round(o["ms_scan"], 2) for o in out], "ms_walk": round(st["ms_walk"], 2),
+                          "launches": st["kernel_launches"], "sites": st["sites"], "edits": st["edits"]}), flush=True)
+
+
+if __name__ == "__main__":
+    main()
