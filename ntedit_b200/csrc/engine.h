@@ -188,7 +188,10 @@ struct WalkerIO
 
 constexpr uint32_t MAX_INS_TRIES = 341;   // num_tries[5], ntedit.cpp:172
 constexpr uint32_t MAX_DELETIONS = 10;    // ntedit.cpp:2489-2493
-constexpr int PROBE_G = 10;               // sampled k-mers whose probes are in flight together, per lane
+#ifndef NTB_PROBE_G
+#define NTB_PROBE_G 10
+#endif
+constexpr int PROBE_G = NTB_PROBE_G;              // sampled k-mers whose probes are in flight together, per lane
 constexpr int PROBE_HU = 4;               // hash functions probed per pass (hash_num <= HMAX takes ceil(h/4) passes)
 constexpr uint32_t TEXT_CACHE = 256;      // bytes of contig text kept in the shared state around the window
 constexpr uint32_t LOOKAHEAD = 32;        // dirty-window positions whose site test is evaluated in one pass
@@ -335,10 +338,24 @@ struct Walker
 	static constexpr int OVCAP = WalkerState<NCAP>::OVCAP;
 	static constexpr int PREVCAP = 2 * KMAX + 16;
 
-	WalkerState<NCAP>& S;
 	const KParams& P;
-
-	NTB_FN Walker(WalkerState<NCAP>& s_, const KParams& p_) : S(s_), P(p_) {}
+#if defined(__CUDA_ARCH__)
+	// Device: the state of this team lives in the CTA's dynamic shared memory (walk_kernel lays the teams' states out from
+	// offset 0).  Every member function re-derives its address from the __shared__ symbol instead of keeping a reference in
+	// the object: a reference would be a generic pointer once `this` escapes into a non-inlined call, and every state access
+	// a generic LD/ST; this way they are LDS/STS.
+	__device__ __forceinline__ WalkerState<NCAP>& state_() const
+	{
+		extern __shared__ __align__(16) uint8_t ntb_walk_smem[];
+		return reinterpret_cast<WalkerState<NCAP>*>(ntb_walk_smem)[threadIdx.x / NTB_TEAM];
+	}
+	__device__ Walker(WalkerState<NCAP>&, const KParams& p_) : P(p_) {}
+#else
+	WalkerState<NCAP>& S_;
+	WalkerState<NCAP>& state_() const { return S_; }
+	Walker(WalkerState<NCAP>& s_, const KParams& p_) : P(p_), S_(s_) {}
+#endif
+#define S (state_())
 
 	// ---------------------------------------------------------------- text / rope access
 	NTB_FN unsigned char rd(uint32_t pos) const
@@ -2339,6 +2356,7 @@ struct Walker
 		}
 		finish(res);
 	}
+#undef S
 };
 
 } // namespace ntb
