@@ -332,30 +332,40 @@ struct WalkerState
 constexpr uint32_t ACT_STOP = 0, ACT_CLEAN = 1, ACT_DIRTY = 2;
 constexpr uint32_t NEXT_CAND = 0, NEXT_INDELS = 1, NEXT_STOP = 2;
 
+constexpr uint32_t WALK_KP_BYTES = (sizeof(KParams) + 127u) & ~127u; // device: the CTA's copy of the parameters sits in front of the team states
+
 template<int NCAP>
 struct Walker
 {
 	static constexpr int OVCAP = WalkerState<NCAP>::OVCAP;
 	static constexpr int PREVCAP = 2 * KMAX + 16;
 
-	const KParams& P;
 #if defined(__CUDA_ARCH__)
 	// Device: the state of this team lives in the CTA's dynamic shared memory (walk_kernel lays the teams' states out from
 	// offset 0).  Every member function re-derives its address from the __shared__ symbol instead of keeping a reference in
 	// the object: a reference would be a generic pointer once `this` escapes into a non-inlined call, and every state access
 	// a generic LD/ST; this way they are LDS/STS.
+	// Layout of the dynamic shared memory: [KParams copy, WALK_KP_BYTES][team states][rotation table].
 	__device__ __forceinline__ WalkerState<NCAP>& state_() const
 	{
 		extern __shared__ __align__(16) uint8_t ntb_walk_smem[];
-		return reinterpret_cast<WalkerState<NCAP>*>(ntb_walk_smem)[threadIdx.x / NTB_TEAM];
+		return reinterpret_cast<WalkerState<NCAP>*>(ntb_walk_smem + WALK_KP_BYTES)[threadIdx.x / NTB_TEAM];
 	}
-	__device__ Walker(WalkerState<NCAP>&, const KParams& p_) : P(p_) {}
+	__device__ __forceinline__ const KParams& params_() const
+	{
+		extern __shared__ __align__(16) uint8_t ntb_walk_smem[];
+		return *reinterpret_cast<const KParams*>(ntb_walk_smem);
+	}
+	__device__ Walker(WalkerState<NCAP>&, const KParams&) {}
 #else
 	WalkerState<NCAP>& S_;
+	const KParams& P_;
 	WalkerState<NCAP>& state_() const { return S_; }
-	Walker(WalkerState<NCAP>& s_, const KParams& p_) : P(p_), S_(s_) {}
+	const KParams& params_() const { return P_; }
+	Walker(WalkerState<NCAP>& s_, const KParams& p_) : S_(s_), P_(p_) {}
 #endif
 #define S (state_())
+#define P (params_())
 
 	// ---------------------------------------------------------------- text / rope access
 	NTB_FN unsigned char rd(uint32_t pos) const
@@ -2357,6 +2367,7 @@ struct Walker
 		finish(res);
 	}
 #undef S
+#undef P
 };
 
 } // namespace ntb
