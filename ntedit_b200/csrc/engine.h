@@ -332,6 +332,7 @@ struct WalkerState
 constexpr uint32_t ACT_STOP = 0, ACT_CLEAN = 1, ACT_DIRTY = 2;
 constexpr uint32_t NEXT_CAND = 0, NEXT_INDELS = 1, NEXT_STOP = 2;
 
+constexpr uint32_t WALK_ROT_BYTES = (ROT_WORDS * 8u + 127u) & ~127u;
 constexpr uint32_t WALK_KP_BYTES = (sizeof(KParams) + 127u) & ~127u; // device: the CTA's copy of the parameters sits in front of the team states
 
 template<int NCAP>
@@ -345,11 +346,16 @@ struct Walker
 	// offset 0).  Every member function re-derives its address from the __shared__ symbol instead of keeping a reference in
 	// the object: a reference would be a generic pointer once `this` escapes into a non-inlined call, and every state access
 	// a generic LD/ST; this way they are LDS/STS.
-	// Layout of the dynamic shared memory: [KParams copy, WALK_KP_BYTES][team states][rotation table].
+	// Layout of the dynamic shared memory: [KParams copy, WALK_KP_BYTES][rotation table, WALK_ROT_BYTES][team states].
 	__device__ __forceinline__ WalkerState<NCAP>& state_() const
 	{
 		extern __shared__ __align__(16) uint8_t ntb_walk_smem[];
-		return reinterpret_cast<WalkerState<NCAP>*>(ntb_walk_smem + WALK_KP_BYTES)[threadIdx.x / NTB_TEAM];
+		return reinterpret_cast<WalkerState<NCAP>*>(ntb_walk_smem + WALK_KP_BYTES + WALK_ROT_BYTES)[threadIdx.x / NTB_TEAM];
+	}
+	__device__ __forceinline__ const uint64_t* rot_() const
+	{
+		extern __shared__ __align__(16) uint8_t ntb_walk_smem[];
+		return reinterpret_cast<const uint64_t*>(ntb_walk_smem + WALK_KP_BYTES);
 	}
 	__device__ __forceinline__ const KParams& params_() const
 	{
@@ -362,6 +368,7 @@ struct Walker
 	const KParams& P_;
 	WalkerState<NCAP>& state_() const { return S_; }
 	const KParams& params_() const { return P_; }
+	const uint64_t* rot_() const { return S_.io.rot; }
 	Walker(WalkerState<NCAP>& s_, const KParams& p_) : S_(s_), P_(p_) {}
 #endif
 #define S (state_())
@@ -1078,7 +1085,7 @@ struct Walker
 		bool direct = S.n_rolls >= k && k <= ROT_STRIDE;
 		if (direct) {
 			// the window after R rolls is lin_out[R..k) ++ lin_in[0..R): hash it from the rotation table, one window per lane
-			const uint64_t* rot = S.io.rot;
+			const uint64_t* rot = rot_();
 			uint32_t bad = 0;
 			for (uint32_t R = ln; R <= n; R += lane_count()) {
 				uint64_t f = 0, r = 0;
@@ -1140,7 +1147,7 @@ struct Walker
 		const uint32_t per_cand = 1 + n_sub;
 		const uint32_t njobs = nC + ncand * per_cand;
 		const uint32_t df = base_code(S.draft), dr = rev_code(S.draft);
-		const uint64_t* rot = S.io.rot;
+		const uint64_t* rot = rot_();
 		warp_sync();
 		for (uint32_t j0 = 0; j0 < njobs; j0 += lane_count() * PROBE_G) {
 			// this lane's jobs of the round: j0 + ln, j0 + ln + lanes, ...
@@ -1330,7 +1337,7 @@ struct Walker
 		}
 		const uint32_t xf = base_code(S.index_char), xr = rev_code(S.index_char);
 		const uint32_t df = base_code(S.draft), dr = rev_code(S.draft);
-		const uint64_t* rot = S.io.rot;
+		const uint64_t* rot = rot_();
 		const uint32_t nv = S.ins_nvalid[L - 1];
 		uint32_t pre_ok = 0, count = 0, nchk = 0;
 		for (uint32_t s0 = 0; s0 < nv; s0 += PROBE_G) {
@@ -1351,11 +1358,79 @@ struct Walker
 		return count;
 	}
 
+	// eval_insertion_fast for the common configuration -- bit filter, no secondary filter: the candidate's sampled k-mers
+	// are hashed from the bases and probed four at a time through registers (first hash function of all four in flight
+	// together; the few k-mers whose first bit is set then check their other bits, stopping at the first clear one --
+	// btllib's early exit, ntedit.cpp:368-371).  Same count as eval_insertion_fast.
+	NTB_FN uint32_t eval_insertion_bits(uint32_t i)
+	{
+		const uint32_t k = P.k, jump = P.jump;
+		uint64_t packed;
+		const uint32_t L = indel_string(S.index_char, i, packed);
+		// seed codes of the synthetic incoming chars: string[1..L-1], then the draft char (ntedit.cpp:1583-1606)
+		uint32_t fc[5], rc[5];
+#pragma unroll
+		for (uint32_t q = 0; q < 5; q++) {
+			const unsigned char c = q + 1 < L ? (unsigned char)((packed >> (8 * (q + 1))) & 0xFF) : S.draft;
+			fc[q] = base_code(c) * ROT_STRIDE;
+			rc[q] = rev_code(c) * ROT_STRIDE;
+		}
+		const uint32_t xf = base_code(S.index_char) * ROT_STRIDE, xr = rev_code(S.index_char) * ROT_STRIDE;
+		const uint32_t df = base_code(S.draft) * ROT_STRIDE, dr = rev_code(S.draft) * ROT_STRIDE;
+		const uint64_t* rot = rot_();
+		const uint64_t* bf = S.ins_base_f[L - 1];
+		const uint64_t* br = S.ins_base_r[L - 1];
+		const uint32_t nv = S.ins_nvalid[L - 1];
+		const FilterView& F = S.io.bloom;
+		const uint32_t hn = F.hash_num;
+		uint32_t count = 0;
+		for (uint32_t s0 = 0; s0 < nv; s0 += 4) {
+			uint64_t hv[4];
+			uint32_t got[4], sh[4];
+#pragma unroll
+			for (uint32_t g = 0; g < 4; g++) {
+				const uint32_t sidx = s0 + g < nv ? s0 + g : nv - 1; // a padding lane repeats the last sample and is not counted
+				const uint32_t R = sidx * jump + 1;                   // rolls done when the sample is taken
+				uint64_t f = bf[sidx] ^ rot[df + R] ^ rot[xf + R];
+				uint64_t r = br[sidx] ^ rot[dr + (k - 1 - R)] ^ rot[xr + (k - 1 - R)];
+				const uint32_t m = L < R ? L : R;
+#pragma unroll
+				for (uint32_t q = 0; q < 5; q++) {
+					if (q < m) {
+						f ^= rot[fc[q] + (R - 1 - q)];
+						r ^= rot[rc[q] + (k - R + q)];
+					}
+				}
+				hv[g] = f + r;
+				const uint64_t slot = filter_slot(F, hv[g]);
+				sh[g] = (uint32_t)slot & 7u;
+				got[g] = probe_byte(F.data + (slot >> 3));
+			}
+#pragma unroll
+			for (uint32_t g = 0; g < 4; g++) {
+				if (s0 + g < nv && ((got[g] >> sh[g]) & 1u)) {
+					bool all = true;
+					for (uint32_t h = 1; h < hn && all; h++) {
+						const uint64_t slot = filter_slot(F, hash_extend(hv[g], k, h));
+						all = ((probe_byte(F.data + (slot >> 3)) >> ((uint32_t)slot & 7u)) & 1u) != 0;
+					}
+					count += all ? 1u : 0u;
+				}
+			}
+		}
+		return count;
+	}
+
 	// insertion candidates [i0, i1) of tryIndels for S.index_char: one per lane, 32 at a time
 	NTB_FN void phase_insertions(uint32_t i0, uint32_t i1)
 	{
 		warp_sync();
+		const bool bits_only = S.ins_fast && !P.counting && !P.h_rep;
 		for (uint32_t i = i0 + lane_id(); i < i1; i += lane_count()) {
+			if (bits_only) {
+				S.ins_sup[i] = (uint8_t)eval_insertion_bits(i);
+				continue;
+			}
 			if (S.ins_fast) {
 				S.ins_sup[i] = (uint8_t)eval_insertion_fast(i);
 				continue;
@@ -2261,7 +2336,7 @@ struct Walker
 				// NTMC64 seeding form (ntedit.cpp:403-416) of the unedited window that ends at the flagged position:
 				// every lane contributes its bases' terms from the rotation table
 				const uint32_t k = P.k, head = S.visit_hit + 1 - k;
-				const uint64_t* rot = S.io.rot;
+				const uint64_t* rot = rot_();
 				for (uint32_t i = lane_id(); i < k; i += lane_count()) {
 					const unsigned char c = text_at(head + i);
 					seed_f ^= rot[base_code(c) * ROT_STRIDE + (k - 1 - i)];

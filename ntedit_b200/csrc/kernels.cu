@@ -728,10 +728,10 @@ walk_kernel(const uint8_t* text, const uint32_t* visit, FilterView bloom, Filter
             const Task* tasks, const uint32_t* order, TaskResult* results, uint32_t n_tasks, Event* events, uint32_t ev_cap, Counters* ctr)
 {
 	extern __shared__ __align__(16) uint8_t walk_smem[];
-	// [KParams copy][team states][rotation table] -- engine.h's Walker finds its state and the parameters by this layout
-	WalkerState<NCAP>* states = reinterpret_cast<WalkerState<NCAP>*>(walk_smem + WALK_KP_BYTES);
+	// [KParams copy][rotation table][team states] -- engine.h's Walker finds all three by this layout
+	WalkerState<NCAP>* states = reinterpret_cast<WalkerState<NCAP>*>(walk_smem + WALK_KP_BYTES + WALK_ROT_BYTES);
 	WalkerState<NCAP>& S = states[threadIdx.x / NTB_TEAM];
-	uint64_t* rot = reinterpret_cast<uint64_t*>(walk_smem + WALK_KP_BYTES + (size_t)WALK_TEAMS * sizeof(WalkerState<NCAP>));
+	uint64_t* rot = reinterpret_cast<uint64_t*>(walk_smem + WALK_KP_BYTES);
 	for (uint32_t q = threadIdx.x; q < sizeof(KParams) / 4; q += WALK_THREADS) {
 		reinterpret_cast<uint32_t*>(walk_smem)[q] = reinterpret_cast<const uint32_t*>(&kp)[q];
 	}
@@ -839,7 +839,7 @@ launch_walk_n(const uint8_t* text, const uint32_t* visit, const FilterView& bloo
               cudaStream_t stream)
 {
 	static int blocks_per_sm = 0;
-	const size_t smem = WALK_KP_BYTES + (size_t)WALK_TEAMS * sizeof(WalkerState<NCAP>) + ROT_WORDS * sizeof(uint64_t);
+	const size_t smem = WALK_KP_BYTES + WALK_ROT_BYTES + (size_t)WALK_TEAMS * sizeof(WalkerState<NCAP>);
 	if (blocks_per_sm == 0) {
 		cudaError_t e = cudaFuncSetAttribute(walk_kernel<NCAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 		if (e != cudaSuccess) {
