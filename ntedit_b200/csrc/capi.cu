@@ -99,6 +99,51 @@ struct ntb_batch
 	std::vector<uint64_t> offsets;
 	int device = 0;
 	float ms_h2d = 0;
+	// streamed upload (ntb_polish_batch): the text is copied piece by piece on its own stream while the scan of the earlier
+	// pieces already runs; piece i is on the device when up_events[i] has fired
+	const char* up_src = nullptr;
+	cudaStream_t up_stream = nullptr;
+	cudaEvent_t up_begin = nullptr, up_end = nullptr;
+	std::vector<cudaEvent_t> up_events;
+	uint64_t up_issued = 0; // bytes whose copy has been issued
+	static constexpr uint64_t UP_PIECE = 64ull << 20;
+
+	// issue the copies of every piece that overlaps [0, end); returns the event that covers byte end-1 (nullptr: nothing streamed)
+	cudaError_t upload_until(uint64_t end, cudaEvent_t* covering)
+	{
+		*covering = nullptr;
+		if (!up_src) {
+			return cudaSuccess;
+		}
+		if (end > total) {
+			end = total;
+		}
+		while (up_issued < end) {
+			const uint64_t len = std::min<uint64_t>(UP_PIECE, total - up_issued);
+			cudaError_t e = cudaMemcpyAsync(d_text + up_issued, up_src + up_issued, len, cudaMemcpyHostToDevice, up_stream);
+			if (e != cudaSuccess) {
+				return e;
+			}
+			cudaEvent_t ev = nullptr;
+			e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+			if (e != cudaSuccess) {
+				return e;
+			}
+			up_events.push_back(ev);
+			e = cudaEventRecord(ev, up_stream);
+			if (e != cudaSuccess) {
+				return e;
+			}
+			up_issued += len;
+			if (up_issued == total && up_end) {
+				cudaEventRecord(up_end, up_stream);
+			}
+		}
+		if (end > 0 && !up_events.empty()) {
+			*covering = up_events[std::min<uint64_t>(up_events.size() - 1, (end - 1) / UP_PIECE)];
+		}
+		return cudaSuccess;
+	}
 };
 
 struct ntb_result
@@ -109,15 +154,15 @@ struct ntb_result
 namespace {
 
 int
-batch_alloc(ntb_batch* b, uint64_t total)
+batch_alloc(ntb_batch* b, uint64_t total, cudaStream_t stream = 0)
 {
 	b->total = total;
 	b->n_tiles = (total + SCAN_TILE - 1) / SCAN_TILE;
 	const uint64_t padded = b->n_tiles * SCAN_TILE;
 	NTB_CUDA(cudaMalloc((void**)&b->d_alloc, SCAN_HALO + padded + 64));
 	b->d_text = b->d_alloc + SCAN_HALO;
-	NTB_CUDA(cudaMemsetAsync(b->d_alloc, 0, SCAN_HALO, 0));
-	NTB_CUDA(cudaMemsetAsync(b->d_text + total, 0, padded - total + 64, 0));
+	NTB_CUDA(cudaMemsetAsync(b->d_alloc, 0, SCAN_HALO, stream));
+	NTB_CUDA(cudaMemsetAsync(b->d_text + total, 0, padded - total + 64, stream));
 	return NTB_OK;
 }
 
@@ -295,8 +340,21 @@ struct CudaBackend
 			NTB_BE(cudaMalloc((void**)&ws->d_visit, words * 4));
 			ws->cap_visit = words;
 		}
-		// the batch was uploaded on the default stream
-		NTB_BE(cudaStreamSynchronize(0));
+		// a batch that is not streamed was uploaded on the default stream
+		if (!batch->up_src) {
+			NTB_BE(cudaStreamSynchronize(0));
+		}
+		return NTB_OK;
+	}
+
+	// make the work stream wait until text bytes [0, end) are on the device (streamed batches only)
+	int need_text(uint64_t end)
+	{
+		cudaEvent_t ev = nullptr;
+		NTB_BE(batch->upload_until(end, &ev));
+		if (ev) {
+			NTB_BE(cudaStreamWaitEvent(ws->stream, ev, 0));
+		}
 		return NTB_OK;
 	}
 
@@ -376,6 +434,9 @@ struct CudaBackend
 			A.scan.n_tiles = nt;
 			A.scan.visit = ws->d_visit + t0 * SCAN_BITWORDS;
 			A.chunk_base = t0 * SCAN_TILE;
+			if (need_text((t0 + nt) * SCAN_TILE) != NTB_OK) {
+				return rc;
+			}
 			NTB_BE(cudaMemsetAsync(ws->d_cursor, 0, (BIN_MAX_BUCKETS + 1) * sizeof(uint32_t), ws->stream));
 			NTB_BE(launch_scan_binned(A, bloom->counting != 0, (int)std::min<uint64_t>(nt, (uint64_t)sms * 2),
 			                          (int)env_u64("NTB_BIN_PROBE_CTAS_PER_SM", 4), ws->stream));
@@ -402,6 +463,9 @@ struct CudaBackend
 		a.visit = ws->d_visit;
 		fill_scan_tables(a, kp.k);
 		const int grid = (int)std::min<uint64_t>(batch->n_tiles, (uint64_t)sm_count(batch->device) * 3);
+		if (need_text(batch->total) != NTB_OK) {
+			return rc;
+		}
 		NTB_BE(cudaEventRecord(ws->ev0, ws->stream));
 		if (grid > 0) {
 			NTB_BE(launch_scan(a, bloom->counting != 0, false, grid, ws->stream));
@@ -653,6 +717,9 @@ polish_common(ntb_filter* bloom, ntb_filter* rep, const ntb_params* p, ntb_batch
 	res->impl.stats.ms_scan = be.ms_scan;
 	res->impl.stats.ms_walk = be.ms_walk;
 	res->impl.stats.ms_d2h = be.ms_d2h;
+	if (batch->up_src && batch->up_end && batch->up_issued == batch->total && cudaEventSynchronize(batch->up_end) == cudaSuccess) {
+		cudaEventElapsedTime(&batch->ms_h2d, batch->up_begin, batch->up_end); // includes the waits between pieces
+	}
 	res->impl.stats.ms_h2d = batch->ms_h2d;
 	res->impl.stats.kernel_launches = be.launches;
 	*out = res;
@@ -1050,6 +1117,57 @@ ntb_batch_upload(const char* bases, const uint64_t* offsets, uint64_t n_contigs,
 	return NTB_OK;
 }
 
+// ntb_polish_batch's upload: allocation now, the copies as the scan asks for them (ntb_batch::upload_until)
+static int
+batch_upload_streamed(const char* bases, const uint64_t* offsets, uint64_t n_contigs, int device, ntb_batch** out)
+{
+	if (!bases || !out) {
+		return fail(NTB_EINVAL, "NULL argument");
+	}
+	int rc = check_offsets(offsets, n_contigs);
+	if (rc != NTB_OK) {
+		return rc;
+	}
+	for (uint64_t c = 0; c < n_contigs; c++) {
+		if (bases[offsets[c + 1] - 1] != 0) {
+			return fail(NTB_EINVAL, "contig " + std::to_string(c) + " is not NUL-terminated inside the batch buffer");
+		}
+	}
+	rc = select_device(device);
+	if (rc != NTB_OK) {
+		return rc;
+	}
+	ntb_batch* b = new (std::nothrow) ntb_batch();
+	if (!b) {
+		return fail(NTB_ENOMEM, "out of memory");
+	}
+	b->device = device;
+	b->offsets.assign(offsets, offsets + n_contigs + 1);
+	cudaError_t e = cudaStreamCreateWithFlags(&b->up_stream, cudaStreamNonBlocking);
+	if (e == cudaSuccess) {
+		e = cudaEventCreate(&b->up_begin);
+	}
+	if (e == cudaSuccess) {
+		e = cudaEventCreate(&b->up_end);
+	}
+	if (e != cudaSuccess) {
+		ntb_batch_free(b);
+		return cuda_fail(e, "cudaStreamCreate(upload)");
+	}
+	rc = batch_alloc(b, offsets[n_contigs], b->up_stream);
+	if (rc != NTB_OK) {
+		ntb_batch_free(b);
+		return rc;
+	}
+	b->up_src = bases;
+	cudaEventRecord(b->up_begin, b->up_stream);
+	if (b->total == 0) {
+		cudaEventRecord(b->up_end, b->up_stream);
+	}
+	*out = b;
+	return NTB_OK;
+}
+
 int
 ntb_batch_wrap_device(void* dev_bases, const uint64_t* host_offsets, uint64_t n_contigs, int device, ntb_batch** out)
 {
@@ -1100,8 +1218,23 @@ ntb_batch_free(ntb_batch* b)
 	if (!b) {
 		return;
 	}
+	cudaSetDevice(b->device);
+	if (b->up_stream) {
+		cudaStreamSynchronize(b->up_stream);
+	}
+	for (cudaEvent_t ev : b->up_events) {
+		cudaEventDestroy(ev);
+	}
+	if (b->up_begin) {
+		cudaEventDestroy(b->up_begin);
+	}
+	if (b->up_end) {
+		cudaEventDestroy(b->up_end);
+	}
+	if (b->up_stream) {
+		cudaStreamDestroy(b->up_stream);
+	}
 	if (b->d_alloc) {
-		cudaSetDevice(b->device);
 		cudaFree(b->d_alloc);
 	}
 	delete b;
@@ -1185,7 +1318,7 @@ ntb_polish_batch(ntb_filter* bloom, ntb_filter* rep, const ntb_params* p, char* 
 		return fail(NTB_EINVAL, "NULL argument");
 	}
 	ntb_batch* b = nullptr;
-	int rc = ntb_batch_upload(bases, offsets, n_contigs, bloom->device, &b);
+	int rc = batch_upload_streamed(bases, offsets, n_contigs, bloom->device, &b);
 	if (rc != NTB_OK) {
 		return rc;
 	}
