@@ -9,8 +9,8 @@ whole hot path (scan kernel, walker kernel rounds, host stitch + rope replay) ov
   value : bases/s, batch already resident in HBM when the timed region starts (K steps in one bracket)
   e2e   : bases/s through the C-ABI call a binding makes (ntb_polish_batch) with the draft in pinned HOST memory --
           host->device copy of the bases and device->host copy of the edit events inside the timed region
-  roofline : scan kernel (K1), algorithmic bytes = (1 + 32*h) per base (one text byte + h random
-          32-byte sectors), duration from CUDA events on its stream
+  roofline : the scan stage (K1b: bin_kernel + probe_bin_kernel per text chunk), algorithmic bytes = (1 + 32*h) per base
+          (one text byte + h random 32-byte sectors), duration from CUDA events on its stream
   cpu_baseline : the UNMODIFIED reference (oracle/_ref/ntedit_ref, OpenMP over contigs) on a bounded sample of the
           same draft with the same filter file, on this box's host cores
 
@@ -36,6 +36,11 @@ import torch  # noqa: E402
 
 K, H = 25, 3
 SEED = 20261017
+# dram__bytes_read.sum + dram__bytes_write.sum of the scan stage from the committed ncu --set full capture of this command
+# (profiles/): per-chunk bin + probe traffic x chunks; None until captured for the current kernels
+NCU_TRAFFIC_BYTES_PER_STAGE = int((0.349726e9 + 8.048014e9 + 17.965268e9 + 0.483822e9) * 88796 / 9991)
+NCU_TRAFFIC_SOURCE = ("profiles/r01b_ncu_full_bin_probe_walk_summary.csv: (bin_kernel 8.40 GB + probe_bin_kernel 18.45 GB) per "
+                      "9991-tile chunk x 88796/9991 chunks; the direct scan kernel moved 1146 GB for the same work")
 
 WORKLOADS = {
     # name: (total bases, filter bytes, large contigs, small contigs, mode)
@@ -408,9 +413,14 @@ def main():
                     "note": "ntb_polish_batch on pinned host memory; working copy restored between steps outside the timed region"},
             "gpu_launches": int(sum(s["kernel_launches"] for s in stats)),
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "kernel": "scan_kernel<3,false,false>", "achieved": achieved, "peak": peak,
-                         "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": ms_scan},
+            # the HBM-bound stage of the path: K1b = bin_kernel<3,false> + probe_bin_kernel<false>, one pair per text chunk;
+            # "launch" = one pass of that stage over the whole batch (CUDA events on its stream around all its launches)
+            "roofline": {"bound": "hbm", "kernel": "K1b scan stage: bin_kernel<3,false> + probe_bin_kernel<false> per text chunk",
+                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": NCU_TRAFFIC_BYTES_PER_STAGE, "traffic_source": NCU_TRAFFIC_SOURCE, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": ms_scan,
+                         "gather_ceiling_note": "a direct 1-byte probe costs a 128-byte DRAM line on B200 (37.9 G probes/s "
+                                                "ceiling, profiles/r01_gather_*); K1b serves probes from L2-resident filter regions"},
             "cpu_baseline": cpu,
             "breakdown_ms": {"scan_kernel": ms_scan, "walk_kernel": ms_walk, "host_stitch_replay": ms_host,
                              "d2h_events": float(np.mean([s["ms_d2h"] for s in stats])), "rounds": stats[-1]["rounds"],

@@ -203,6 +203,9 @@ struct Workspace
 {
 	int device = 0;
 	cudaStream_t stream = nullptr;
+	cudaStream_t stream2 = nullptr;                      // K1b: the probe kernels run beside the next chunk's bin kernel
+	cudaEvent_t ev_bin[2] = { nullptr, nullptr };        // K1b: records of buffer i are complete
+	cudaEvent_t ev_probe[2] = { nullptr, nullptr };      // K1b: buffer i has been consumed
 	cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 	uint32_t* d_visit = nullptr;
 	size_t cap_visit = 0; // words
@@ -244,6 +247,17 @@ struct Workspace
 		}
 		if (ev1) {
 			cudaEventDestroy(ev1);
+		}
+		for (int i = 0; i < 2; i++) {
+			if (ev_bin[i]) {
+				cudaEventDestroy(ev_bin[i]);
+			}
+			if (ev_probe[i]) {
+				cudaEventDestroy(ev_probe[i]);
+			}
+		}
+		if (stream2) {
+			cudaStreamDestroy(stream2);
 		}
 		if (stream) {
 			cudaStreamDestroy(stream);
@@ -392,8 +406,12 @@ struct CudaBackend
 
 	int scan_binned(const KParams& kp, uint32_t rl, uint32_t nb)
 	{
+		// NTB_BIN_OVERLAP=1 (experiment, off): two record buffers, the probe kernel of chunk c on a second stream beside the bin
+		// kernel of chunk c+1.  Measured 2x SLOWER (profiles/r01b_scan_stage_tuning_overlap.jsonl): the bin kernel's 8 GB/chunk write
+		// stream evicts the filter region the probe kernel needs in L2, so the two kernels of a chunk run back to back.
 		const uint64_t H = bloom->h;
-		const uint64_t budget_records = (env_u64("NTB_BIN_SCRATCH_MB", 8192) << 20) / 8;
+		const bool overlap = env_u64("NTB_BIN_OVERLAP", 0) != 0;
+		const uint64_t budget_records = (env_u64("NTB_BIN_SCRATCH_MB", 8192) << 20) / 8 / (overlap ? 2 : 1);
 		uint64_t chunk_tiles = budget_records / (uint64_t)((double)SCAN_TILE * (double)H * 1.06);
 		chunk_tiles = std::max<uint64_t>(1, std::min<uint64_t>(chunk_tiles, batch->n_tiles));
 		chunk_tiles = std::min<uint64_t>(chunk_tiles, (0xFFFFFFFFull / SCAN_TILE) - 1); // record positions are 32-bit
@@ -403,16 +421,24 @@ struct CudaBackend
 		if (cap > 0xFFFFFFE0ull) {
 			cap = 0xFFFFFFE0ull;
 		}
-		const size_t need = (size_t)nb * cap;
-		if (need > ws->cap_records) {
+		const size_t per_buffer = (size_t)nb * cap;
+		const size_t n_buffers = overlap ? 2 : 1;
+		if (n_buffers * per_buffer > ws->cap_records) {
 			cudaFree(ws->d_records);
 			ws->d_records = nullptr;
 			ws->cap_records = 0;
-			NTB_BE(cudaMalloc((void**)&ws->d_records, need * 8));
-			ws->cap_records = need;
+			NTB_BE(cudaMalloc((void**)&ws->d_records, n_buffers * per_buffer * 8));
+			ws->cap_records = n_buffers * per_buffer;
 		}
 		if (!ws->d_cursor) {
-			NTB_BE(cudaMalloc((void**)&ws->d_cursor, (BIN_MAX_BUCKETS + 1) * sizeof(uint32_t)));
+			NTB_BE(cudaMalloc((void**)&ws->d_cursor, 2 * (BIN_MAX_BUCKETS + 1) * sizeof(uint32_t)));
+		}
+		if (!ws->stream2) {
+			NTB_BE(cudaStreamCreateWithFlags(&ws->stream2, cudaStreamNonBlocking));
+			for (int i = 0; i < 2; i++) {
+				NTB_BE(cudaEventCreateWithFlags(&ws->ev_bin[i], cudaEventDisableTiming));
+				NTB_BE(cudaEventCreateWithFlags(&ws->ev_probe[i], cudaEventDisableTiming));
+			}
 		}
 		BinArgs A;
 		std::memset(&A, 0, sizeof A);
@@ -420,27 +446,41 @@ struct CudaBackend
 		A.scan.k = kp.k;
 		A.scan.min_threshold = kp.min_threshold;
 		fill_scan_tables(A.scan, kp.k);
-		A.records = ws->d_records;
-		A.cursor = ws->d_cursor;
 		A.bucket_cap = (uint32_t)cap;
 		A.n_buckets = nb;
 		A.region_log2 = rl;
 		const int sms = sm_count(batch->device);
+		const int probe_ctas = (int)env_u64("NTB_BIN_PROBE_CTAS_PER_SM", 4);
+		cudaStream_t s_probe = overlap ? ws->stream2 : ws->stream;
 		NTB_BE(cudaEventRecord(ws->ev0, ws->stream));
 		NTB_BE(cudaMemsetAsync(ws->d_visit, 0, batch->n_tiles * SCAN_BITWORDS * 4, ws->stream));
-		for (uint64_t t0 = 0; t0 < batch->n_tiles; t0 += chunk_tiles) {
+		uint64_t c = 0;
+		for (uint64_t t0 = 0; t0 < batch->n_tiles; t0 += chunk_tiles, c++) {
 			const uint64_t nt = std::min<uint64_t>(chunk_tiles, batch->n_tiles - t0);
+			const int buf = overlap ? (int)(c & 1) : 0;
 			A.scan.text = batch->d_text + t0 * SCAN_TILE;
 			A.scan.n_tiles = nt;
 			A.scan.visit = ws->d_visit + t0 * SCAN_BITWORDS;
 			A.chunk_base = t0 * SCAN_TILE;
+			A.records = ws->d_records + (size_t)buf * per_buffer;
+			A.cursor = ws->d_cursor + (size_t)buf * (BIN_MAX_BUCKETS + 1);
 			if (need_text((t0 + nt) * SCAN_TILE) != NTB_OK) {
 				return rc;
 			}
-			NTB_BE(cudaMemsetAsync(ws->d_cursor, 0, (BIN_MAX_BUCKETS + 1) * sizeof(uint32_t), ws->stream));
-			NTB_BE(launch_scan_binned(A, bloom->counting != 0, (int)std::min<uint64_t>(nt, (uint64_t)sms * 2),
-			                          (int)env_u64("NTB_BIN_PROBE_CTAS_PER_SM", 4), ws->stream));
+			if (overlap && c >= 2) {
+				NTB_BE(cudaStreamWaitEvent(ws->stream, ws->ev_probe[buf], 0)); // the buffer's previous chunk has been probed
+			}
+			NTB_BE(cudaMemsetAsync(A.cursor, 0, (BIN_MAX_BUCKETS + 1) * sizeof(uint32_t), ws->stream));
+			NTB_BE(launch_bin(A, bloom->counting != 0, (int)std::min<uint64_t>(nt, (uint64_t)sms * 2), ws->stream));
+			NTB_BE(cudaEventRecord(ws->ev_bin[buf], ws->stream));
+			NTB_BE(cudaStreamWaitEvent(s_probe, ws->ev_bin[buf], 0));
+			NTB_BE(launch_probe_bin(A, bloom->counting != 0, probe_ctas, s_probe));
+			NTB_BE(cudaEventRecord(ws->ev_probe[buf], s_probe));
 			launches += 2;
+		}
+		// the walkers (work stream) need every probe done
+		for (int i = 0; overlap && i < 2 && (uint64_t)i < c; i++) {
+			NTB_BE(cudaStreamWaitEvent(ws->stream, ws->ev_probe[i], 0));
 		}
 		NTB_BE(cudaEventRecord(ws->ev1, ws->stream));
 		return NTB_OK;

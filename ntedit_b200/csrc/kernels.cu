@@ -677,26 +677,28 @@ launch_bin_h(const BinArgs& a, bool counting, int grid, cudaStream_t stream)
 }
 
 cudaError_t
-launch_scan_binned(const BinArgs& a, bool counting, int grid_bin, int grid_probe, cudaStream_t stream)
+launch_bin(const BinArgs& a, bool counting, int grid, cudaStream_t stream)
 {
 	if (a.n_buckets == 0 || a.n_buckets > (uint32_t)BIN_MAX_BUCKETS || a.region_log2 < 3 || a.region_log2 > 32) {
 		return cudaErrorInvalidValue;
 	}
-	cudaError_t e;
 	switch (a.scan.filter.hash_num) {
-	case 1: e = launch_bin_h<1>(a, counting, grid_bin, stream); break;
-	case 2: e = launch_bin_h<2>(a, counting, grid_bin, stream); break;
-	case 3: e = launch_bin_h<3>(a, counting, grid_bin, stream); break;
-	case 4: e = launch_bin_h<4>(a, counting, grid_bin, stream); break;
-	case 5: e = launch_bin_h<5>(a, counting, grid_bin, stream); break;
-	case 6: e = launch_bin_h<6>(a, counting, grid_bin, stream); break;
-	case 7: e = launch_bin_h<7>(a, counting, grid_bin, stream); break;
-	case 8: e = launch_bin_h<8>(a, counting, grid_bin, stream); break;
+	case 1: return launch_bin_h<1>(a, counting, grid, stream);
+	case 2: return launch_bin_h<2>(a, counting, grid, stream);
+	case 3: return launch_bin_h<3>(a, counting, grid, stream);
+	case 4: return launch_bin_h<4>(a, counting, grid, stream);
+	case 5: return launch_bin_h<5>(a, counting, grid, stream);
+	case 6: return launch_bin_h<6>(a, counting, grid, stream);
+	case 7: return launch_bin_h<7>(a, counting, grid, stream);
+	case 8: return launch_bin_h<8>(a, counting, grid, stream);
 	default: return cudaErrorInvalidValue;
 	}
-	if (e != cudaSuccess) {
-		return e;
-	}
+}
+
+cudaError_t
+launch_probe_bin(const BinArgs& a, bool counting, int grid_probe, cudaStream_t stream)
+{
+	cudaError_t e;
 	// cooperative launch: all CTAs resident (the kernel paces itself across CTAs); grid_probe = CTAs per SM wanted
 	static int per_sm[2] = { 0, 0 };
 	const void* fn = counting ? (const void*)probe_bin_kernel<true> : (const void*)probe_bin_kernel<false>;

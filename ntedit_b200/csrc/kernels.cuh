@@ -82,9 +82,11 @@ struct BinArgs
 	uint32_t region_log2;   // slots per region = 1 << region_log2
 };
 
-// launches bin_kernel<hash_num, counting> on `grid_bin` persistent CTAs and probe_bin_kernel<counting> cooperatively on
-// min(grid_probe, occupancy) CTAs per SM; `cursor` has BIN_MAX_BUCKETS + 1 zeroed entries (the last one paces the probe CTAs)
-cudaError_t launch_scan_binned(const BinArgs& a, bool counting, int grid_bin, int grid_probe, cudaStream_t stream);
+// bin_kernel<hash_num, counting> on `grid` persistent CTAs
+cudaError_t launch_bin(const BinArgs& a, bool counting, int grid, cudaStream_t stream);
+// probe_bin_kernel<counting>, launched cooperatively on min(ctas_per_sm, occupancy) CTAs per SM; `cursor` has
+// BIN_MAX_BUCKETS + 1 entries zeroed before the bin kernel (the last one paces the probe CTAs)
+cudaError_t launch_probe_bin(const BinArgs& a, bool counting, int ctas_per_sm, cudaStream_t stream);
 
 // K2 geometry: WALK_TEAMS walkers per CTA, each with its own WalkerState in dynamic shared memory
 #ifndef NTB_WALK_WARPS

@@ -1,0 +1,157 @@
+"""BASELINE.json configurations as parity cases at (or scaled towards) their stated sizes.
+
+* configs[1] -- synthetic 100 Mbp draft, 1 GiB k=25 Bloom filter, mode 0 -- at FULL size: `ntedit-b200` against the
+  unmodified reference binary on the same FASTA and filter files (reference run with every host core; its output order
+  is then nondeterministic, ntedit.cpp:2145-2150, so records are compared per contig).
+* configs[4] -- conifer-like draft of very many short contigs, mode 0 -- the same 100 Mbp re-cut into ~20 k log-normal
+  contigs (N50 ~ 20 kbp, some below the -z cut-off), same filter.
+* configs[3] -- k=32 counting Bloom filter, mode 2, -s 1 -- scaled to a size the C oracle finishes in seconds.
+"""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+pytestmark = pytest.mark.gpu
+
+
+def fasta_records(blob):
+    out = {}
+    for rec in blob.split(b">")[1:]:
+        hdr, _, seq = rec.partition(b"\n")
+        out[hdr] = seq.rstrip(b"\n")
+    return out
+
+
+def tsv_by_contig(blob):
+    lines = blob.splitlines()
+    out = {}
+    for l in lines[1:]:
+        out.setdefault(l.split(b"\t", 1)[0], []).append(l)
+    return lines[0], out
+
+
+def vcf_by_contig(blob):
+    out = {}
+    for l in blob.splitlines():
+        if l and not l.startswith(b"#"):
+            out.setdefault(l.split(b"\t", 1)[0], []).append(l)
+    return out
+
+
+@pytest.fixture(scope="module")
+def config1(nb, oracle, tmp_path_factory):
+    """The 100 Mbp / 1 GiB workload of bench.py, written out as files."""
+    if not oracle.have_ref():
+        pytest.skip("oracle/_ref/ntedit_ref not present")
+    import torch
+    sys.path.insert(0, ROOT)
+    import bench
+    w = bench.WORKLOADS["100Mbp_k25_1GiB_m0"]
+    dev = torch.device("cuda", 0)
+    filt = torch.zeros(w["fbytes"] + 64, dtype=torch.uint8, device=dev)
+    bloom = nb.BloomFilter.wrap_device(filt.data_ptr(), w["fbytes"], bench.K, bench.H, counting=False, device=0)
+    buf, offs = bench.build_workload(w, dev, 0, bloom, nb)
+    tmp = tmp_path_factory.mktemp("config1")
+    fpath = str(tmp / "reads_k25.bf")
+    bloom.save(fpath)
+    host = buf.cpu().numpy()
+    del buf, filt
+    torch.cuda.empty_cache()
+    return dict(tmp=tmp, filter=fpath, host=host, offs=offs)
+
+
+def run_both(oracle, lib, draft, filt, tmp, tag, flags):
+    ours = str(tmp / (tag + "_ours"))
+    r = subprocess.run([lib.CLI, "-f", draft, "-r", filt, "-b", ours, "-t", "8"] + [str(x) for x in flags],
+                       stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=900)
+    assert r.returncode == 0, r.stderr.decode(errors="replace")[-2000:]
+    got = [open(ours + sfx, "rb").read() for sfx in ("_edited.fa", "_changes.tsv", "_variants.vcf")]
+    ref = oracle.run_ref(draft, filt, workdir=str(tmp), threads=os.cpu_count() or 4, extra=flags)
+    return got, ref
+
+
+def compare_per_contig(got, ref):
+    gfa, rfa = fasta_records(got[0]), fasta_records(ref[0])
+    assert gfa.keys() == rfa.keys()
+    bad = [h for h in gfa if gfa[h] != rfa[h]]
+    assert not bad, "contigs with different polished sequence: %r" % bad[:3]
+    gh, gt = tsv_by_contig(got[1])
+    rh, rt = tsv_by_contig(ref[1])
+    assert gh == rh
+    assert gt == rt
+    assert vcf_by_contig(got[2]) == vcf_by_contig(ref[2])
+    return len(gfa), sum(len(v) for v in gt.values())
+
+
+def test_config1_full_size_cli_vs_reference(nb, oracle, config1):
+    from ntedit_b200 import lib
+    c = config1
+    draft = str(c["tmp"] / "draft_100Mbp.fa")
+    with open(draft, "wb") as fh:
+        for i in range(len(c["offs"]) - 1):
+            s, e = int(c["offs"][i]), int(c["offs"][i + 1]) - 1
+            fh.write(b">contig%d len=%d\n" % (i, e - s))
+            fh.write(c["host"][s:e].tobytes())
+            fh.write(b"\n")
+    got, ref = run_both(oracle, lib, draft, c["filter"], c["tmp"], "c1", ("-m", 0))
+    n_contigs, n_rows = compare_per_contig(got, ref)
+    assert n_contigs == 100 and n_rows > 80_000
+    # our output is in input order
+    assert [l.split(b" ")[0] for l in got[0].splitlines() if l.startswith(b">")] == [b">contig%d" % i for i in range(100)]
+
+
+def test_config4_like_many_short_contigs(nb, oracle, config1):
+    from ntedit_b200 import lib
+    c = config1
+    rng = np.random.default_rng(4)
+    draft = str(c["tmp"] / "draft_conifer_like.fa")
+    n = 0
+    short = 0
+    with open(draft, "wb") as fh:
+        for i in range(len(c["offs"]) - 1):
+            s, e = int(c["offs"][i]), int(c["offs"][i + 1]) - 1
+            p = s
+            while p < e:
+                ln = int(min(e - p, max(20, rng.lognormal(np.log(6000), 1.2))))
+                fh.write(b">scaffold_%d\n" % n)
+                fh.write(c["host"][p:p + ln].tobytes())
+                fh.write(b"\n")
+                short += ln < 100
+                p += ln
+                n += 1
+    assert n > 10_000 and short > 0
+    got, ref = run_both(oracle, lib, draft, c["filter"], c["tmp"], "c4", ("-m", 0))
+    n_contigs, n_rows = compare_per_contig(got, ref)
+    assert n_contigs == n - short and n_rows > 50_000
+
+
+def test_config3_like_cbf_k32_snv_mode2(nb, oracle):
+    from ntedit_b200 import synth
+    rng = np.random.default_rng(33)
+    k, h = 32, 3
+    truth = synth.random_genome(400_000, rng, dup_frac=0.05)
+    # a second haplotype with SNVs: both alleles are in the reads, at different coverage
+    alt = truth.copy()
+    idx = rng.choice(len(alt), size=400, replace=False)
+    alt[idx] = np.frombuffer(b"ACGT", dtype=np.uint8)[(np.searchsorted(np.frombuffer(b"ACGT", dtype=np.uint8), alt[idx]) + 1) % 4]
+    draft = synth.mutate(truth, rng, 5e-4, 0.0, lower_frac=0.002, n_frac=0.001)
+    contigs = [(b"chrA", draft[:250_000].tobytes()), (b"chrB", draft[250_000:].tobytes())]
+    fbytes = 8 << 20
+    ofilt = oracle.OracleFilter.new(fbytes, k, h, True)
+    bloom = nb.BloomFilter.create(fbytes, k, h, counting=True, device=0)
+    for cov, seq in ((6, truth), (3, alt)):
+        for _ in range(cov):
+            ofilt.insert_seq(seq.tobytes())
+            bloom.insert([(b"t", seq.tobytes())])
+    assert np.array_equal(ofilt.data(), bloom.download())
+    p = nb.default_params(mode=2, snv=1, min_threshold=2)
+    fa, tsv, vcf, st = nb.polish(contigs, bloom, p)
+    op = oracle.default_params(k, h, mode=2, snv=1, min_threshold=2, max_insertions=0, max_deletions=0)
+    ofa, otsv, ovcf = oracle.polish(contigs, ofilt, op)
+    assert fa == ofa and tsv == otsv and vcf == ovcf
+    assert vcf.count(b"\n") > 300
+    ofilt.free()

@@ -7,7 +7,7 @@ TAG=${1:-r01}
 FULL=${2:-}
 OUT=gpurun_out
 mkdir -p $OUT
-KERN='regex:scan_kernel|walk_kernel|order_tasks_kernel'   # the kernels of the timed region (insert_kernel builds the filter during setup)
+KERN='regex:scan_kernel|bin_kernel|walk_kernel|order_tasks_kernel'   # the kernels of the timed region (insert_kernel builds the filter during setup)
 
 # 1. practical ceiling of random 32-byte-sector reads over a 4 GiB buffer
 if [ -x tools/gather_bench ]; then
@@ -21,9 +21,11 @@ fi
 ncu --metrics gpu__time_duration.sum --clock-control none -k "$KERN" -c 400 --csv \
 	--log-file $OUT/launches_${TAG}.csv python bench.py --steps 1 --warmup 1 --no-cpu-baseline > $OUT/bench_under_ncu_${TAG}.log 2>&1
 
-# 3. one full capture of the first scan and the first (largest) walker launch
+# 3. full captures: the first bin / probe pair of the scan stage, and the first (largest) walker launch
 if [ -n "$FULL" ]; then
-	ncu --set full --clock-control none --import-source on -k 'regex:scan_kernel|walk_kernel' -c 2 -f \
-		-o $OUT/prof_${TAG} python bench.py --steps 1 --warmup 0 --no-cpu-baseline > $OUT/bench_under_ncu_full_${TAG}.log 2>&1
+	ncu --set full --clock-control none --import-source on -k 'regex:bin_kernel' -c 2 -f \
+		-o $OUT/prof_scan_${TAG} python bench.py --steps 1 --warmup 0 --no-cpu-baseline > $OUT/bench_under_ncu_full_scan_${TAG}.log 2>&1
+	ncu --set full --clock-control none --import-source on -k 'regex:walk_kernel' -c 1 -f \
+		-o $OUT/prof_walk_${TAG} python bench.py --steps 1 --warmup 0 --no-cpu-baseline > $OUT/bench_under_ncu_full_walk_${TAG}.log 2>&1
 fi
 ls -la $OUT
