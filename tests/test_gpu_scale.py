@@ -116,7 +116,7 @@ def test_config4_like_many_short_contigs(nb, oracle, config1):
             s, e = int(c["offs"][i]), int(c["offs"][i + 1]) - 1
             p = s
             while p < e:
-                ln = int(min(e - p, max(20, rng.lognormal(np.log(6000), 1.2))))
+                ln = int(min(e - p, max(20, rng.lognormal(np.log(3000), 1.2))))
                 fh.write(b">scaffold_%d\n" % n)
                 fh.write(c["host"][p:p + ln].tobytes())
                 fh.write(b"\n")
