@@ -16,17 +16,15 @@ constexpr unsigned MULTISHIFT = 27;
 
 // Base classes.  code 0..3 = A C G T (either case; U/u hash as T but are not "accepted"), 4 = other.
 // The reverse strand of base code c uses the seed of 3-c.
+// (branch-free: these run once per base in every kernel, and a switch costs an indirect branch -- an instruction-fetch stall)
 NTB_HD unsigned
 base_code(unsigned char ch)
 {
-	switch (ch | 0x20) {
-	case 'a': return 0;
-	case 'c': return 1;
-	case 'g': return 2;
-	case 't': return 3;
-	case 'u': return 3;
-	default: return 4;
-	}
+	const uint32_t i = (uint32_t)(ch | 0x20) - (uint32_t)'a';
+	const uint32_t sh = i < 26u ? i : 31u;
+	const uint32_t is_base = (0x00180045u >> sh) & 1u;                  // a c g t u
+	const uint32_t code = (uint32_t)(0x3C000002010ULL >> (2u * (sh & 31u))) & 3u; // a:0 c:1 g:2 t:3 u:3
+	return is_base ? code : 4u;
 }
 
 NTB_HD uint64_t
@@ -44,31 +42,19 @@ seed_fwd(unsigned char ch)
 
 // SEED_TAB[ch & CP_OFF]: btllib's reverse-strand lookup goes through the low three bits of the character,
 // slots {1:T, 3:G, 4:A, 5:A, 7:C}; every other slot is 0.  Note this is defined for ANY byte, e.g. 'Y'&7 == 1.
+NTB_HD unsigned rev_code(unsigned char ch);
+
 NTB_HD uint64_t
 seed_rev(unsigned char ch)
 {
-	switch (ch & 7) {
-	case 1: return SEED_T;
-	case 3: return SEED_G;
-	case 4: return SEED_A;
-	case 5: return SEED_A;
-	case 7: return SEED_C;
-	default: return 0ULL;
-	}
+	return seed_of_code(rev_code(ch));
 }
 
-// code (A C G T = 0..3, 4 = none) of the seed that SEED_TAB[ch & CP_OFF] selects
+// code (A C G T = 0..3, 4 = none) of the seed that SEED_TAB[ch & CP_OFF] selects: slots {1:T, 3:G, 4:A, 5:A, 7:C}
 NTB_HD unsigned
 rev_code(unsigned char ch)
 {
-	switch (ch & 7) {
-	case 1: return 3;
-	case 3: return 2;
-	case 4: return 0;
-	case 5: return 0;
-	case 7: return 1;
-	default: return 4;
-	}
+	return (0x30051Cu >> (3u * ((uint32_t)ch & 7u))) & 7u;
 }
 
 // ntedit.cpp:486-499 (callers always pass toupper(c))
@@ -93,13 +79,9 @@ to_lower(unsigned char c)
 NTB_HD bool
 is_accepted_any_case(unsigned char c)
 {
-	switch (to_upper(c)) {
-	case 'A': case 'T': case 'G': case 'C': case 'R': case 'Y': case 'S':
-	case 'W': case 'K': case 'M': case 'B': case 'D': case 'H': case 'V':
-		return true;
-	default:
-		return false;
-	}
+	// A T G C R Y S W K M B D H V, either case
+	const uint32_t i = (uint32_t)(c | 0x20) - (uint32_t)'a';
+	return i < 26u && ((0x016E14CFu >> i) & 1u);
 }
 
 // split rotate by one: bits 0..32 and bits 33..63 rotate independently
@@ -191,12 +173,9 @@ hash_canonical(const HashState& s)
 NTB_HD uint64_t
 hash_extend(uint64_t base, unsigned k, unsigned i)
 {
-	if (i == 0) {
-		return base;
-	}
 	uint64_t t = base * ((uint64_t)i ^ ((uint64_t)k * MULTISEED));
 	t ^= t >> MULTISHIFT;
-	return t;
+	return i == 0 ? base : t;
 }
 
 NTB_HD uint64_t
@@ -218,12 +197,8 @@ filter_slot(const FilterView& f, uint64_t x)
 	}
 	const uint64_t q = mulhi64(x, f.recip);
 	uint64_t r = x - q * f.mod;
-	if (r >= f.mod) {
-		r -= f.mod;
-	}
-	if (r >= f.mod) {
-		r -= f.mod;
-	}
+	r -= r >= f.mod ? f.mod : 0ULL;
+	r -= r >= f.mod ? f.mod : 0ULL;
 	return r;
 }
 
