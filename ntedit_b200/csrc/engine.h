@@ -1089,9 +1089,12 @@ struct Walker
 			uint32_t bad = 0;
 			for (uint32_t R = ln; R <= n; R += lane_count()) {
 				uint64_t f = 0, r = 0;
+				// lin_out_c and lin_in_c are members of the same object: one load through a selected index instead of a branch
+				const uint8_t* const lo = S.lin_out_c;
+				const uint32_t in_off = (uint32_t)(S.lin_in_c - S.lin_out_c);
 				for (uint32_t i = 0; i < k; i++) {
 					const uint32_t m = R + i;
-					const uint32_t c = m < k ? S.lin_out_c[m] : S.lin_in_c[m - k];
+					const uint32_t c = lo[m < k ? m : m - k + in_off];
 					f ^= rot[(c & 7u) * ROT_STRIDE + (k - 1 - i)];
 					r ^= rot[((c >> 3) & 7u) * ROT_STRIDE + i];
 				}
@@ -1396,10 +1399,10 @@ struct Walker
 				const uint32_t m = L < R ? L : R;
 #pragma unroll
 				for (uint32_t q = 0; q < 5; q++) {
-					if (q < m) {
-						f ^= rot[fc[q] + (R - 1 - q)];
-						r ^= rot[rc[q] + (k - R + q)];
-					}
+					// branch-free: a char that has not entered the window yet (q >= m) reads the all-zero "no seed" row
+					const bool in = q < m;
+					f ^= rot[in ? fc[q] + (R - 1 - q) : 4u * ROT_STRIDE];
+					r ^= rot[in ? rc[q] + (k - R + q) : 4u * ROT_STRIDE];
 				}
 				hv[g] = f + r;
 				const uint64_t slot = filter_slot(F, hv[g]);
