@@ -189,7 +189,7 @@ struct WalkerIO
 constexpr uint32_t MAX_INS_TRIES = 341;   // num_tries[5], ntedit.cpp:172
 constexpr uint32_t MAX_DELETIONS = 10;    // ntedit.cpp:2489-2493
 #ifndef NTB_PROBE_G
-#define NTB_PROBE_G 10
+#define NTB_PROBE_G 3
 #endif
 constexpr int PROBE_G = NTB_PROBE_G;              // sampled k-mers whose probes are in flight together, per lane
 constexpr int PROBE_HU = 4;               // hash functions probed per pass (hash_num <= HMAX takes ceil(h/4) passes)

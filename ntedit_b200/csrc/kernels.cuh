@@ -90,7 +90,7 @@ cudaError_t launch_probe_bin(const BinArgs& a, bool counting, int ctas_per_sm, c
 
 // K2 geometry: WALK_TEAMS walkers per CTA, each with its own WalkerState in dynamic shared memory
 #ifndef NTB_WALK_WARPS
-#define NTB_WALK_WARPS 2
+#define NTB_WALK_WARPS 4
 #endif
 constexpr int WALK_WARPS = NTB_WALK_WARPS;
 constexpr int WALK_THREADS = WALK_WARPS * 32;
