@@ -725,7 +725,7 @@ launch_probe_bin(const BinArgs& a, bool counting, int grid_probe, cudaStream_t s
 // The walker state of every warp lives in shared memory (engine.h: WalkerState); lane 0 is the leader.
 // NCAP (capacity of the local rope copy) is 2.5 k + 32 rounded up: 160 serves k <= 48, 352 serves k <= KMAX.
 template<int NCAP>
-__global__ void __launch_bounds__(WALK_THREADS)
+__global__ void __launch_bounds__(WALK_THREADS, NTB_WALK_MIN_CTAS)
 walk_kernel(const uint8_t* text, const uint32_t* visit, FilterView bloom, FilterView rep, const __grid_constant__ KParams kp,
             const Task* tasks, const uint32_t* order, TaskResult* results, uint32_t n_tasks, Event* events, uint32_t ev_cap, Counters* ctr)
 {

@@ -92,6 +92,9 @@ cudaError_t launch_probe_bin(const BinArgs& a, bool counting, int ctas_per_sm, c
 #ifndef NTB_WALK_WARPS
 #define NTB_WALK_WARPS 4
 #endif
+#ifndef NTB_WALK_MIN_CTAS
+#define NTB_WALK_MIN_CTAS 5   // CTAs per SM the walker's shared-memory footprint allows: keep the register count below that bound too
+#endif
 constexpr int WALK_WARPS = NTB_WALK_WARPS;
 constexpr int WALK_THREADS = WALK_WARPS * 32;
 constexpr int WALK_TEAMS = WALK_THREADS / NTB_TEAM;   // walkers per CTA (engine.h: a team of NTB_TEAM lanes runs one walker)
