@@ -214,6 +214,7 @@ struct Workspace
 	TaskResult* d_results = nullptr;
 	size_t cap_tasks = 0;
 	Event* d_events = nullptr;
+	Event* d_events_sorted = nullptr; // the same events, grouped by walker (compact_events_kernel)
 	size_t cap_events = 0;
 	Counters* d_ctr = nullptr;
 	uint64_t* d_records = nullptr; // K1b: probe records, n_buckets x bucket_cap
@@ -235,6 +236,7 @@ struct Workspace
 		cudaFree(d_order);
 		cudaFree(d_results);
 		cudaFree(d_events);
+		cudaFree(d_events_sorted);
 		cudaFree(d_ctr);
 		cudaFree(d_records);
 		cudaFree(d_cursor);
@@ -595,6 +597,7 @@ struct CudaBackend
 			// sized for the recipe's ~1.1e-3 edits per base with headroom; grown on overflow
 			const size_t want = std::max<size_t>(1u << 16, (size_t)(batch->total / 256));
 			NTB_BE(cudaMalloc((void**)&ws->d_events, want * sizeof(Event)));
+			NTB_BE(cudaMalloc((void**)&ws->d_events_sorted, want * sizeof(Event)));
 			ws->cap_events = want;
 		}
 		NTB_BE(cudaMemcpyAsync(ws->d_tasks, ws->h_tasks, n * sizeof(Task), cudaMemcpyHostToDevice, stream));
@@ -619,10 +622,13 @@ struct CudaBackend
 			ms_walk += ms;
 			if (ctr.overflow) {
 				cudaFree(ws->d_events);
+				cudaFree(ws->d_events_sorted);
 				ws->d_events = nullptr;
+				ws->d_events_sorted = nullptr;
 				const size_t want = ws->cap_events * 4;
 				ws->cap_events = 0;
 				NTB_BE(cudaMalloc((void**)&ws->d_events, want * sizeof(Event)));
+				NTB_BE(cudaMalloc((void**)&ws->d_events_sorted, want * sizeof(Event)));
 				ws->cap_events = want;
 				continue;
 			}
@@ -640,7 +646,11 @@ struct CudaBackend
 			}
 			NTB_BE(cudaEventRecord(ws->ev0, stream));
 			if (ctr.n_events) {
-				NTB_BE(cudaMemcpyAsync(ws->h_events + ev_used, ws->d_events, (size_t)ctr.n_events * sizeof(Event), cudaMemcpyDeviceToHost, stream));
+				// group the events by walker on the device, then bring them over
+				NTB_BE(launch_compact_events(ws->d_events, ws->d_events_sorted, ws->d_results, (uint32_t)n, ws->d_ctr, stream));
+				launches++;
+				NTB_BE(cudaMemcpyAsync(ws->h_events + ev_used, ws->d_events_sorted, (size_t)ctr.n_events * sizeof(Event),
+				                       cudaMemcpyDeviceToHost, stream));
 			}
 			NTB_BE(cudaMemcpyAsync(ws->h_results, ws->d_results, n * sizeof(TaskResult), cudaMemcpyDeviceToHost, stream));
 			NTB_BE(cudaEventRecord(ws->ev1, stream));

@@ -834,6 +834,41 @@ order_tasks_kernel(const uint32_t* visit, const Task* tasks, uint32_t n_tasks, u
 	}
 }
 
+// The walkers append events to one arena through an atomic cursor, so the events of a walker are scattered and only linked
+// backwards.  One thread per task copies its chain into a contiguous run, first event first, and points the result at it:
+// the host then reads every walker's events sequentially instead of chasing `prev` through a 100 MB arena.
+__global__ void __launch_bounds__(256)
+compact_events_kernel(const Event* in, Event* out, TaskResult* results, uint32_t n_tasks, Counters* ctr)
+{
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n_tasks) {
+		return;
+	}
+	const uint32_t n = results[i].n_events;
+	if (n == 0) {
+		results[i].last_event = NONE32;
+		return;
+	}
+	const uint32_t base = atomicAdd(&ctr->n_compact, n);
+	uint32_t e = results[i].last_event;
+	for (uint32_t j = n; j > 0 && e != NONE32; j--) {
+		const Event ev = in[e];
+		out[base + j - 1] = ev;
+		e = ev.prev;
+	}
+	results[i].last_event = base;
+}
+
+cudaError_t
+launch_compact_events(const Event* in, Event* out, TaskResult* results, uint32_t n_tasks, Counters* ctr, cudaStream_t stream)
+{
+	if (n_tasks == 0) {
+		return cudaSuccess;
+	}
+	compact_events_kernel<<<(n_tasks + 255) / 256, 256, 0, stream>>>(in, out, results, n_tasks, ctr);
+	return cudaGetLastError();
+}
+
 template<int NCAP>
 static cudaError_t
 launch_walk_n(const uint8_t* text, const uint32_t* visit, const FilterView& bloom, const FilterView& rep, const KParams& kp, const Task* tasks,

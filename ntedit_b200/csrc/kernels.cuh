@@ -105,6 +105,9 @@ cudaError_t launch_walk(const uint8_t* text, const uint32_t* visit, const Filter
                         const Task* tasks, uint32_t* order, TaskResult* results, uint32_t n_tasks, Event* events, uint32_t ev_cap,
                         Counters* ctr, int sm_count, cudaStream_t stream);
 
+// lays every walker's events out contiguously in `out`, in emission order; results[i].last_event becomes the index of the first
+cudaError_t launch_compact_events(const Event* in, Event* out, TaskResult* results, uint32_t n_tasks, Counters* ctr, cudaStream_t stream);
+
 __global__ void insert_kernel(const uint8_t* text, uint64_t total, uint8_t* data, FilterView f, const __grid_constant__ KParams kp);
 
 __global__ void occupancy_kernel(const uint8_t* data, uint64_t bytes, int counting, unsigned long long* out);

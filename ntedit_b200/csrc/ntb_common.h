@@ -69,7 +69,9 @@ struct TaskResult
 {
 	uint32_t end_pos;      // tail position at which the walker stopped with a clean window (>= task.end), or len
 	uint32_t first_touch;  // tail position of the first site it evaluated (NONE32 if none)
-	uint32_t last_event;   // index of its last event in the arena (NONE32 if none); events chain through `prev`
+	uint32_t last_event;   // as the walker writes it: index of its last event in the arena (NONE32 if none), events chain
+	                       // through `prev`.  As Backend::walk() hands it to the host: index of its FIRST event -- the
+	                       // backend lays every walker's n_events events out contiguously, in emission order
 	uint32_t n_events;
 	uint32_t n_sites;
 	uint32_t status;
@@ -116,7 +118,7 @@ struct Counters
 	uint32_t next_task;  // work queue of the persistent walker warps
 	uint32_t n_front;    // order_tasks_kernel: dense tasks placed so far (from the front of the queue)
 	uint32_t n_back;     // ... the others (from the back)
-	uint32_t pad_;
+	uint32_t n_compact;  // compact_events_kernel: events placed so far
 	unsigned long long prof[16]; // -DNTB_PHASE_PROF: leader cycles per phase of the walker
 };
 

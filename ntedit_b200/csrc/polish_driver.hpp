@@ -9,7 +9,8 @@
 //   Task* task_buffer(size_t n);                           -- host buffer (pinned in the CUDA backend) for n tasks
 //   int   walk(const KParams&, size_t n_tasks, const TaskResult** results, const Event** events, size_t* n_events);
 //         -- K2 over the tasks in task_buffer(); results stay valid until the next walk(), the events of every
-//            round until the backend is destroyed
+//            round until the backend is destroyed.  The events of task i are events[results[i].last_event ..
+//            + results[i].n_events), in the order the walker emitted them
 // The product instantiates this with the CUDA backend (capi.cu); tests/hostsim instantiates it with a CPU
 // simulator of the same engine so the stitch/replay logic can be fuzzed without a GPU.
 #pragma once
@@ -21,6 +22,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <functional>
 #include <memory>
 #include <thread>
 
@@ -288,97 +290,202 @@ polish_run(Backend& be, const KParams& kp, const ntb_params& up, char* host_base
 		}
 	}
 
-	// ---- replay accepted events into ropes, contigs in parallel
+	// ---- replay accepted events into ropes.
+	// Every accepted walker result starts from a clean window ("anchored": k unedited bases on the rope's final position
+	// node), so the rope a contig ends up with is the concatenation of ropes replayed independently from fresh roots, cut
+	// anywhere between two accepted results: the cut only splits the position node that spans it.  Long contigs are
+	// therefore replayed as several PIECES in parallel (the largest human-like contig would otherwise be the critical path).
 	const auto t1 = clk::now();
-	std::atomic<uint64_t> next(0);
-	std::atomic<int> failed(0);
-	std::atomic<uint64_t> n_edits(0);
-	std::string first_error;
-	std::atomic_flag err_lock = ATOMIC_FLAG_INIT;
-	auto worker = [&]() {
-		std::vector<const Event*> chain;
-		for (;;) {
-			const uint64_t c = next.fetch_add(1);
-			if (c >= n_contigs) {
-				break;
-			}
-			ContigResult& cr = out.contigs[c];
-			if (!cr.polished) {
-				continue;
-			}
-			const uint32_t len = (uint32_t)(offsets[c + 1] - offsets[c] - 1);
-			// without a host copy of the bases, substitutions are only reported through the records
-			RopeReplay rp(host_bases ? host_bases + offsets[c] : nullptr, len, kp.k, kp.insertion_cap, kp.snv, kp.mask);
-			uint32_t prev_end = 0;
-			uint64_t edits = 0;
-			uint8_t stale[4] = { 0, 0, 0, 0 }; // see STALE_REF
-			auto resolve = [&stale](uint8_t v) -> uint8_t { return (v & STALE_REF) ? stale[v & 3] : v; };
-			for (uint64_t i = first_seg[c]; i < first_seg[c + 1] && !rp.ended; i++) {
-				const Segment& s = segs[i];
-				const uint32_t need = std::max(prev_end, s.p0);
-				if (need >= s.p1) {
-					continue;
-				}
-				const Event* arena = arenas[(size_t)s.arena];
-				chain.clear();
-				for (uint32_t e = s.res.last_event; e != NONE32; e = arena[e].prev) {
-					chain.push_back(&arena[e]);
-				}
-				for (size_t q = chain.size(); q > 0; q--) {
-					Event ev = *chain[q - 1];
-					ev.base = resolve(ev.base);
-					for (int a = 0; a < 3; a++) {
-						ev.altbase[a] = resolve(ev.altbase[a]);
-					}
-					if (!rp.apply(ev)) {
-						break;
-					}
-					if (chain[q - 1]->kind) {
-						edits++;
-					}
-				}
-				if (!rp.error.empty()) {
-					break;
-				}
-				const uint8_t next_stale[4] = { resolve(s.res.stale[0]), resolve(s.res.stale[1]), resolve(s.res.stale[2]),
-					                            resolve(s.res.stale[3]) };
-				std::memcpy(stale, next_stale, 4);
-				prev_end = s.res.end_pos;
-				if (s.res.status & ST_CONTIG_END) {
-					break;
-				}
-			}
-			if (!rp.error.empty()) {
-				failed = 1;
-				while (err_lock.test_and_set()) {
-				}
-				if (first_error.empty()) {
-					first_error = "contig " + std::to_string(c) + ": " + rp.error;
-				}
-				err_lock.clear();
-				continue;
-			}
-			n_edits += edits;
-			cr.nodes.swap(rp.rope);
-			cr.srecs.swap(rp.recs);
-		}
+	struct Piece
+	{
+		uint32_t contig;
+		uint64_t a0, a1;      // range inside `accepted`
+		uint8_t stale[4];     // reference's stale site locals at the start of the piece (see STALE_REF)
+		std::vector<ntb_node> nodes;
+		std::vector<ntb_srec> recs;
+		bool ended = false;
+		uint64_t edits = 0;
+		std::string error;
 	};
 	unsigned nthreads = std::thread::hardware_concurrency();
 	if (nthreads == 0) {
 		nthreads = 4;
 	}
-	nthreads = (unsigned)std::min<uint64_t>(nthreads, std::max<uint64_t>(1, n_contigs));
-	if (nthreads <= 1) {
-		worker();
-	} else {
+	auto run_parallel = [&](uint64_t n_items, const std::function<void(uint64_t)>& fn) {
+		std::atomic<uint64_t> next(0);
+		auto worker = [&]() {
+			for (;;) {
+				const uint64_t i = next.fetch_add(1);
+				if (i >= n_items) {
+					break;
+				}
+				fn(i);
+			}
+		};
+		const unsigned nt = (unsigned)std::min<uint64_t>(nthreads, std::max<uint64_t>(1, n_items));
+		if (nt <= 1) {
+			worker();
+			return;
+		}
 		std::vector<std::thread> pool;
-		for (unsigned i = 0; i < nthreads; i++) {
+		for (unsigned i = 0; i < nt; i++) {
 			pool.emplace_back(worker);
 		}
 		for (auto& th : pool) {
 			th.join();
 		}
+	};
+
+	// (A) per contig: the accepted results in order, the stale bytes each one starts with, and the cuts
+	uint64_t total_events = 0;
+	for (uint64_t i = 0; i < segs.size(); i++) {
+		total_events += segs[i].res.n_events;
 	}
+	uint64_t piece_events = std::max<uint64_t>(4096, total_events / ((uint64_t)nthreads * 8 + 1));
+	if (const char* v = std::getenv("NTB_REPLAY_PIECE_EVENTS")) { // testing aid: tiny pieces put a cut behind (almost) every result
+		piece_events = std::max<uint64_t>(1, std::strtoull(v, nullptr, 10));
+	}
+	std::vector<std::vector<uint64_t>> accepted(n_contigs);       // segment indices
+	std::vector<std::vector<Piece>> pieces(n_contigs);
+	run_parallel(n_contigs, [&](uint64_t c) {
+		if (!out.contigs[c].polished) {
+			return;
+		}
+		std::vector<uint64_t>& acc = accepted[c];
+		std::vector<Piece>& pc = pieces[c];
+		uint32_t prev_end = 0;
+		uint8_t stale[4] = { 0, 0, 0, 0 };
+		auto resolve = [&stale](uint8_t v) -> uint8_t { return (v & STALE_REF) ? stale[v & 3] : v; };
+		uint64_t in_piece = 0;
+		auto open_piece = [&]() {
+			Piece p;
+			p.contig = (uint32_t)c;
+			p.a0 = p.a1 = acc.size();
+			std::memcpy(p.stale, stale, 4);
+			pc.push_back(std::move(p));
+			in_piece = 0;
+		};
+		open_piece();
+		for (uint64_t i = first_seg[c]; i < first_seg[c + 1]; i++) {
+			const Segment& sg = segs[i];
+			const uint32_t need = std::max(prev_end, sg.p0);
+			if (need >= sg.p1) {
+				continue;
+			}
+			if (in_piece >= piece_events) {
+				open_piece();
+			}
+			acc.push_back(i);
+			pc.back().a1 = acc.size();
+			in_piece += sg.res.n_events + 1;
+			const uint8_t next_stale[4] = { resolve(sg.res.stale[0]), resolve(sg.res.stale[1]), resolve(sg.res.stale[2]),
+				                            resolve(sg.res.stale[3]) };
+			std::memcpy(stale, next_stale, 4);
+			prev_end = sg.res.end_pos;
+			if (sg.res.status & ST_CONTIG_END) {
+				break;
+			}
+		}
+	});
+
+	// (B) every piece on its own
+	std::vector<std::pair<uint32_t, uint32_t>> work; // (contig, piece)
+	for (uint64_t c = 0; c < n_contigs; c++) {
+		for (size_t q = 0; q < pieces[c].size(); q++) {
+			work.emplace_back((uint32_t)c, (uint32_t)q);
+		}
+	}
+	run_parallel(work.size(), [&](uint64_t w) {
+		const uint64_t c = work[w].first;
+		Piece& pc = pieces[c][work[w].second];
+		const uint32_t len = (uint32_t)(offsets[c + 1] - offsets[c] - 1);
+		// without a host copy of the bases, substitutions are only reported through the records
+		RopeReplay rp(host_bases ? host_bases + offsets[c] : nullptr, len, kp.k, kp.insertion_cap, kp.snv, kp.mask);
+		uint8_t stale[4];
+		std::memcpy(stale, pc.stale, 4);
+		auto resolve = [&stale](uint8_t v) -> uint8_t { return (v & STALE_REF) ? stale[v & 3] : v; };
+		for (uint64_t a = pc.a0; a < pc.a1 && !rp.ended; a++) {
+			const Segment& sg = segs[accepted[c][a]];
+			// the backend hands every walker's events over as one contiguous run, first event first
+			const Event* run = sg.res.n_events ? arenas[(size_t)sg.arena] + sg.res.last_event : nullptr;
+			for (uint32_t q = 0; q < sg.res.n_events; q++) {
+				Event ev = run[q];
+				ev.base = resolve(ev.base);
+				for (int x = 0; x < 3; x++) {
+					ev.altbase[x] = resolve(ev.altbase[x]);
+				}
+				if (!rp.apply(ev)) {
+					break;
+				}
+				if (ev.kind) {
+					pc.edits++;
+				}
+			}
+			if (!rp.error.empty()) {
+				break;
+			}
+			const uint8_t next_stale[4] = { resolve(sg.res.stale[0]), resolve(sg.res.stale[1]), resolve(sg.res.stale[2]),
+				                            resolve(sg.res.stale[3]) };
+			std::memcpy(stale, next_stale, 4);
+		}
+		pc.error = rp.error;
+		pc.ended = rp.ended;
+		pc.nodes.swap(rp.rope);
+		pc.recs.swap(rp.recs);
+	});
+
+	// (C) per contig: join the pieces' ropes
+	std::atomic<int> failed(0);
+	std::atomic<uint64_t> n_edits(0);
+	std::string first_error;
+	std::atomic_flag err_lock = ATOMIC_FLAG_INIT;
+	run_parallel(n_contigs, [&](uint64_t c) {
+		ContigResult& cr = out.contigs[c];
+		if (!cr.polished) {
+			return;
+		}
+		uint64_t edits = 0;
+		for (size_t q = 0; q < pieces[c].size(); q++) {
+			Piece& pc = pieces[c][q];
+			if (!pc.error.empty()) {
+				failed = 1;
+				while (err_lock.test_and_set()) {
+				}
+				if (first_error.empty()) {
+					first_error = "contig " + std::to_string(c) + ": " + pc.error;
+				}
+				err_lock.clear();
+				return;
+			}
+			edits += pc.edits;
+			if (q == 0) {
+				cr.nodes.swap(pc.nodes);
+				cr.srecs.swap(pc.recs);
+			} else {
+				// drop dead slots behind the rope so far; its last live node is the position node the cut went through
+				while (!cr.nodes.empty() && cr.nodes.back().node_type == -1) {
+					cr.nodes.pop_back();
+				}
+				if (cr.nodes.empty() || cr.nodes.back().node_type != 0 || pc.nodes.empty() || pc.nodes[0].node_type != 0) {
+					failed = 1;
+					while (err_lock.test_and_set()) {
+					}
+					if (first_error.empty()) {
+						first_error = "contig " + std::to_string(c) + ": rope pieces do not join on a position node";
+					}
+					err_lock.clear();
+					return;
+				}
+				cr.nodes.back().e_pos = pc.nodes[0].e_pos; // keeps s_pos / num_support of the node on the left of the cut
+				cr.nodes.insert(cr.nodes.end(), pc.nodes.begin() + 1, pc.nodes.end());
+				cr.srecs.insert(cr.srecs.end(), pc.recs.begin(), pc.recs.end());
+			}
+			if (pc.ended) {
+				break; // the reference's main loop ended inside this piece: nothing behind it was ever evaluated
+			}
+		}
+		n_edits += edits;
+	});
 	if (failed) {
 		err = first_error;
 		return NTB_EINTERNAL;

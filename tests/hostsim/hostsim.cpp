@@ -112,6 +112,11 @@ struct HostBackend
 			delete st;
 			if (!ctr.overflow) {
 				events.resize(ctr.n_events);
+				// Backend contract: last_event = index of the walker's first event, its events contiguous and in order.
+				// The tasks ran one after the other, so every chain already is a contiguous ascending run.
+				for (size_t i = 0; i < n_tasks; i++) {
+					results[i].last_event = results[i].n_events ? results[i].last_event + 1 - results[i].n_events : NONE32;
+				}
 				*res_out = results.data();
 				*ev_out = events.data();
 				*n_ev_out = events.size();

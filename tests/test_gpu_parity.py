@@ -141,3 +141,18 @@ def test_large_batch_properties(nb, oracle):
     ofa, otsv, _ = oracle.polish([(b"d", draft.tobytes())], ofilt, oracle.default_params(25, 3, mode=0))
     assert fa1 == ofa and tsv1 == otsv
     ofilt.free()
+
+
+def test_piecewise_replay_on_device_results(nb, oracle, monkeypatch):
+    """Same as tests/test_hostsim.py::test_piecewise_replay_joins_ropes_exactly, with the walkers' events coming from the GPU."""
+    monkeypatch.setenv("NTB_REPLAY_PIECE_EVENTS", "2")
+    for name in ("m1", "m2_i2_d3", "high_fpr_m0"):
+        case = [c for c in tc.CASES if c["name"] == name][0]
+        inp = tc.make_inputs(9000 + tc.CASES.index(case), **case.get("g", {}))
+        ofilt, orep = tc.oracle_filters(oracle, inp)
+        bloom, rep = device_filters(nb, inp)
+        fa, tsv, vcf, st = nb.polish(inp["contigs"], bloom, nb.default_params(segment_len=200, **case["p"]), bloomrep=rep)
+        op = oracle.default_params(inp["k"], inp["h"], **tc.oracle_param_overrides(case["p"]))
+        ofa, otsv, ovcf = oracle.polish(inp["contigs"], ofilt, op, bloomrep=orep)
+        assert fa == ofa and tsv == otsv and vcf == ovcf
+        ofilt.free()

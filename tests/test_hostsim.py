@@ -79,3 +79,22 @@ def test_neighbouring_errors_at_every_distance(oracle, mode):
     assert fa == ofa and tsv == otsv and vcf == ovcf
     assert st.edits > 300
     filt.free()
+
+
+@pytest.mark.parametrize("piece_events", [1, 7])
+@pytest.mark.parametrize("name", ["m0_i4_d5", "m2_i2_d3", "snv", "mask", "cbf_p2_q200", "high_fpr_m2", "short_contigs_z1000"])
+def test_piecewise_replay_joins_ropes_exactly(oracle, monkeypatch, name, piece_events):
+    """The host replays long contigs as independent pieces cut between walker results and joins the ropes
+    (polish_driver.hpp).  Tiny pieces + short segments put a cut behind (almost) every result."""
+    monkeypatch.setenv("NTB_REPLAY_PIECE_EVENTS", str(piece_events))
+    g = gu.load(name)
+    filt = oracle.OracleFilter.load(g["filter_path"])
+    rep = oracle.OracleFilter.load(g["rep_path"]) if g["rep_path"] else None
+    for seg in (0, 110):
+        fa, tsv, vcf, st = run_hostsim(g["contigs"], filt, g["case"]["params"], rep=rep, segment_len=seg)
+        assert fa == g["fa"]
+        assert tsv == g["tsv"]
+        assert vcf == g["vcf"]
+    filt.free()
+    if rep:
+        rep.free()
