@@ -7,6 +7,7 @@
 // (ntb_polish_batch); with --gpus N batches go round-robin to N devices, the filter replicated on each.  Output is
 // always in input order (= the reference's `-t 1` order).  No hashing and no filter probe happens in this file.
 #include "../../include/ntedit_b200.h"
+#include "fastx.hpp"
 #include "writer.hpp"
 
 #include <getopt.h>
@@ -143,148 +144,6 @@ die_ntb(const char* what)
 	std::cerr << PROGRAM ": error: " << what << ": " << ntb_last_error() << "\n";
 	std::exit(EXIT_FAILURE);
 }
-
-// ---------------------------------------------------------------- kseq-compatible FASTA/FASTQ reader over zlib
-// Same record semantics as lib/kseq.h:175-215: name = up to the first whitespace, comment = rest of the header line,
-// sequence lines concatenated with every character kept except newlines / carriage returns... (kseq keeps all
-// printable characters of a sequence line; it drops only the line terminator and isgraph-failing bytes)
-class FastxReader
-{
-  public:
-	explicit FastxReader(const std::string& path) : buf_(1 << 20)
-	{
-		fp_ = gzopen(path.c_str(), "r");
-		if (fp_) {
-			gzbuffer(fp_, 1 << 20);
-		}
-	}
-	~FastxReader()
-	{
-		if (fp_) {
-			gzclose(fp_);
-		}
-	}
-	bool ok() const { return fp_ != nullptr; }
-
-	// reads the next record; sequence is appended to `seq`.  Returns false at end of file.
-	bool next(std::string& name, std::string& comment, std::string& seq)
-	{
-		int c;
-		if (last_char_ == 0) { // jump to the next header line
-			while ((c = getc_()) != -1 && c != '>' && c != '@') {
-			}
-			if (c == -1) {
-				return false;
-			}
-			last_char_ = c;
-		}
-		name.clear();
-		comment.clear();
-		// name: up to the first whitespace
-		while ((c = getc_()) != -1 && !isspace_(c)) {
-			name.push_back((char)c);
-		}
-		if (c == -1 && name.empty()) {
-			return false;
-		}
-		if (c != '\n' && c != -1) { // comment: the rest of the line
-			while ((c = getc_()) != -1 && c != '\n') {
-				comment.push_back((char)c);
-			}
-			if (!comment.empty() && comment.back() == '\r') {
-				comment.pop_back();
-			}
-		}
-		const size_t seq0 = seq.size();
-		while ((c = getc_()) != -1 && c != '>' && c != '+' && c != '@') {
-			if (c == '\n') {
-				continue;
-			}
-			seq.push_back((char)c);
-			append_line_(seq); // rest of the line
-		}
-		if (c == '>' || c == '@') {
-			last_char_ = c;
-		} else {
-			last_char_ = 0;
-		}
-		if (c != '+') {
-			return true;
-		}
-		// FASTQ: skip the rest of the '+' line, then as many quality characters as there are bases
-		while ((c = getc_()) != -1 && c != '\n') {
-		}
-		if (c == -1) {
-			return true;
-		}
-		const size_t want = seq.size() - seq0;
-		size_t have = 0;
-		std::string q;
-		while (have < want && (c = getc_()) != -1) {
-			if (c == '\n') {
-				continue;
-			}
-			q.clear();
-			q.push_back((char)c);
-			append_line_(q);
-			have += q.size();
-		}
-		last_char_ = 0;
-		return true;
-	}
-
-  private:
-	static bool isspace_(int c) { return c == ' ' || c == '\t' || c == '\n' || c == '\r' || c == '\v' || c == '\f'; }
-
-	int getc_()
-	{
-		if (pos_ >= len_) {
-			if (eof_) {
-				return -1;
-			}
-			const int n = gzread(fp_, buf_.data(), (unsigned)buf_.size());
-			if (n <= 0) {
-				eof_ = true;
-				return -1;
-			}
-			len_ = (size_t)n;
-			pos_ = 0;
-		}
-		return (unsigned char)buf_[pos_++];
-	}
-
-	// appends the rest of the current line (without its terminator) to s
-	void append_line_(std::string& s)
-	{
-		for (;;) {
-			if (pos_ >= len_) {
-				const int c = getc_();
-				if (c == -1) {
-					break;
-				}
-				pos_--;
-			}
-			const char* b = buf_.data() + pos_;
-			const char* nl = (const char*)std::memchr(b, '\n', len_ - pos_);
-			const size_t n = nl ? (size_t)(nl - b) : len_ - pos_;
-			s.append(b, n);
-			pos_ += n;
-			if (nl) {
-				pos_++; // consume the newline
-				break;
-			}
-		}
-		if (!s.empty() && s.back() == '\r') {
-			s.pop_back();
-		}
-	}
-
-	gzFile fp_ = nullptr;
-	std::vector<char> buf_;
-	size_t pos_ = 0, len_ = 0;
-	bool eof_ = false;
-	int last_char_ = 0;
-};
 
 // vcf_entry_to_map, ntedit.cpp:2261-2274
 void
@@ -589,7 +448,7 @@ main(int argc, char** argv)
 	std::cout << "---------- reading/processing input sequence        : " << now_str();
 
 	// ---- readAndCorrect, ntedit.cpp:2154-2259
-	FastxReader reader(opt.draft);
+	ntb::FastxReader reader(opt.draft);
 	if (!reader.ok()) {
 		std::cerr << PROGRAM ": error: cannot open `" << opt.draft << "'\n";
 		return EXIT_FAILURE;

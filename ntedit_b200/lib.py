@@ -12,6 +12,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "_lib")
 SO = os.path.join(LIBDIR, "libntedit_b200.so")
 CLI = os.path.join(LIBDIR, "ntedit-b200")
+MAKE_BF = os.path.join(LIBDIR, "ntedit-b200-make-bf")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17"]
@@ -42,11 +43,12 @@ def build(force=False, verbose=False):
     if force or _stale(SO, _deps()):
         cmd = [nvcc] + NVCC_FLAGS + ["-Xcompiler", "-fPIC", "-shared"] + _sources() + ["-o", SO]
         subprocess.run(cmd, check=True, stdout=out)
-    cli_src = os.path.join(CSRC, "cli.cpp")
-    if os.path.exists(cli_src) and (force or _stale(CLI, _deps() + [SO])):
-        cmd = ["g++", "-O2", "-std=c++17", "-I", INCLUDE, cli_src, "-o", CLI, "-L", LIBDIR, "-lntedit_b200",
-               "-Wl,-rpath,$ORIGIN", "-lz", "-pthread"]
-        subprocess.run(cmd, check=True, stdout=out)
+    for src, exe in (("cli.cpp", CLI), ("make_bf_cli.cpp", MAKE_BF)):
+        path = os.path.join(CSRC, src)
+        if os.path.exists(path) and (force or _stale(exe, _deps() + [SO])):
+            cmd = ["g++", "-O2", "-std=c++17", "-I", INCLUDE, path, "-o", exe, "-L", LIBDIR, "-lntedit_b200",
+                   "-Wl,-rpath,$ORIGIN", "-lz", "-pthread"]
+            subprocess.run(cmd, check=True, stdout=out)
     return SO
 
 

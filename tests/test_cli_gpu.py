@@ -120,3 +120,62 @@ def test_cli_fastq_and_crlf_input(nb, oracle, tmp_path):
     rfa, rtsv, rvcf = oracle.run_ref(fq, fpath, workdir=str(tmp_path), extra=("-m", 1))
     assert got[0] == rfa and got[1] == rtsv
     assert strip_date(got[2]) == strip_date(rvcf)
+
+
+def test_make_bf_cli_builds_the_filter_the_oracle_builds(nb, oracle, tmp_path):
+    """ntedit-b200-make-bf (ntedit_make_genome_bf's role, src/ntedit_make_genome_bf.cpp:49-165): FASTA in, btllib filter
+    file out, byte-identical to the oracle's builder; sized by --bf, --num_elements or the genome length; then used to
+    polish with both our CLI and the reference."""
+    import math
+    rng = np.random.default_rng(808)
+    truths = [synth.random_genome(n, rng) for n in (30000, 24, 25, 12000)]   # one record shorter than k: skipped
+    g1 = str(tmp_path / "g1.fa")
+    g2 = str(tmp_path / "g2.fa.gz")
+    synth.write_fasta(g1, [(b"chr1 x", truths[0].tobytes()), (b"tiny", truths[1].tobytes())])
+    plain = str(tmp_path / "g2.fa")
+    synth.write_fasta(plain, [(b"k", truths[2].tobytes()), (b"chr2", truths[3].tobytes())], width=0)
+    with open(plain, "rb") as src, gzip.open(g2, "wb") as dst:
+        dst.write(src.read())
+
+    def run(args):
+        r = subprocess.run([lib.MAKE_BF] + [str(a) for a in args], stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=300)
+        assert r.returncode == 0, r.stderr.decode(errors="replace")
+        return r.stdout.decode()
+
+    out = str(tmp_path / "genome.bf")
+    stdout = run(["--genome", g1, g2, "-k", 25, "--bf", 100003, "-o", out])
+    assert "BF size (bytes): 100000" in stdout          # whole 64-bit words
+    of = oracle.OracleFilter.load(out)
+    assert (of.k, of.h, of.counting, of.nbytes) == (25, 3, False, 100000)
+    want = oracle.OracleFilter.new(100000, 25, 3, False)
+    for t in (truths[0], truths[2], truths[3]):
+        want.insert_seq(t.tobytes())
+    assert np.array_equal(of.data(), want.data())
+    assert ("Bloom filter FPR: %g" % want.fpr()) in stdout
+
+    # sizing from the genome length (Broder & Mitzenmacher, src/ntedit_make_genome_bf.cpp:41-47)
+    stdout = run(["--genome", g1, g2, "-k", 25, "--fpr", 0.001, "--hashes", 4, "-o", out])
+    n = sum(len(t) for t in truths)
+    r = -4 / math.log(1.0 - math.exp(math.log(0.001) / 4))
+    expect = int(math.ceil(n * r) / 8) // 8 * 8
+    assert ("Genome size (bp): %d" % n) in stdout and ("BF size (bytes): %d" % expect) in stdout
+    of2 = oracle.OracleFilter.load(out)
+    assert (of2.h, of2.nbytes) == (4, expect)
+
+    # counting variant + polishing through the file with both command lines
+    cbf = str(tmp_path / "genome.cbf")
+    run(["--genome", g1, g2, "-k", 25, "--num_elements", 50000, "--counting", "-o", cbf])
+    draft = synth.mutate(truths[0], rng, 2e-3, 5e-4)
+    dpath = str(tmp_path / "draft.fa")
+    synth.write_fasta(dpath, [(b"chr1 draft", draft.tobytes())])
+    for fpath, flags in ((str(tmp_path / "genome1.bf"), ("-m", 1)), (cbf, ("-m", 2))):
+        if not os.path.exists(fpath):
+            run(["--genome", g1, "-k", 25, "--bf", 1 << 17, "-o", fpath])
+        got = run_cli(dpath, fpath, str(tmp_path / "o"), extra=flags)
+        if oracle.have_ref():
+            rfa, rtsv, rvcf = oracle.run_ref(dpath, fpath, workdir=str(tmp_path), extra=flags)
+            assert got[0] == rfa and got[1] == rtsv and strip_date(got[2]) == strip_date(rvcf)
+        assert got[1].count(b"\n") > 20
+    of.free()
+    of2.free()
+    want.free()
