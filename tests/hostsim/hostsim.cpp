@@ -106,8 +106,14 @@ struct HostBackend
 				io.ev_cap = (uint32_t)events.size();
 				io.ctr = &ctr;
 				io.rot = rot.data();
-				Walker<352> w(*st, kp);
-				w.run(tasks[i], results[i]);
+				// the same two instantiations the device kernel dispatches between
+				if (!kp.counting && !kp.h_rep && !kp.snv && !kp.mask) {
+					Walker<352, true> w(*st, kp);
+					w.run(tasks[i], results[i]);
+				} else {
+					Walker<352, false> w(*st, kp);
+					w.run(tasks[i], results[i]);
+				}
 			}
 			delete st;
 			if (!ctr.overflow) {
