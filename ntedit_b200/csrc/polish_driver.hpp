@@ -192,121 +192,8 @@ polish_run(Backend& be, const KParams& kp, const ntb_params& up, char* host_base
 	if (dbg) {
 		std::fprintf(stderr, "[ntb] host: %zu segments built in %.1f ms\n", segs.size(), since(t_begin));
 	}
-	const auto t_scan = clk::now();
-	be.scan_end();
-	if (dbg) {
-		std::fprintf(stderr, "[ntb] host: scan returned after %.1f ms\n", since(t_scan));
-	}
 
-	// ---- rounds of walkers + stitching
-	std::vector<const Event*> arenas; // events of each round (owned by the backend)
-	std::vector<uint64_t> pending; // segment indices to (re)run
-	pending.reserve(segs.size());
-	for (uint64_t i = 0; i < segs.size(); i++) {
-		pending.push_back(i);
-	}
-	double host_ms = 0;
-	while (!pending.empty()) {
-		Task* tasks = be.task_buffer(pending.size());
-		if (!tasks) {
-			err = be.error();
-			return NTB_ENOMEM;
-		}
-		for (size_t i = 0; i < pending.size(); i++) {
-			const Segment& s = segs[pending[i]];
-			Task& t = tasks[i];
-			t.text_off = offsets[s.contig];
-			t.len = (uint32_t)(offsets[s.contig + 1] - offsets[s.contig] - 1);
-			t.start = s.run_start;
-			t.end = s.p1;
-			t.contig = s.contig;
-			t.flags = (s.p0 == 0 && s.run_start == 0) ? TASK_CONTIG_START : 0;
-			t.pad_ = 0;
-		}
-		const TaskResult* results = nullptr;
-		const Event* round_events = nullptr;
-		size_t n_round_events = 0;
-		const auto t_walk = clk::now();
-		const int rc = be.walk(kp, pending.size(), &results, &round_events, &n_round_events);
-		if (dbg) {
-			std::fprintf(stderr, "[ntb] host: walk round (%zu tasks, %zu events) returned after %.1f ms\n", pending.size(), n_round_events,
-			             since(t_walk));
-		}
-		if (rc != NTB_OK) {
-			err = be.error();
-			return rc;
-		}
-		arenas.push_back(round_events);
-		out.stats.rounds++;
-		out.stats.segments += pending.size();
-		if (out.stats.rounds > 1) {
-			out.stats.reruns += pending.size();
-		}
-		const auto t0 = clk::now();
-		for (size_t i = 0; i < pending.size(); i++) {
-			Segment& s = segs[pending[i]];
-			s.res = results[i];
-			s.arena = (int32_t)arenas.size() - 1;
-			if (s.res.status & ST_ROPE_OVERFLOW) {
-				err = "device rope capacity exceeded (pathological insertion run); input not supported";
-				return NTB_EINTERNAL;
-			}
-			if (!(s.res.status & ST_DONE) || (s.res.status & ST_EV_OVERFLOW)) {
-				err = "device walker did not finish";
-				return NTB_EINTERNAL;
-			}
-			out.stats.sites += s.res.n_sites;
-		}
-		// stitch pass: accept results in contig order; where a predecessor ran past a successor's first site, re-run
-		// that successor from the predecessor's clean end (optimistically assuming the re-run will end on its own border)
-		pending.clear();
-		for (uint64_t c = 0; c < n_contigs; c++) {
-			uint32_t prev_end = 0;
-			for (uint64_t i = first_seg[c]; i < first_seg[c + 1]; i++) {
-				Segment& s = segs[i];
-				const uint32_t need = std::max(prev_end, s.p0);
-				if (need >= s.p1) {
-					continue; // entirely covered by the predecessor's overrun
-				}
-				const uint32_t ft = s.res.first_touch != NONE32 ? std::min(s.res.first_touch, s.res.end_pos) : s.res.end_pos;
-				const bool valid = s.arena >= 0 && s.run_start <= need && need <= ft;
-				if (valid) {
-					prev_end = s.res.end_pos;
-					if (s.res.status & ST_CONTIG_END) {
-						break;
-					}
-				} else {
-					s.run_start = need;
-					s.arena = -1;
-					pending.push_back(i);
-					prev_end = s.p1;
-				}
-			}
-		}
-		host_ms += std::chrono::duration<double, std::milli>(clk::now() - t0).count();
-		if (out.stats.rounds > 64) {
-			err = "stitcher did not converge";
-			return NTB_EINTERNAL;
-		}
-	}
-
-	// ---- replay accepted events into ropes.
-	// Every accepted walker result starts from a clean window ("anchored": k unedited bases on the rope's final position
-	// node), so the rope a contig ends up with is the concatenation of ropes replayed independently from fresh roots, cut
-	// anywhere between two accepted results: the cut only splits the position node that spans it.  Long contigs are
-	// therefore replayed as several PIECES in parallel (the largest human-like contig would otherwise be the critical path).
-	const auto t1 = clk::now();
-	struct Piece
-	{
-		uint32_t contig;
-		uint64_t a0, a1;      // range inside `accepted`
-		uint8_t stale[4];     // reference's stale site locals at the start of the piece (see STALE_REF)
-		std::vector<ntb_node> nodes;
-		std::vector<ntb_srec> recs;
-		bool ended = false;
-		uint64_t edits = 0;
-		std::string error;
-	};
+	// host thread pool helper: fn(i) for i in [0, n_items), dynamically scheduled
 	unsigned nthreads = std::thread::hardware_concurrency();
 	if (nthreads == 0) {
 		nthreads = 4;
@@ -336,6 +223,162 @@ polish_run(Backend& be, const KParams& kp, const ntb_params& up, char* host_base
 		}
 	};
 
+	// ---- rounds of walkers + stitching
+	std::vector<const Event*> arenas; // events of each round (owned by the backend)
+	std::vector<uint64_t> pending; // segment indices to (re)run
+	pending.reserve(segs.size());
+	for (uint64_t i = 0; i < segs.size(); i++) {
+		pending.push_back(i);
+	}
+	double host_ms = 0;
+	bool scan_pending = true; // K1 is still running while the first round's tasks are written
+	while (!pending.empty()) {
+		Task* tasks = be.task_buffer(pending.size());
+		if (!tasks) {
+			err = be.error();
+			return NTB_ENOMEM;
+		}
+		{
+			const uint64_t n_pending = pending.size();
+			const uint64_t chunk = 16384;
+			run_parallel((n_pending + chunk - 1) / chunk, [&](uint64_t q) {
+				const uint64_t e = std::min<uint64_t>(n_pending, (q + 1) * chunk);
+				for (uint64_t i = q * chunk; i < e; i++) {
+					const Segment& sg = segs[pending[i]];
+					Task& t = tasks[i];
+					t.text_off = offsets[sg.contig];
+					t.len = (uint32_t)(offsets[sg.contig + 1] - offsets[sg.contig] - 1);
+					t.start = sg.run_start;
+					t.end = sg.p1;
+					t.contig = sg.contig;
+					t.flags = (sg.p0 == 0 && sg.run_start == 0) ? TASK_CONTIG_START : 0;
+					t.pad_ = 0;
+				}
+			});
+		}
+		if (scan_pending) {
+			const auto t_scan = clk::now();
+			be.scan_end();
+			scan_pending = false;
+			if (dbg) {
+				std::fprintf(stderr, "[ntb] host: scan returned after %.1f ms\n", since(t_scan));
+			}
+		}
+		const TaskResult* results = nullptr;
+		const Event* round_events = nullptr;
+		size_t n_round_events = 0;
+		const auto t_walk = clk::now();
+		const int rc = be.walk(kp, pending.size(), &results, &round_events, &n_round_events);
+		if (dbg) {
+			std::fprintf(stderr, "[ntb] host: walk round (%zu tasks, %zu events) returned after %.1f ms\n", pending.size(), n_round_events,
+			             since(t_walk));
+		}
+		if (rc != NTB_OK) {
+			err = be.error();
+			return rc;
+		}
+		arenas.push_back(round_events);
+		out.stats.rounds++;
+		out.stats.segments += pending.size();
+		if (out.stats.rounds > 1) {
+			out.stats.reruns += pending.size();
+		}
+		const auto t0 = clk::now();
+		{
+			// take the results over (chunks of tasks in parallel)
+			const uint64_t n_pending = pending.size();
+			const uint64_t chunk = 16384;
+			const uint64_t n_chunks = (n_pending + chunk - 1) / chunk;
+			std::vector<uint64_t> chunk_sites(n_chunks, 0);
+			std::atomic<int> bad(0);
+			const int32_t arena_idx = (int32_t)arenas.size() - 1;
+			run_parallel(n_chunks, [&](uint64_t q) {
+				uint64_t sites = 0;
+				const uint64_t e = std::min<uint64_t>(n_pending, (q + 1) * chunk);
+				for (uint64_t i = q * chunk; i < e; i++) {
+					Segment& sg = segs[pending[i]];
+					sg.res = results[i];
+					sg.arena = arena_idx;
+					if (sg.res.status & ST_ROPE_OVERFLOW) {
+						bad = 1;
+					} else if (!(sg.res.status & ST_DONE) || (sg.res.status & ST_EV_OVERFLOW)) {
+						bad = 2;
+					}
+					sites += sg.res.n_sites;
+				}
+				chunk_sites[q] = sites;
+			});
+			if (bad == 1) {
+				err = "device rope capacity exceeded (pathological insertion run); input not supported";
+				return NTB_EINTERNAL;
+			}
+			if (bad == 2) {
+				err = "device walker did not finish";
+				return NTB_EINTERNAL;
+			}
+			for (uint64_t q = 0; q < n_chunks; q++) {
+				out.stats.sites += chunk_sites[q];
+			}
+		}
+		// stitch pass, contigs in parallel: accept results in contig order; where a predecessor ran past a successor's first
+		// site, re-run that successor from the predecessor's clean end (optimistically assuming the re-run will end on its
+		// own border)
+		std::vector<std::vector<uint64_t>> redo(n_contigs);
+		run_parallel(n_contigs, [&](uint64_t c) {
+			uint32_t prev_end = 0;
+			for (uint64_t i = first_seg[c]; i < first_seg[c + 1]; i++) {
+				Segment& sg = segs[i];
+				const uint32_t need = std::max(prev_end, sg.p0);
+				if (need >= sg.p1) {
+					continue; // entirely covered by the predecessor's overrun
+				}
+				const uint32_t ft = sg.res.first_touch != NONE32 ? std::min(sg.res.first_touch, sg.res.end_pos) : sg.res.end_pos;
+				const bool valid = sg.arena >= 0 && sg.run_start <= need && need <= ft;
+				if (valid) {
+					prev_end = sg.res.end_pos;
+					if (sg.res.status & ST_CONTIG_END) {
+						break;
+					}
+				} else {
+					sg.run_start = need;
+					sg.arena = -1;
+					redo[c].push_back(i);
+					prev_end = sg.p1;
+				}
+			}
+		});
+		pending.clear();
+		for (uint64_t c = 0; c < n_contigs; c++) {
+			pending.insert(pending.end(), redo[c].begin(), redo[c].end());
+		}
+		host_ms += std::chrono::duration<double, std::milli>(clk::now() - t0).count();
+		if (out.stats.rounds > 64) {
+			err = "stitcher did not converge";
+			return NTB_EINTERNAL;
+		}
+	}
+
+	if (scan_pending) {
+		be.scan_end();
+	}
+
+	// ---- replay accepted events into ropes.
+	// Every accepted walker result starts from a clean window ("anchored": k unedited bases on the rope's final position
+	// node), so the rope a contig ends up with is the concatenation of ropes replayed independently from fresh roots, cut
+	// anywhere between two accepted results: the cut only splits the position node that spans it.  Long contigs are
+	// therefore replayed as several PIECES in parallel (the largest human-like contig would otherwise be the critical path).
+	const auto t1 = clk::now();
+	struct Piece
+	{
+		uint32_t contig;
+		uint64_t a0, a1;      // range inside `accepted`
+		uint8_t stale[4];     // reference's stale site locals at the start of the piece (see STALE_REF)
+		std::vector<ntb_node> nodes;
+		std::vector<ntb_srec> recs;
+		bool ended = false;
+		uint64_t edits = 0;
+		std::string error;
+	};
 	// (A) per contig: the accepted results in order, the stale bytes each one starts with, and the cuts
 	uint64_t total_events = 0;
 	for (uint64_t i = 0; i < segs.size(); i++) {
