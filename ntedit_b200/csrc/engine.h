@@ -338,7 +338,9 @@ constexpr uint32_t WALK_KP_BYTES = (sizeof(KParams) + 127u) & ~127u; // device: 
 // COMMON = the configuration nearly every polishing run uses -- bit filter, no secondary filter (-e), not -s 1, not -a 1 --
 // known at compile time: the counting-filter, secondary-filter, SNV and masking branches fold away, which takes ~7 % off
 // the kernel's code and ~10 % off its run time (the walker is bound by instruction fetch).
-template<int NCAP, bool COMMON = false>
+// POW2 = every filter the walker probes has a power-of-two number of slots: `% size` is a mask and the multiply-high
+// remainder (20 instructions per probe, if-converted into every probe site otherwise) is not compiled in.
+template<int NCAP, bool COMMON = false, bool POW2 = false>
 struct Walker
 {
 	static constexpr int OVCAP = WalkerState<NCAP>::OVCAP;
@@ -381,6 +383,7 @@ struct Walker
 	NTB_FN int snv_() const { return COMMON ? 0 : P.snv; }
 	NTB_FN int mask_() const { return COMMON ? 0 : P.mask; }
 	NTB_FN uint32_t fcounting_(const FilterView& f) const { return COMMON ? 0u : f.counting; }
+	NTB_FN uint64_t slot_(const FilterView& f, uint64_t x) const { return POW2 ? (x & f.mask) : filter_slot(f, x); }
 
 	// ---------------------------------------------------------------- text / rope access
 	NTB_FN unsigned char rd(uint32_t pos) const
@@ -635,7 +638,7 @@ struct Walker
 			}
 			const uint64_t hb = S.hb[g][ln];
 			for (uint32_t u = 0; u < hn; u++) {
-				const uint64_t slot = filter_slot(F, hash_extend(hb, P.k, i0 + u));
+				const uint64_t slot = slot_(F, hash_extend(hb, P.k, i0 + u));
 				const uint64_t byte = fcounting_(F) ? slot : slot >> 3;
 				S.psh[g][u][ln] = (uint8_t)(((uint32_t)byte & 3u) * 8u + (fcounting_(F) ? 0u : ((uint32_t)slot & 7u)));
 				const uint8_t* src = F.data + (byte & ~3ULL);
@@ -1421,7 +1424,7 @@ struct Walker
 					r ^= rot[in ? rc[q] + (k - R + q) : 4u * ROT_STRIDE];
 				}
 				hv[g] = f + r;
-				const uint64_t slot = filter_slot(F, hv[g]);
+				const uint64_t slot = slot_(F, hv[g]);
 				sh[g] = (uint32_t)slot & 7u;
 				got[g] = probe_byte(F.data + (slot >> 3));
 			}
@@ -1430,7 +1433,7 @@ struct Walker
 				if (s0 + g < nv && ((got[g] >> sh[g]) & 1u)) {
 					bool all = true;
 					for (uint32_t h = 1; h < hn && all; h++) {
-						const uint64_t slot = filter_slot(F, hash_extend(hv[g], k, h));
+						const uint64_t slot = slot_(F, hash_extend(hv[g], k, h));
 						all = ((probe_byte(F.data + (slot >> 3)) >> ((uint32_t)slot & 7u)) & 1u) != 0;
 					}
 					count += all ? 1u : 0u;

@@ -724,7 +724,7 @@ launch_probe_bin(const BinArgs& a, bool counting, int grid_probe, cudaStream_t s
 // K2: persistent warps, one task (contig segment) per warp at a time, tasks handed out through an atomic counter.
 // The walker state of every warp lives in shared memory (engine.h: WalkerState); lane 0 is the leader.
 // NCAP (capacity of the local rope copy) is 2.5 k + 32 rounded up: 160 serves k <= 48, 352 serves k <= KMAX.
-template<int NCAP, bool COMMON>
+template<int NCAP, bool COMMON, bool POW2>
 __global__ void __launch_bounds__(WALK_THREADS, NTB_WALK_MIN_CTAS)
 walk_kernel(const uint8_t* text, const uint32_t* visit, FilterView bloom, FilterView rep, const __grid_constant__ KParams kp,
             const Task* tasks, const uint32_t* order, TaskResult* results, uint32_t n_tasks, Event* events, uint32_t ev_cap, Counters* ctr)
@@ -742,7 +742,7 @@ walk_kernel(const uint8_t* text, const uint32_t* visit, FilterView bloom, Filter
 	}
 	__syncthreads();
 	const uint32_t lane = lane_id();
-	Walker<NCAP, COMMON> w(S, kp);
+	Walker<NCAP, COMMON, POW2> w(S, kp);
 	bool have = false;
 	uint32_t i = 0;
 	Task task;
@@ -869,7 +869,7 @@ launch_compact_events(const Event* in, Event* out, TaskResult* results, uint32_t
 	return cudaGetLastError();
 }
 
-template<int NCAP, bool COMMON>
+template<int NCAP, bool COMMON, bool POW2>
 static cudaError_t
 launch_walk_n(const uint8_t* text, const uint32_t* visit, const FilterView& bloom, const FilterView& rep, const KParams& kp, const Task* tasks,
               const uint32_t* order, TaskResult* results, uint32_t n_tasks, Event* events, uint32_t ev_cap, Counters* ctr, int sm_count,
@@ -878,12 +878,12 @@ launch_walk_n(const uint8_t* text, const uint32_t* visit, const FilterView& bloo
 	static int blocks_per_sm = 0;
 	const size_t smem = WALK_KP_BYTES + WALK_ROT_BYTES + (size_t)WALK_TEAMS * sizeof(WalkerState<NCAP>);
 	if (blocks_per_sm == 0) {
-		cudaError_t e = cudaFuncSetAttribute(walk_kernel<NCAP, COMMON>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+		cudaError_t e = cudaFuncSetAttribute(walk_kernel<NCAP, COMMON, POW2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 		if (e != cudaSuccess) {
 			return e;
 		}
 		int n = 0;
-		e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, walk_kernel<NCAP, COMMON>, WALK_THREADS, smem);
+		e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, walk_kernel<NCAP, COMMON, POW2>, WALK_THREADS, smem);
 		if (e != cudaSuccess) {
 			return e;
 		}
@@ -901,7 +901,7 @@ launch_walk_n(const uint8_t* text, const uint32_t* visit, const FilterView& bloo
 	if (grid == 0) {
 		return cudaSuccess;
 	}
-	walk_kernel<NCAP, COMMON><<<grid, WALK_THREADS, smem, stream>>>(text, visit, bloom, rep, kp, tasks, order, results, n_tasks, events, ev_cap, ctr);
+	walk_kernel<NCAP, COMMON, POW2><<<grid, WALK_THREADS, smem, stream>>>(text, visit, bloom, rep, kp, tasks, order, results, n_tasks, events, ev_cap, ctr);
 	return cudaGetLastError();
 }
 
@@ -917,13 +917,18 @@ launch_walk(const uint8_t* text, const uint32_t* visit, const FilterView& bloom,
 			return e;
 		}
 	}
-	// the specialised instantiation serves the common configuration (see engine.h: Walker<NCAP, COMMON>)
+	// the specialised instantiations serve the common configuration (see engine.h: Walker<NCAP, COMMON, POW2>)
 	const bool common = !kp.counting && !kp.h_rep && !kp.snv && !kp.mask;
+	const bool pow2 = common && bloom.mask != 0;
 #define NTB_WALK_ARGS text, visit, bloom, rep, kp, tasks, order, results, n_tasks, events, ev_cap, ctr, sm_count, stream
 	if (kp.k <= 48) {
-		return common ? launch_walk_n<160, true>(NTB_WALK_ARGS) : launch_walk_n<160, false>(NTB_WALK_ARGS);
+		return pow2     ? launch_walk_n<160, true, true>(NTB_WALK_ARGS)
+		       : common ? launch_walk_n<160, true, false>(NTB_WALK_ARGS)
+		                : launch_walk_n<160, false, false>(NTB_WALK_ARGS);
 	}
-	return common ? launch_walk_n<352, true>(NTB_WALK_ARGS) : launch_walk_n<352, false>(NTB_WALK_ARGS);
+	return pow2     ? launch_walk_n<352, true, true>(NTB_WALK_ARGS)
+	       : common ? launch_walk_n<352, true, false>(NTB_WALK_ARGS)
+	                : launch_walk_n<352, false, false>(NTB_WALK_ARGS);
 #undef NTB_WALK_ARGS
 }
 

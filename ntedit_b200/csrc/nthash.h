@@ -188,7 +188,9 @@ mulhi64(uint64_t a, uint64_t b)
 #endif
 }
 
-// x % f.mod without a divide: q = mulhi(x, floor((2^64-1)/mod)) underestimates x/mod by at most 2.
+// x % f.mod without a divide.  With c = floor((2^64-1)/mod) = (2^64-1-rho)/mod, 0 <= rho < mod:
+//   x*c/2^64 = x/mod - x*(1+rho)/(mod*2^64), and the second term is < 1 (x < 2^64, 1+rho <= mod),
+// so q = mulhi(x, c) is floor(x/mod) or one less: a single conditional subtraction finishes the job.
 NTB_HD uint64_t
 filter_slot(const FilterView& f, uint64_t x)
 {
@@ -197,7 +199,6 @@ filter_slot(const FilterView& f, uint64_t x)
 	}
 	const uint64_t q = mulhi64(x, f.recip);
 	uint64_t r = x - q * f.mod;
-	r -= r >= f.mod ? f.mod : 0ULL;
 	r -= r >= f.mod ? f.mod : 0ULL;
 	return r;
 }

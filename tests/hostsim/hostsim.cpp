@@ -107,11 +107,14 @@ struct HostBackend
 				io.ctr = &ctr;
 				io.rot = rot.data();
 				// the same two instantiations the device kernel dispatches between
-				if (!kp.counting && !kp.h_rep && !kp.snv && !kp.mask) {
-					Walker<352, true> w(*st, kp);
+				if (!kp.counting && !kp.h_rep && !kp.snv && !kp.mask && bloom.mask != 0) {
+					Walker<352, true, true> w(*st, kp);
+					w.run(tasks[i], results[i]);
+				} else if (!kp.counting && !kp.h_rep && !kp.snv && !kp.mask) {
+					Walker<352, true, false> w(*st, kp);
 					w.run(tasks[i], results[i]);
 				} else {
-					Walker<352, false> w(*st, kp);
+					Walker<352, false, false> w(*st, kp);
 					w.run(tasks[i], results[i]);
 				}
 			}
