@@ -179,3 +179,18 @@ def test_make_bf_cli_builds_the_filter_the_oracle_builds(nb, oracle, tmp_path):
     of.free()
     of2.free()
     want.free()
+
+
+def test_cli_shards_batches_over_two_gpus(nb, oracle, tmp_path):
+    """--gpus 2: batches of contigs go round-robin to two devices, each with its own replica of the filter; the output
+    is still in input order and bit-exact.  Skipped on a one-GPU box."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    if not oracle.have_ref():
+        pytest.skip("oracle/_ref/ntedit_ref not present")
+    inp = tc.make_inputs(606, ncontigs=7, n=12000)
+    dpath, fpath, _ = write_inputs(nb, tmp_path, inp)
+    got = run_cli(dpath, fpath, str(tmp_path / "ours"), extra=("-m", 1, "--gpus", 2, "--batch_bases", 20000))
+    rfa, rtsv, rvcf = oracle.run_ref(dpath, fpath, workdir=str(tmp_path), extra=("-m", 1))
+    assert got[0] == rfa and got[1] == rtsv and strip_date(got[2]) == strip_date(rvcf)
