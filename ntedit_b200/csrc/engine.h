@@ -260,6 +260,7 @@ struct WalkerState
 	uint32_t last_event, n_events, n_sites, first_touch, status;
 
 	// main-loop control (decided by the leader, read by every lane)
+	uint32_t t_start, t_end; // the task's borders after safe_boundary()
 	uint32_t end_pos;
 	uint32_t act;
 	uint32_t visit_hit;
@@ -2103,6 +2104,53 @@ struct Walker
 		S.t.ni -= lo;
 	}
 
+	// last flagged position (K1 visit bit) in [lo, hi) of the contig, NONE32 if there is none
+	NTB_FN uint32_t last_flag_in(uint32_t lo, uint32_t hi) const
+	{
+		if (lo >= hi) {
+			return NONE32;
+		}
+		const uint64_t g0 = S.io.goff + lo, g1 = S.io.goff + hi;
+		for (uint64_t w = (g1 - 1) >> 5;; w--) {
+			uint32_t bits = S.io.visit[w];
+			if (w == ((g1 - 1) >> 5) && (g1 & 31)) {
+				bits &= (1u << (g1 & 31)) - 1u;
+			}
+			if (w == (g0 >> 5)) {
+				bits &= 0xFFFFFFFFu << (g0 & 31);
+			}
+			if (bits) {
+				uint32_t top = 31;
+				while (!((bits >> top) & 1u)) {
+					top--;
+				}
+				return (uint32_t)((w << 5) + top - S.io.goff);
+			}
+			if (w == (g0 >> 5)) {
+				return NONE32;
+			}
+		}
+	}
+
+	// Segment borders are nominal (multiples of the segment length).  A border in the middle of a run of flagged positions
+	// makes the successor start inside its predecessor's dirty stretch, and the stitcher then has to run it again.  Both
+	// neighbours therefore move the border -- each on its own, by the same rule on the same bitmap -- to the first position
+	// p >= b (at most boundary_lim further) with no flagged position in [p - W, p), W = 2k + 16: the predecessor is then
+	// clean again before p.  (Only a hint: the stitcher still validates every result.)
+	NTB_FN uint32_t safe_boundary(uint32_t b) const
+	{
+		const uint32_t W = 2 * P.k + 16;
+		uint32_t p = b;
+		while (p <= b + P.boundary_lim && p < S.io.len) {
+			const uint32_t q = last_flag_in(p >= W ? p - W : 0, p);
+			if (q == NONE32) {
+				return p;
+			}
+			p = q + W + 1;
+		}
+		return b;
+	}
+
 	// ---------------------------------------------------------------- the main loop, ntedit.cpp:1797-2139
 	// leader: start of a task
 	NTB_FN void task_begin(const Task& task)
@@ -2135,6 +2183,8 @@ struct Walker
 		S.la_bits = 0;
 		S.act = ACT_CLEAN;
 		S.h.ni = S.t.ni = 0;
+		S.t_start = (P.boundary_lim && (task.flags & TASK_ADJUST_START)) ? safe_boundary(task.start) : task.start;
+		S.t_end = (P.boundary_lim && (task.flags & TASK_ADJUST_END)) ? safe_boundary(task.end) : task.end;
 		for (unsigned c = 0; c < 8; c++) {
 			S.seed_tab[c] = c < 4 ? seed_of_code(c) : 0;
 			S.rotk_tab[c] = c < 4 ? P.seed_rot_k[c] : 0;
@@ -2150,8 +2200,8 @@ struct Walker
 				S.t.pos = h0 + k - 1;
 			}
 		} else {
-			S.t.pos = task.start;
-			S.h.pos = task.start + 1 - k;
+			S.t.pos = S.t_start;
+			S.h.pos = S.t_start + 1 - k;
 		}
 		if (S.act != ACT_STOP) {
 			reset_rope(S.h.pos);
@@ -2175,7 +2225,7 @@ struct Walker
 			reset_rope(S.h.pos);
 			S.anchored = true;
 			S.la_n = 0;
-			if (S.t.pos >= task.end) {
+			if (S.t.pos >= S.t_end) {
 				S.end_pos = S.t.pos;
 				S.act = ACT_STOP;
 				return;
@@ -2330,11 +2380,11 @@ struct Walker
 			return false;
 		}
 		if (S.act == ACT_CLEAN) {
-			const uint32_t nv = next_visit(S.t.pos, task.end);
+			const uint32_t nv = next_visit(S.t.pos, S.t_end);
 			NTB_PROF(1);
 			NTB_LEADER_BEGIN
 			if (nv == NONE32) {
-				S.end_pos = task.end;
+				S.end_pos = S.t_end;
 				S.act = ACT_STOP;
 			} else {
 				S.do_seed = nv != S.t.pos || S.need_seed;
@@ -2452,6 +2502,7 @@ struct Walker
 		res.stale[2] = S.stale_alt2;
 		res.stale[3] = S.stale_alt3;
 		res.kcycles = 0;
+		res.start_pos = S.t_start;
 		NTB_LEADER_END
 	}
 

@@ -45,6 +45,8 @@ struct KParams
 	uint32_t insertion_cap;
 	uint32_t min_threshold, max_threshold;
 	uint32_t counting;
+	uint32_t boundary_lim;   // first-round tasks may move their borders forward by up to this many positions (0 = never), see
+	                         // engine.h: safe_boundary()
 	// pre-rotated seeds: srol^(k)(S[c]) and srol^(k-1)(S[c]) for the 4 bases (index: A C G T)
 	uint64_t seed_rot_k[4];
 	uint64_t seed_rot_k1[4];
@@ -63,6 +65,8 @@ struct Task
 	uint32_t pad_;
 };
 constexpr uint32_t TASK_CONTIG_START = 1u;
+constexpr uint32_t TASK_ADJUST_START = 2u; // `start` is a nominal border: begin at safe_boundary(start)
+constexpr uint32_t TASK_ADJUST_END = 4u;   // `end` is a nominal border: the successor begins at safe_boundary(end)
 
 // What a walker reports besides its events.
 struct TaskResult
@@ -77,6 +81,7 @@ struct TaskResult
 	uint32_t status;
 	uint8_t stale[4];      // values of the reference's uninitialised locals after the walker's last site (see STALE_REF)
 	uint32_t kcycles;      // SM clock cycles / 1024 the walker ran for (diagnostics)
+	uint32_t start_pos;    // the tail position the walker actually began at (== task.start unless TASK_ADJUST_START moved it)
 };
 constexpr uint32_t ST_DONE = 1u;          // finished normally
 constexpr uint32_t ST_CONTIG_END = 2u;    // the reference's main loop ended (roll failed / guard): nothing after this walker counts

@@ -136,7 +136,7 @@ struct Segment
 
 template<class Backend>
 int
-polish_run(Backend& be, const KParams& kp, const ntb_params& up, char* host_bases, const uint64_t* offsets, uint64_t n_contigs,
+polish_run(Backend& be, const KParams& kp_in, const ntb_params& up, char* host_bases, const uint64_t* offsets, uint64_t n_contigs,
            ResultImpl& out, std::string& err)
 {
 	using clk = std::chrono::steady_clock;
@@ -145,10 +145,14 @@ polish_run(Backend& be, const KParams& kp, const ntb_params& up, char* host_base
 	auto since = [&](clk::time_point t) { return std::chrono::duration<double, std::milli>(clk::now() - t).count(); };
 	out.contigs.assign(n_contigs, ContigResult());
 	std::memset(&out.stats, 0, sizeof out.stats);
+	KParams kp = kp_in;
 	uint32_t seg_len = up.segment_len ? up.segment_len : (kp.snv ? 1024u : 4096u);
 	if (seg_len < 4 * kp.k) {
 		seg_len = 4 * kp.k;
 	}
+
+	// first-round walkers may move their segment borders out of runs of flagged positions (engine.h: safe_boundary)
+	kp.boundary_lim = std::getenv("NTB_NO_BORDER_ADJUST") ? 0u : std::min<uint32_t>(512u, seg_len / 2);
 
 	// K1 runs while the host cuts the contigs into segments
 	be.scan_begin(kp);
@@ -238,6 +242,7 @@ polish_run(Backend& be, const KParams& kp, const ntb_params& up, char* host_base
 			err = be.error();
 			return NTB_ENOMEM;
 		}
+		const bool first_round = out.stats.rounds == 0;
 		{
 			const uint64_t n_pending = pending.size();
 			const uint64_t chunk = 16384;
@@ -252,6 +257,10 @@ polish_run(Backend& be, const KParams& kp, const ntb_params& up, char* host_base
 					t.end = sg.p1;
 					t.contig = sg.contig;
 					t.flags = (sg.p0 == 0 && sg.run_start == 0) ? TASK_CONTIG_START : 0;
+					if (first_round) {
+						// nominal borders: both neighbours move them by the same rule
+						t.flags |= (sg.p0 > 0 ? TASK_ADJUST_START : 0u) | (sg.p1 < t.len ? TASK_ADJUST_END : 0u);
+					}
 					t.pad_ = 0;
 				}
 			});
@@ -299,6 +308,11 @@ polish_run(Backend& be, const KParams& kp, const ntb_params& up, char* host_base
 					Segment& sg = segs[pending[i]];
 					sg.res = results[i];
 					sg.arena = arena_idx;
+					if (first_round && kp.boundary_lim && sg.p0 > 0) {
+						// the border this walker (and its predecessor) actually used; round 1 holds every segment, in order
+						sg.p0 = sg.run_start = sg.res.start_pos;
+						segs[pending[i] - 1].p1 = sg.res.start_pos;
+					}
 					if (sg.res.status & ST_ROPE_OVERFLOW) {
 						bad = 1;
 					} else if (!(sg.res.status & ST_DONE) || (sg.res.status & ST_EV_OVERFLOW)) {
