@@ -410,7 +410,12 @@ def main():
             "config": config,
             "e2e": {"value": world * bases * n_e2e / e2e_max, "unit": "bases/s", "h2d_bytes_per_step": int(offs[-1]),
                     "d2h_bytes_per_step": d2h, "steps": n_e2e,
-                    "note": "ntb_polish_batch on pinned host memory; working copy restored between steps outside the timed region"},
+                    "note": "ntb_polish_batch on pinned host memory; working copy restored between steps outside the timed region",
+                    "breakdown_ms": {"wall": 1000.0 * e2e_max / n_e2e,
+                                     "h2d_stream": float(np.mean([s["ms_h2d"] for s in e2e_stats])),
+                                     "scan_stage_incl_upload_waits": float(np.mean([s["ms_scan"] for s in e2e_stats])),
+                                     "walk_kernel": float(np.mean([s["ms_walk"] for s in e2e_stats])),
+                                     "host_stitch_replay": float(np.mean([s["ms_host"] for s in e2e_stats]))}},
             "gpu_launches": int(sum(s["kernel_launches"] for s in stats)),
             "clocks": clocks,
             # the HBM-bound stage of the path: K1b = bin_kernel<3,false> + probe_bin_kernel<false>, one pair per text chunk;

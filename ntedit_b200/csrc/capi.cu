@@ -93,6 +93,7 @@ struct ntb_filter
 struct ntb_batch
 {
 	uint8_t* d_alloc = nullptr; // SCAN_HALO zero bytes, the text, zero padding to whole scan tiles
+	bool owns_text = true;      // false: d_alloc is the calling workspace's cached text buffer (ntb_polish_batch)
 	uint8_t* d_text = nullptr;  // d_alloc + SCAN_HALO
 	uint64_t total = 0;         // bytes of text (including the NUL separators)
 	uint64_t n_tiles = 0;
@@ -153,17 +154,34 @@ struct ntb_result
 
 namespace {
 
+// bytes of device memory a batch of `total` text bytes needs (halo in front, zero padding to whole scan tiles behind)
+uint64_t
+batch_device_bytes(uint64_t total)
+{
+	return SCAN_HALO + (total + SCAN_TILE - 1) / SCAN_TILE * SCAN_TILE + 64;
+}
+
+// lays the batch out in `mem` (batch_device_bytes(total) bytes) and zeroes halo and padding on `stream`
 int
-batch_alloc(ntb_batch* b, uint64_t total, cudaStream_t stream = 0)
+batch_bind(ntb_batch* b, uint64_t total, uint8_t* mem, bool owned, cudaStream_t stream)
 {
 	b->total = total;
 	b->n_tiles = (total + SCAN_TILE - 1) / SCAN_TILE;
 	const uint64_t padded = b->n_tiles * SCAN_TILE;
-	NTB_CUDA(cudaMalloc((void**)&b->d_alloc, SCAN_HALO + padded + 64));
+	b->d_alloc = mem;
+	b->owns_text = owned;
 	b->d_text = b->d_alloc + SCAN_HALO;
 	NTB_CUDA(cudaMemsetAsync(b->d_alloc, 0, SCAN_HALO, stream));
 	NTB_CUDA(cudaMemsetAsync(b->d_text + total, 0, padded - total + 64, stream));
 	return NTB_OK;
+}
+
+int
+batch_alloc(ntb_batch* b, uint64_t total, cudaStream_t stream = 0)
+{
+	uint8_t* mem = nullptr;
+	NTB_CUDA(cudaMalloc((void**)&mem, batch_device_bytes(total)));
+	return batch_bind(b, total, mem, true, stream);
 }
 
 int
@@ -217,6 +235,8 @@ struct Workspace
 	Event* d_events_sorted = nullptr; // the same events, grouped by walker (compact_events_kernel)
 	size_t cap_events = 0;
 	Counters* d_ctr = nullptr;
+	uint8_t* d_text = nullptr;     // text buffer of streamed batches (cudaMalloc / cudaFree of GBs per call can stall for 100s of ms)
+	size_t cap_text = 0;
 	uint64_t* d_records = nullptr; // K1b: probe records, n_buckets x bucket_cap
 	size_t cap_records = 0;
 	uint32_t* d_cursor = nullptr;  // K1b: BIN_MAX_BUCKETS record counters + the probe kernel's pacing counter
@@ -240,6 +260,7 @@ struct Workspace
 		cudaFree(d_ctr);
 		cudaFree(d_records);
 		cudaFree(d_cursor);
+		cudaFree(d_text);
 		cudaFreeHost(h_tasks);
 		cudaFreeHost(h_results);
 		cudaFreeHost(h_events);
@@ -347,6 +368,25 @@ struct CudaBackend
 			NTB_BE(cudaEventCreate(&ws->ev1));
 			NTB_BE(cudaMalloc((void**)&ws->d_ctr, sizeof(Counters)));
 			NTB_BE(cudaHostAlloc((void**)&ws->h_ctr, sizeof(Counters), cudaHostAllocDefault));
+		}
+		if (batch->up_src && !batch->d_alloc) {
+			// a streamed batch lives in the workspace's cached text buffer
+			const uint64_t need = batch_device_bytes(batch->total);
+			if (need > ws->cap_text) {
+				cudaFree(ws->d_text);
+				ws->d_text = nullptr;
+				ws->cap_text = 0;
+				NTB_BE(cudaMalloc((void**)&ws->d_text, need + need / 16));
+				ws->cap_text = need + need / 16;
+			}
+			if (batch_bind(batch, batch->total, ws->d_text, false, batch->up_stream) != NTB_OK) {
+				err = g_error;
+				return rc = NTB_ECUDA;
+			}
+			NTB_BE(cudaEventRecord(batch->up_begin, batch->up_stream));
+			if (batch->total == 0) {
+				NTB_BE(cudaEventRecord(batch->up_end, batch->up_stream));
+			}
 		}
 		const size_t words = batch->n_tiles * SCAN_BITWORDS + 16;
 		if (words > ws->cap_visit) {
@@ -1204,16 +1244,10 @@ batch_upload_streamed(const char* bases, const uint64_t* offsets, uint64_t n_con
 		ntb_batch_free(b);
 		return cuda_fail(e, "cudaStreamCreate(upload)");
 	}
-	rc = batch_alloc(b, offsets[n_contigs], b->up_stream);
-	if (rc != NTB_OK) {
-		ntb_batch_free(b);
-		return rc;
-	}
+	// the device buffer is bound when the polishing call checks its workspace out (CudaBackend::init)
+	b->total = offsets[n_contigs];
+	b->n_tiles = (b->total + SCAN_TILE - 1) / SCAN_TILE;
 	b->up_src = bases;
-	cudaEventRecord(b->up_begin, b->up_stream);
-	if (b->total == 0) {
-		cudaEventRecord(b->up_end, b->up_stream);
-	}
 	*out = b;
 	return NTB_OK;
 }
@@ -1284,7 +1318,7 @@ ntb_batch_free(ntb_batch* b)
 	if (b->up_stream) {
 		cudaStreamDestroy(b->up_stream);
 	}
-	if (b->d_alloc) {
+	if (b->d_alloc && b->owns_text) {
 		cudaFree(b->d_alloc);
 	}
 	delete b;

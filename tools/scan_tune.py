@@ -42,6 +42,25 @@ def main():
             res.free()
             out.append(st)
         st = out[-1]
+        if os.environ.get("NTB_TUNE_E2E"):
+            import time
+            host = torch.empty(len(buf), dtype=torch.uint8, pin_memory=True)
+            work = torch.empty(len(buf), dtype=torch.uint8, pin_memory=True)
+            host.copy_(buf)
+            torch.cuda.synchronize()
+            for _ in range(3):
+                work.copy_(host)
+                torch.cuda.synchronize()
+                t1 = time.perf_counter()
+                res = nb.kmerize_and_correct(work.numpy(), offs, bloom, params)
+                t2 = time.perf_counter()
+                d = res.stats().as_dict()
+                t3 = time.perf_counter()
+                res.free()
+                t4 = time.perf_counter()
+                print(json.dumps({"e2e_call_ms": round(1000 * (t2 - t1), 1), "free_ms": round(1000 * (t4 - t3), 1),
+                                  "h2d": round(d["ms_h2d"], 1), "scan": round(d["ms_scan"], 1), "walk": round(d["ms_walk"], 1),
+                                  "host": round(d["ms_host"], 1), "d2h": round(d["ms_d2h"], 1)}), flush=True)
         print(json.dumps({"env": cfg, "ms_scan": [round(o["ms_scan"], 2) for o in out], "ms_walk": round(st["ms_walk"], 2),
                           "launches": st["kernel_launches"], "sites": st["sites"], "edits": st["edits"]}), flush=True)
 
