@@ -513,7 +513,7 @@ struct CudaBackend
 				NTB_BE(cudaStreamWaitEvent(ws->stream, ws->ev_probe[buf], 0)); // the buffer's previous chunk has been probed
 			}
 			NTB_BE(cudaMemsetAsync(A.cursor, 0, (BIN_MAX_BUCKETS + 1) * sizeof(uint32_t), ws->stream));
-			NTB_BE(launch_bin(A, bloom->counting != 0, (int)std::min<uint64_t>(nt, (uint64_t)sms * 2), ws->stream));
+			NTB_BE(launch_bin(A, bloom->counting != 0, (int)std::min<uint64_t>(nt, (uint64_t)sms * BIN_CTAS_PER_SM), ws->stream));
 			NTB_BE(cudaEventRecord(ws->ev_bin[buf], ws->stream));
 			NTB_BE(cudaStreamWaitEvent(s_probe, ws->ev_bin[buf], 0));
 			NTB_BE(launch_probe_bin(A, bloom->counting != 0, probe_ctas, s_probe));

@@ -353,14 +353,14 @@ probe_misses(const uint8_t* data, uint64_t slot, uint32_t thr)
 }
 
 template<int H, bool COUNTING>
-__global__ void __launch_bounds__(SCAN_THREADS, 2)
+__global__ void __launch_bounds__(SCAN_THREADS, BIN_CTAS_PER_SM)
 bin_kernel(const __grid_constant__ BinArgs A)
 {
 	const ScanArgs& a = A.scan;
 	constexpr int RR = SCAN_THREADS * BIN_POS_PER_ROUND * H; // records a round can produce
 	extern __shared__ __align__(128) uint8_t smem[];
-	uint8_t* stage_buf = smem;                                                // SCAN_STAGES * SCAN_STAGE_BYTES
-	uint64_t* sorted = (uint64_t*)(smem + SCAN_STAGES * SCAN_STAGE_BYTES);    // the round's records, grouped by bucket
+	uint8_t* stage_buf = smem;                                                // BIN_STAGES * SCAN_STAGE_BYTES
+	uint64_t* sorted = (uint64_t*)(smem + BIN_STAGES * SCAN_STAGE_BYTES);    // the round's records, grouped by bucket
 	uint16_t* sorted_b = (uint16_t*)(sorted + RR);                            // their buckets
 	uint32_t* cnt = (uint32_t*)(sorted_b + RR);                               // per bucket: records of this round
 	uint32_t* off = cnt + BIN_MAX_BUCKETS;                                    // per bucket: start inside sorted[]
@@ -368,7 +368,7 @@ bin_kernel(const __grid_constant__ BinArgs A)
 	uint32_t* wsum = gbase + BIN_MAX_BUCKETS;                                 // [0..8) warp totals, [8] round total
 	uint8_t* cls = (uint8_t*)(wsum + 16);                                     // 256
 	uint64_t* tab = (uint64_t*)(cls + 256);                                   // seed[8], rotk[8]
-	uint64_t* bars = tab + 16;                                                // SCAN_STAGES mbarriers
+	uint64_t* bars = tab + 16;                                                // BIN_STAGES mbarriers
 
 	const int tid = threadIdx.x;
 	const int lane = tid & 31, warp = tid >> 5;
@@ -383,7 +383,7 @@ bin_kernel(const __grid_constant__ BinArgs A)
 		tab[8 + tid] = tid < 5 ? a.rotk[tid] : 0;
 	}
 	if (tid == 0) {
-		for (int s = 0; s < SCAN_STAGES; s++) {
+		for (int s = 0; s < BIN_STAGES; s++) {
 			mbar_init(&bars[s], 1);
 		}
 		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -402,8 +402,8 @@ bin_kernel(const __grid_constant__ BinArgs A)
 	const uint32_t thr = a.min_threshold > 1u ? a.min_threshold : 1u;
 
 	uint64_t tile = blockIdx.x;
-	uint32_t phase[SCAN_STAGES];
-	for (int s = 0; s < SCAN_STAGES; s++) {
+	uint32_t phase[BIN_STAGES];
+	for (int s = 0; s < BIN_STAGES; s++) {
 		phase[s] = 0;
 	}
 	int stage = 0;
@@ -413,7 +413,7 @@ bin_kernel(const __grid_constant__ BinArgs A)
 	}
 	for (; tile < a.n_tiles; tile += gridDim.x) {
 		const uint64_t next = tile + gridDim.x;
-		if (tid == 0 && next < a.n_tiles) {
+		if (BIN_STAGES == 2 && tid == 0 && next < a.n_tiles) {
 			asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 			mbar_expect_tx(&bars[stage ^ 1], SCAN_STAGE_BYTES);
 			bulk_copy_g2s(stage_buf + (stage ^ 1) * SCAN_STAGE_BYTES, a.text + next * SCAN_TILE - SCAN_HALO, SCAN_STAGE_BYTES,
@@ -548,7 +548,14 @@ bin_kernel(const __grid_constant__ BinArgs A)
 			// again after the next round's first barrier, which every thread reaches after finishing (d)
 		}
 		__syncthreads(); // tile consumed: its stage may be refilled
-		stage ^= 1;
+		if (BIN_STAGES == 2) {
+			stage ^= 1;
+		} else if (tid == 0 && next < a.n_tiles) {
+			// one stage: the next tile is fetched now; the other CTAs of the SM cover the wait
+			asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+			mbar_expect_tx(&bars[0], SCAN_STAGE_BYTES);
+			bulk_copy_g2s(stage_buf, a.text + next * SCAN_TILE - SCAN_HALO, SCAN_STAGE_BYTES, &bars[0]);
+		}
 	}
 }
 

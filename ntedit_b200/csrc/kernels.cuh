@@ -63,11 +63,16 @@ cudaError_t launch_scan(const ScanArgs& a, bool counting, bool extra, int grid, 
 constexpr int BIN_POS_PER_ROUND = 4;                             // positions per thread and round (same step as K1)
 constexpr int BIN_MAX_BUCKETS = SCAN_THREADS;                    // one thread per bucket in the per-round scan
 constexpr int BIN_ROUND_RECORDS = SCAN_THREADS * BIN_POS_PER_ROUND * (int)HMAX; // upper bound for the template maximum
+#ifndef NTB_BIN_STAGES
+#define NTB_BIN_STAGES 1
+#endif
+constexpr int BIN_STAGES = NTB_BIN_STAGES;                       // staged text tiles per CTA: 1 leaves room for a third CTA per SM
+constexpr int BIN_CTAS_PER_SM = BIN_STAGES == 1 ? 3 : 2;
 inline size_t
 bin_smem_bytes(int hash_num)
 {
 	const size_t round_records = (size_t)SCAN_THREADS * BIN_POS_PER_ROUND * (size_t)hash_num;
-	return (size_t)SCAN_STAGES * SCAN_STAGE_BYTES + round_records * 8 + round_records * 2 + 3 * BIN_MAX_BUCKETS * 4 + 16 * 4 + 256 + 16 * 8 +
+	return (size_t)BIN_STAGES * SCAN_STAGE_BYTES + round_records * 8 + round_records * 2 + 3 * BIN_MAX_BUCKETS * 4 + 16 * 4 + 256 + 16 * 8 +
 	       SCAN_STAGES * 8 + 64;
 }
 
