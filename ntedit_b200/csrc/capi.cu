@@ -453,7 +453,18 @@ struct CudaBackend
 		// stream evicts the filter region the probe kernel needs in L2, so the two kernels of a chunk run back to back.
 		const uint64_t H = bloom->h;
 		const bool overlap = env_u64("NTB_BIN_OVERLAP", 0) != 0;
-		const uint64_t budget_records = (env_u64("NTB_BIN_SCRATCH_MB", 8192) << 20) / 8 / (overlap ? 2 : 1);
+		// record scratch: fewer, larger chunks amortise the per-bucket pacing of the probe kernel (16 GB: 75 ms, 8 GB: 77 ms,
+		// 4 GB: 94 ms per 3 G positions); never more than a quarter of the memory that is free right now
+		uint64_t scratch_mb = env_u64("NTB_BIN_SCRATCH_MB", 0);
+		if (scratch_mb == 0) {
+			scratch_mb = 16384;
+			size_t free_b = 0, total_b = 0;
+			if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
+				const uint64_t have = ((uint64_t)free_b + (uint64_t)ws->cap_records * 8) >> 20;
+				scratch_mb = std::max<uint64_t>(64, std::min<uint64_t>(scratch_mb, have / 4));
+			}
+		}
+		const uint64_t budget_records = (scratch_mb << 20) / 8 / (overlap ? 2 : 1);
 		uint64_t chunk_tiles = budget_records / (uint64_t)((double)SCAN_TILE * (double)H * 1.06);
 		chunk_tiles = std::max<uint64_t>(1, std::min<uint64_t>(chunk_tiles, batch->n_tiles));
 		chunk_tiles = std::min<uint64_t>(chunk_tiles, (0xFFFFFFFFull / SCAN_TILE) - 1); // record positions are 32-bit
@@ -492,7 +503,7 @@ struct CudaBackend
 		A.n_buckets = nb;
 		A.region_log2 = rl;
 		const int sms = sm_count(batch->device);
-		const int probe_ctas = (int)env_u64("NTB_BIN_PROBE_CTAS_PER_SM", 4);
+		const int probe_ctas = (int)env_u64("NTB_BIN_PROBE_CTAS_PER_SM", 3); // measured: 2 -> 81 ms, 3 -> 77, 4 -> 85, 5 -> 93
 		cudaStream_t s_probe = overlap ? ws->stream2 : ws->stream;
 		NTB_BE(cudaEventRecord(ws->ev0, ws->stream));
 		NTB_BE(cudaMemsetAsync(ws->d_visit, 0, batch->n_tiles * SCAN_BITWORDS * 4, ws->stream));
