@@ -38,9 +38,9 @@ K, H = 25, 3
 SEED = 20261017
 # dram__bytes_read.sum + dram__bytes_write.sum of the scan stage from the committed ncu --set full capture of this command
 # (profiles/): per-chunk bin + probe traffic x chunks; None until captured for the current kernels
-NCU_TRAFFIC_BYTES_PER_STAGE = int((0.349948e9 + 8.048851e9 + 20.377044e9 + 0.508624e9) * 88796 / 9991)
-NCU_TRAFFIC_SOURCE = ("profiles/r01z_ncu_full_bin_probe_walk_summary.csv: (bin_kernel 8.40 GB + probe_bin_kernel 20.89 GB) per "
-                      "9991-tile chunk x 88796/9991 chunks; the direct scan kernel moved 1146 GB for the same work")
+NCU_TRAFFIC_BYTES_PER_STAGE = int((0.688038e9 + 16.137119e9 + 22.335070e9 + 0.884871e9) * 88796 / 19982)
+NCU_TRAFFIC_SOURCE = ("profiles/r01y_ncu_full_bin_probe_summary.csv: (bin_kernel 16.83 GB + probe_bin_kernel 23.22 GB) per "
+                      "19982-tile chunk x 88796/19982 chunks; the direct scan kernel moved 1146 GB for the same work")
 
 WORKLOADS = {
     # name: (total bases, filter bytes, large contigs, small contigs, mode)
