@@ -458,6 +458,14 @@ polish_run(Backend& be, const KParams& kp_in, const ntb_params& up, char* host_b
 		const uint32_t len = (uint32_t)(offsets[c + 1] - offsets[c] - 1);
 		// without a host copy of the bases, substitutions are only reported through the records
 		RopeReplay rp(host_bases ? host_bases + offsets[c] : nullptr, len, kp.k, kp.insertion_cap, kp.snv, kp.mask);
+		{
+			uint64_t n_ev = 0;
+			for (uint64_t a = pc.a0; a < pc.a1; a++) {
+				n_ev += segs[accepted[c][a]].res.n_events;
+			}
+			rp.rope.reserve(n_ev + n_ev / 2 + 8); // an indel adds 2-6 nodes, a substitution none
+			rp.recs.reserve(n_ev + 1);
+		}
 		uint8_t stale[4];
 		std::memcpy(stale, pc.stale, 4);
 		auto resolve = [&stale](uint8_t v) -> uint8_t { return (v & STALE_REF) ? stale[v & 3] : v; };
@@ -491,58 +499,108 @@ polish_run(Backend& be, const KParams& kp_in, const ntb_params& up, char* host_b
 		pc.recs.swap(rp.recs);
 	});
 
-	// (C) per contig: join the pieces' ropes
+	// (C) join the pieces' ropes.  Per contig a short sequential pass patches the position node every cut went through
+	// (it keeps s_pos / num_support of the piece on its left and takes e_pos from the piece on its right) and lays the
+	// pieces out; the bulk copies then run on the whole pool.
 	std::atomic<int> failed(0);
 	std::atomic<uint64_t> n_edits(0);
 	std::string first_error;
 	std::atomic_flag err_lock = ATOMIC_FLAG_INIT;
+	auto report = [&](uint64_t c, const std::string& what) {
+		failed = 1;
+		while (err_lock.test_and_set()) {
+		}
+		if (first_error.empty()) {
+			first_error = "contig " + std::to_string(c) + ": " + what;
+		}
+		err_lock.clear();
+	};
+	struct CopyJob
+	{
+		uint32_t contig, piece;
+		uint64_t src, count, dst; // nodes [src, src + count) of the piece go to dst
+		uint64_t rec_dst;
+	};
+	std::vector<std::vector<CopyJob>> contig_jobs(n_contigs);
 	run_parallel(n_contigs, [&](uint64_t c) {
 		ContigResult& cr = out.contigs[c];
 		if (!cr.polished) {
 			return;
 		}
+		std::vector<Piece>& pcs = pieces[c];
+		size_t used = 0;
 		uint64_t edits = 0;
-		for (size_t q = 0; q < pieces[c].size(); q++) {
-			Piece& pc = pieces[c][q];
-			if (!pc.error.empty()) {
-				failed = 1;
-				while (err_lock.test_and_set()) {
-				}
-				if (first_error.empty()) {
-					first_error = "contig " + std::to_string(c) + ": " + pc.error;
-				}
-				err_lock.clear();
+		for (size_t q = 0; q < pcs.size(); q++) {
+			if (!pcs[q].error.empty()) {
+				report(c, pcs[q].error);
 				return;
 			}
-			edits += pc.edits;
-			if (q == 0) {
-				cr.nodes.swap(pc.nodes);
-				cr.srecs.swap(pc.recs);
-			} else {
-				// drop dead slots behind the rope so far; its last live node is the position node the cut went through
-				while (!cr.nodes.empty() && cr.nodes.back().node_type == -1) {
-					cr.nodes.pop_back();
-				}
-				if (cr.nodes.empty() || cr.nodes.back().node_type != 0 || pc.nodes.empty() || pc.nodes[0].node_type != 0) {
-					failed = 1;
-					while (err_lock.test_and_set()) {
-					}
-					if (first_error.empty()) {
-						first_error = "contig " + std::to_string(c) + ": rope pieces do not join on a position node";
-					}
-					err_lock.clear();
-					return;
-				}
-				cr.nodes.back().e_pos = pc.nodes[0].e_pos; // keeps s_pos / num_support of the node on the left of the cut
-				cr.nodes.insert(cr.nodes.end(), pc.nodes.begin() + 1, pc.nodes.end());
-				cr.srecs.insert(cr.srecs.end(), pc.recs.begin(), pc.recs.end());
-			}
-			if (pc.ended) {
+			edits += pcs[q].edits;
+			used = q + 1;
+			if (pcs[q].ended) {
 				break; // the reference's main loop ended inside this piece: nothing behind it was ever evaluated
 			}
 		}
 		n_edits += edits;
+		if (used == 1) {
+			cr.nodes.swap(pcs[0].nodes);
+			cr.srecs.swap(pcs[0].recs);
+			return;
+		}
+		uint64_t total = 0, total_recs = 0;
+		ntb_node* back = nullptr; // the rope's last live node so far (inside the piece that holds it)
+		for (size_t q = 0; q < used; q++) {
+			Piece& pc = pcs[q];
+			uint64_t len = pc.nodes.size();
+			if (q + 1 < used) {
+				while (len && pc.nodes[len - 1].node_type == -1) {
+					len--; // dead slots behind a piece that is not the last one
+				}
+			}
+			CopyJob job;
+			job.contig = (uint32_t)c;
+			job.piece = (uint32_t)q;
+			job.rec_dst = total_recs;
+			if (q == 0) {
+				job.src = 0;
+				job.count = len;
+			} else {
+				if (!back || back->node_type != 0 || len == 0 || pc.nodes[0].node_type != 0) {
+					report(c, "rope pieces do not join on a position node");
+					return;
+				}
+				back->e_pos = pc.nodes[0].e_pos;
+				job.src = 1;
+				job.count = len - 1;
+			}
+			job.dst = total;
+			total += job.count;
+			total_recs += pc.recs.size();
+			if (job.count) {
+				back = &pc.nodes[job.src + job.count - 1];
+			}
+			contig_jobs[c].push_back(job);
+		}
+		cr.nodes.resize(total);
+		cr.srecs.resize(total_recs);
 	});
+	if (!failed) {
+		std::vector<CopyJob> jobs;
+		for (uint64_t c = 0; c < n_contigs; c++) {
+			jobs.insert(jobs.end(), contig_jobs[c].begin(), contig_jobs[c].end());
+		}
+		run_parallel(jobs.size(), [&](uint64_t j) {
+			const CopyJob& job = jobs[j];
+			const Piece& pc = pieces[job.contig][job.piece];
+			ContigResult& cr = out.contigs[job.contig];
+			if (job.count) {
+				std::memcpy(cr.nodes.data() + job.dst, pc.nodes.data() + job.src, job.count * sizeof(ntb_node));
+			}
+			if (!pc.recs.empty()) {
+				std::memcpy(cr.srecs.data() + job.rec_dst, pc.recs.data(), pc.recs.size() * sizeof(ntb_srec));
+			}
+		});
+	}
 	if (failed) {
 		err = first_error;
 		return NTB_EINTERNAL;
