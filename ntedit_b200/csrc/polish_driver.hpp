@@ -209,9 +209,22 @@ polish_run(Backend& be, const KParams& kp_in, const ntb_params& up, char* host_b
 	}
 
 	// host thread pool helper: fn(i) for i in [0, n_items), dynamically scheduled
+	// host threads of this call: NTB_HOST_THREADS, else the cores of the box divided by the ranks that share it (torchrun
+	// exports LOCAL_WORLD_SIZE) -- every rank replays its own batch at the same time
 	unsigned nthreads = std::thread::hardware_concurrency();
 	if (nthreads == 0) {
 		nthreads = 4;
+	}
+	if (const char* v = std::getenv("NTB_HOST_THREADS")) {
+		const long n = std::strtol(v, nullptr, 10);
+		if (n > 0) {
+			nthreads = (unsigned)n;
+		}
+	} else if (const char* w = std::getenv("LOCAL_WORLD_SIZE")) {
+		const long n = std::strtol(w, nullptr, 10);
+		if (n > 1) {
+			nthreads = std::max<unsigned>(2, nthreads / (unsigned)n);
+		}
 	}
 	auto run_parallel = [&](uint64_t n_items, const std::function<void(uint64_t)>& fn) {
 		std::atomic<uint64_t> next(0);
