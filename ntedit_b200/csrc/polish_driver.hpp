@@ -228,16 +228,22 @@ polish_run(Backend& be, const KParams& kp_in, const ntb_params& up, char* host_b
 	}
 	auto run_parallel = [&](uint64_t n_items, const std::function<void(uint64_t)>& fn) {
 		std::atomic<uint64_t> next(0);
+		const unsigned nt = (unsigned)std::min<uint64_t>(nthreads, std::max<uint64_t>(1, n_items));
+		// items are handed out in runs: with hundreds of thousands of tiny contigs a shared counter bumped once per item
+		// costs more than the items themselves
+		const uint64_t grain = std::max<uint64_t>(1, std::min<uint64_t>(1024, n_items / ((uint64_t)nt * 32)));
 		auto worker = [&]() {
 			for (;;) {
-				const uint64_t i = next.fetch_add(1);
-				if (i >= n_items) {
+				const uint64_t i0 = next.fetch_add(grain);
+				if (i0 >= n_items) {
 					break;
 				}
-				fn(i);
+				const uint64_t i1 = std::min<uint64_t>(n_items, i0 + grain);
+				for (uint64_t i = i0; i < i1; i++) {
+					fn(i);
+				}
 			}
 		};
-		const unsigned nt = (unsigned)std::min<uint64_t>(nthreads, std::max<uint64_t>(1, n_items));
 		if (nt <= 1) {
 			worker();
 			return;
