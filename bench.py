@@ -402,7 +402,7 @@ def main():
         alg_bytes = (1 + 32 * H) * positions
         achieved = alg_bytes / (ms_scan * 1e-3) / 1e9
         ev_bytes = 36
-        d2h = int(np.mean([s["edits"] for s in e2e_stats]) * ev_bytes) + 28 * int(e2e_stats[0]["segments"])
+        d2h = int(np.mean([s["edits"] for s in e2e_stats]) * ev_bytes) + 36 * int(e2e_stats[0]["segments"])
         line = {
             "metric": "bases polished/sec", "value": world * bases * args.steps / dt_max, "unit": "bases/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * dt_max / args.steps,
