@@ -396,6 +396,9 @@ polish_run(Backend& be, const KParams& kp_in, const ntb_params& up, char* host_b
 			pending.insert(pending.end(), redo[c].begin(), redo[c].end());
 		}
 		host_ms += std::chrono::duration<double, std::milli>(clk::now() - t0).count();
+		if (dbg) {
+			std::fprintf(stderr, "[ntb] host:   take-over + stitch pass %.1f ms, %zu to re-run\n", since(t0), pending.size());
+		}
 		if (out.stats.rounds > 64) {
 			err = "stitcher did not converge";
 			return NTB_EINTERNAL;
@@ -423,7 +426,9 @@ polish_run(Backend& be, const KParams& kp_in, const ntb_params& up, char* host_b
 		uint64_t edits = 0;
 		std::string error;
 	};
-	// (A) per contig: the accepted results in order, the stale bytes each one starts with, and the cuts
+	// (A) per contig: the accepted results in order, the stale bytes each one starts with, and the cuts.  Flat arrays
+	// indexed like `segs` (contig c owns [first_seg[c], first_seg[c+1])): no per-contig allocation -- a conifer-like
+	// draft has millions of contigs.
 	uint64_t total_events = 0;
 	for (uint64_t i = 0; i < segs.size(); i++) {
 		total_events += segs[i].res.n_events;
@@ -432,38 +437,33 @@ polish_run(Backend& be, const KParams& kp_in, const ntb_params& up, char* host_b
 	if (const char* v = std::getenv("NTB_REPLAY_PIECE_EVENTS")) { // testing aid: tiny pieces put a cut behind (almost) every result
 		piece_events = std::max<uint64_t>(1, std::strtoull(v, nullptr, 10));
 	}
-	std::vector<std::vector<uint64_t>> accepted(n_contigs);       // segment indices
-	std::vector<std::vector<Piece>> pieces(n_contigs);
+	std::vector<uint64_t> acc(segs.size());        // accepted segment indices
+	std::vector<uint32_t> acc_n(n_contigs, 0);     // how many of contig c's slots are used
+	std::vector<uint8_t> acc_cut(segs.size(), 0);  // a new piece starts at this accepted result
+	std::vector<uint32_t> acc_stale(segs.size());  // the four stale bytes at the start of this accepted result
 	run_parallel(n_contigs, [&](uint64_t c) {
 		if (!out.contigs[c].polished) {
 			return;
 		}
-		std::vector<uint64_t>& acc = accepted[c];
-		std::vector<Piece>& pc = pieces[c];
+		const uint64_t base = first_seg[c];
+		uint32_t n = 0;
 		uint32_t prev_end = 0;
 		uint8_t stale[4] = { 0, 0, 0, 0 };
 		auto resolve = [&stale](uint8_t v) -> uint8_t { return (v & STALE_REF) ? stale[v & 3] : v; };
 		uint64_t in_piece = 0;
-		auto open_piece = [&]() {
-			Piece p;
-			p.contig = (uint32_t)c;
-			p.a0 = p.a1 = acc.size();
-			std::memcpy(p.stale, stale, 4);
-			pc.push_back(std::move(p));
-			in_piece = 0;
-		};
-		open_piece();
 		for (uint64_t i = first_seg[c]; i < first_seg[c + 1]; i++) {
 			const Segment& sg = segs[i];
 			const uint32_t need = std::max(prev_end, sg.p0);
 			if (need >= sg.p1) {
 				continue;
 			}
-			if (in_piece >= piece_events) {
-				open_piece();
+			if (n > 0 && in_piece >= piece_events) {
+				acc_cut[base + n] = 1;
+				in_piece = 0;
 			}
-			acc.push_back(i);
-			pc.back().a1 = acc.size();
+			acc[base + n] = i;
+			std::memcpy(&acc_stale[base + n], stale, 4);
+			n++;
 			in_piece += sg.res.n_events + 1;
 			const uint8_t next_stale[4] = { resolve(sg.res.stale[0]), resolve(sg.res.stale[1]), resolve(sg.res.stale[2]),
 				                            resolve(sg.res.stale[3]) };
@@ -473,34 +473,72 @@ polish_run(Backend& be, const KParams& kp_in, const ntb_params& up, char* host_b
 				break;
 			}
 		}
+		acc_n[c] = n;
 	});
-
-	// (B) every piece on its own
-	std::vector<std::pair<uint32_t, uint32_t>> work; // (contig, piece)
+	// the pieces, contig by contig (every polished contig has at least one, possibly without any result)
+	std::vector<uint64_t> piece_first(n_contigs + 1, 0);
 	for (uint64_t c = 0; c < n_contigs; c++) {
-		for (size_t q = 0; q < pieces[c].size(); q++) {
-			work.emplace_back((uint32_t)c, (uint32_t)q);
-		}
-	}
-	run_parallel(work.size(), [&](uint64_t w) {
-		const uint64_t c = work[w].first;
-		Piece& pc = pieces[c][work[w].second];
-		const uint32_t len = (uint32_t)(offsets[c + 1] - offsets[c] - 1);
-		// without a host copy of the bases, substitutions are only reported through the records
-		RopeReplay rp(host_bases ? host_bases + offsets[c] : nullptr, len, kp.k, kp.insertion_cap, kp.snv, kp.mask);
-		{
-			uint64_t n_ev = 0;
-			for (uint64_t a = pc.a0; a < pc.a1; a++) {
-				n_ev += segs[accepted[c][a]].res.n_events;
+		uint64_t n = 0;
+		if (out.contigs[c].polished) {
+			n = 1;
+			for (uint64_t a = first_seg[c] + 1; a < first_seg[c] + acc_n[c]; a++) {
+				n += acc_cut[a];
 			}
-			rp.rope.reserve(n_ev + n_ev / 2 + 8); // an indel adds 2-6 nodes, a substitution none
-			rp.recs.reserve(n_ev + 1);
 		}
+		piece_first[c + 1] = piece_first[c] + n;
+	}
+	std::vector<Piece> pieces(piece_first[n_contigs]);
+	run_parallel(n_contigs, [&](uint64_t c) {
+		if (!out.contigs[c].polished) {
+			return;
+		}
+		const uint64_t base = first_seg[c];
+		uint64_t a0 = base, w = piece_first[c];
+		for (uint64_t a = base; a <= base + acc_n[c]; a++) {
+			if (a == base + acc_n[c] || (a > base && acc_cut[a])) {
+				Piece& p = pieces[w++];
+				p.contig = (uint32_t)c;
+				p.a0 = a0;
+				p.a1 = a;
+				std::memset(p.stale, 0, 4);
+				if (a0 < base + acc_n[c]) {
+					std::memcpy(p.stale, &acc_stale[a0], 4);
+				}
+				a0 = a;
+			}
+		}
+	});
+	if (dbg) {
+		std::fprintf(stderr, "[ntb] host:   replay (A) accept + cut %.1f ms\n", since(t1));
+	}
+	const auto t_b = clk::now();
+	// (B) every piece on its own
+	run_parallel(pieces.size(), [&](uint64_t w) {
+		Piece& pc = pieces[w];
+		const uint64_t c = pc.contig;
+		const uint32_t len = (uint32_t)(offsets[c + 1] - offsets[c] - 1);
+		uint64_t n_ev = 0;
+		for (uint64_t a = pc.a0; a < pc.a1; a++) {
+			n_ev += segs[acc[a]].res.n_events;
+		}
+		if (n_ev == 0) {
+			// nothing happened here: the piece's rope is its root node (most contigs of a fragmented draft)
+			ntb_node root;
+			std::memset(&root, 0, sizeof root);
+			root.node_type = 0;
+			root.s_pos = 0;
+			root.e_pos = len - 1;
+			pc.nodes.assign(1, root);
+			return;
+		}
+		// without a host copy of the bases, substitutions are only reported through the records
+		RopeReplay rp(host_bases ? host_bases + offsets[c] : nullptr, len, kp.k, kp.insertion_cap, kp.snv, kp.mask,
+		              n_ev + n_ev / 2 + 8, n_ev + 1); // an indel adds 2-6 nodes, a substitution none
 		uint8_t stale[4];
 		std::memcpy(stale, pc.stale, 4);
 		auto resolve = [&stale](uint8_t v) -> uint8_t { return (v & STALE_REF) ? stale[v & 3] : v; };
 		for (uint64_t a = pc.a0; a < pc.a1 && !rp.ended; a++) {
-			const Segment& sg = segs[accepted[c][a]];
+			const Segment& sg = segs[acc[a]];
 			// the backend hands every walker's events over as one contiguous run, first event first
 			const Event* run = sg.res.n_events ? arenas[(size_t)sg.arena] + sg.res.last_event : nullptr;
 			for (uint32_t q = 0; q < sg.res.n_events; q++) {
@@ -528,7 +566,10 @@ polish_run(Backend& be, const KParams& kp_in, const ntb_params& up, char* host_b
 		pc.nodes.swap(rp.rope);
 		pc.recs.swap(rp.recs);
 	});
-
+	if (dbg) {
+		std::fprintf(stderr, "[ntb] host:   replay (B) %zu pieces %.1f ms\n", pieces.size(), since(t_b));
+	}
+	const auto t_c = clk::now();
 	// (C) join the pieces' ropes.  Per contig a short sequential pass patches the position node every cut went through
 	// (it keeps s_pos / num_support of the piece on its left and takes e_pos from the piece on its right) and lays the
 	// pieces out; the bulk copies then run on the whole pool.
@@ -547,51 +588,53 @@ polish_run(Backend& be, const KParams& kp_in, const ntb_params& up, char* host_b
 	};
 	struct CopyJob
 	{
-		uint32_t contig, piece;
+		uint64_t piece;
 		uint64_t src, count, dst; // nodes [src, src + count) of the piece go to dst
 		uint64_t rec_dst;
 	};
-	std::vector<std::vector<CopyJob>> contig_jobs(n_contigs);
+	std::vector<CopyJob> jobs(pieces.size()); // slot w belongs to piece w; count == ~0 marks "no copy"
+	for (CopyJob& j : jobs) {
+		j.piece = ~0ULL;
+	}
 	run_parallel(n_contigs, [&](uint64_t c) {
 		ContigResult& cr = out.contigs[c];
 		if (!cr.polished) {
 			return;
 		}
-		std::vector<Piece>& pcs = pieces[c];
-		size_t used = 0;
+		const uint64_t p0 = piece_first[c], p1 = piece_first[c + 1];
+		uint64_t used = 0;
 		uint64_t edits = 0;
-		for (size_t q = 0; q < pcs.size(); q++) {
-			if (!pcs[q].error.empty()) {
-				report(c, pcs[q].error);
+		for (uint64_t q = p0; q < p1; q++) {
+			if (!pieces[q].error.empty()) {
+				report(c, pieces[q].error);
 				return;
 			}
-			edits += pcs[q].edits;
-			used = q + 1;
-			if (pcs[q].ended) {
+			edits += pieces[q].edits;
+			used = q - p0 + 1;
+			if (pieces[q].ended) {
 				break; // the reference's main loop ended inside this piece: nothing behind it was ever evaluated
 			}
 		}
 		n_edits += edits;
 		if (used == 1) {
-			cr.nodes.swap(pcs[0].nodes);
-			cr.srecs.swap(pcs[0].recs);
+			cr.nodes.swap(pieces[p0].nodes);
+			cr.srecs.swap(pieces[p0].recs);
 			return;
 		}
 		uint64_t total = 0, total_recs = 0;
 		ntb_node* back = nullptr; // the rope's last live node so far (inside the piece that holds it)
-		for (size_t q = 0; q < used; q++) {
-			Piece& pc = pcs[q];
+		for (uint64_t q = p0; q < p0 + used; q++) {
+			Piece& pc = pieces[q];
 			uint64_t len = pc.nodes.size();
-			if (q + 1 < used) {
+			if (q + 1 < p0 + used) {
 				while (len && pc.nodes[len - 1].node_type == -1) {
 					len--; // dead slots behind a piece that is not the last one
 				}
 			}
 			CopyJob job;
-			job.contig = (uint32_t)c;
-			job.piece = (uint32_t)q;
+			job.piece = q;
 			job.rec_dst = total_recs;
-			if (q == 0) {
+			if (q == p0) {
 				job.src = 0;
 				job.count = len;
 			} else {
@@ -609,20 +652,19 @@ polish_run(Backend& be, const KParams& kp_in, const ntb_params& up, char* host_b
 			if (job.count) {
 				back = &pc.nodes[job.src + job.count - 1];
 			}
-			contig_jobs[c].push_back(job);
+			jobs[q] = job;
 		}
 		cr.nodes.resize(total);
 		cr.srecs.resize(total_recs);
 	});
 	if (!failed) {
-		std::vector<CopyJob> jobs;
-		for (uint64_t c = 0; c < n_contigs; c++) {
-			jobs.insert(jobs.end(), contig_jobs[c].begin(), contig_jobs[c].end());
-		}
 		run_parallel(jobs.size(), [&](uint64_t j) {
 			const CopyJob& job = jobs[j];
-			const Piece& pc = pieces[job.contig][job.piece];
-			ContigResult& cr = out.contigs[job.contig];
+			if (job.piece == ~0ULL) {
+				return;
+			}
+			const Piece& pc = pieces[job.piece];
+			ContigResult& cr = out.contigs[pc.contig];
 			if (job.count) {
 				std::memcpy(cr.nodes.data() + job.dst, pc.nodes.data() + job.src, job.count * sizeof(ntb_node));
 			}
@@ -634,6 +676,9 @@ polish_run(Backend& be, const KParams& kp_in, const ntb_params& up, char* host_b
 	if (failed) {
 		err = first_error;
 		return NTB_EINTERNAL;
+	}
+	if (dbg) {
+		std::fprintf(stderr, "[ntb] host:   replay (C) join %.1f ms\n", since(t_c));
 	}
 	host_ms += std::chrono::duration<double, std::milli>(clk::now() - t1).count();
 	if (dbg) {

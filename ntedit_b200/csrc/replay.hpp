@@ -15,9 +15,16 @@ namespace ntb {
 class RopeReplay
 {
   public:
-	RopeReplay(char* seq, uint32_t len, uint32_t k, uint32_t insertion_cap, int snv, int mask)
+	RopeReplay(char* seq, uint32_t len, uint32_t k, uint32_t insertion_cap, int snv, int mask, size_t reserve_nodes = 0,
+	           size_t reserve_recs = 0)
 	  : seq_(seq), len_(len), k_(k), cap_(insertion_cap), snv_(snv), mask_(mask)
 	{
+		if (reserve_nodes) {
+			rope.reserve(reserve_nodes);
+		}
+		if (reserve_recs) {
+			recs.reserve(reserve_recs);
+		}
 		ntb_node root;
 		std::memset(&root, 0, sizeof root);
 		root.node_type = 0;
