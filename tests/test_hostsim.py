@@ -98,3 +98,31 @@ def test_piecewise_replay_joins_ropes_exactly(oracle, monkeypatch, name, piece_e
     filt.free()
     if rep:
         rep.free()
+
+
+@pytest.mark.parametrize("piece_events", [None, 3])
+def test_fragmented_draft_of_tiny_contigs(oracle, monkeypatch, piece_events):
+    """Thousands of contigs of 20-600 bp (shorter than k, shorter than -z, event-less, multi-event): the host's flat
+    per-contig bookkeeping (accepted results, pieces, rope joins) against the oracle."""
+    if piece_events:
+        monkeypatch.setenv("NTB_REPLAY_PIECE_EVENTS", str(piece_events))
+    monkeypatch.setenv("NTB_HOST_THREADS", "5")
+    rng = np.random.default_rng(77)
+    k, h = 25, 3
+    truth = synth.random_genome(300_000, rng)
+    filt = oracle.OracleFilter.new(1 << 20, k, h, False)
+    filt.insert_seq(truth.tobytes())
+    draft = synth.mutate(truth, rng, 4e-3, 8e-4, lower_frac=0.01, n_frac=0.002)
+    contigs = []
+    p = 0
+    while p < len(draft):
+        ln = int(rng.integers(20, 600))
+        contigs.append((b"frag%d" % len(contigs), draft[p:p + ln].tobytes()))
+        p += ln
+    assert len(contigs) > 900
+    op = oracle.default_params(k, h, mode=1)
+    ofa, otsv, ovcf = oracle.polish(contigs, filt, op)
+    fa, tsv, vcf, st = run_hostsim(contigs, filt, dict(mode=1))
+    assert fa == ofa and tsv == otsv and vcf == ovcf
+    assert st.edits > 500
+    filt.free()
