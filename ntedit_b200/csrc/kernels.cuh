@@ -1,11 +1,15 @@
 // sm_100a kernels of the ntEdit hot path.
-//   K1 scan_kernel    : ntHash roll over every base + h-way filter probe -> visit bitmap (and, on request, counts / validity)
-//                       replaces the main-loop test + roll of ntedit.cpp:1806-1807, 2118-2138
-//   K2 walk_kernel    : one warp per segment replays the edit state machine (engine.h) at the flagged positions, one
-//                       candidate k-mer series per lane
-//                       replaces ntedit.cpp:1808-2116 (check-missing, substitutions, tryIndels, tryDeletion, makeEdit decisions)
-//   K4 occupancy_kernel : popcount / non-zero count of the filter (btllib get_fpr, printed by ntedit.cpp:387-395)
-//   K5 insert_kernel  : filter construction (src/ntedit_make_genome_bf.cpp:151-156)
+//   K1  scan_kernel       : ntHash roll over every base + h-way filter probe -> visit bitmap (and, on request, counts / validity)
+//                           replaces the main-loop test + roll of ntedit.cpp:1806-1807, 2118-2138; filters that fit L2, -s 1, ntb_scan
+//   K1b bin_kernel + probe_bin_kernel : the same bitmap for filters larger than L2 -- probes become records bucketed by filter
+//                           region, then are served bucket by bucket from the L2-resident region (a direct probe costs a 128-byte
+//                           DRAM line on B200)
+//   K2  walk_kernel       : one warp per contig segment replays the edit state machine (engine.h) at the flagged positions, one
+//                           candidate k-mer series per lane
+//                           replaces ntedit.cpp:1808-2116 (check-missing, substitutions, tryIndels, tryDeletion, makeEdit decisions)
+//       order_tasks_kernel, compact_events_kernel : work-queue order in front of K2, per-walker grouping of its events behind it
+//   K4  occupancy_kernel  : popcount / non-zero count of the filter (btllib get_fpr, printed by ntedit.cpp:387-395)
+//   K5  insert_kernel     : filter construction (src/ntedit_make_genome_bf.cpp:151-156)
 #pragma once
 #include "engine.h"
 
