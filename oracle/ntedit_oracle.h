@@ -8,7 +8,7 @@
  * published ntHash2 / Bloom-filter algorithms are restated from SURVEY.md Appendix A/B.
  *
  * Parity status:
- *   - ntHash: pinned by btllib's unit-test vector "ACATGCATGCA" k=5 h=3 (tests/test_oracle_kat.py).
+ *   - ntHash: pinned by btllib's unit-test vector "ACATGCATGCA" k=5 h=3 (tests/test_oracle.py).
  *   - Bloom bit addressing / file header: PARITY UNPINNED (no .bf fixture and no btllib source in
  *     the reference tree); the same restatement backs oracle/shim, so reference-vs-ours comparisons
  *     are self-consistent.
