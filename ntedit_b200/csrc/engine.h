@@ -334,6 +334,7 @@ constexpr uint32_t ACT_STOP = 0, ACT_CLEAN = 1, ACT_DIRTY = 2;
 constexpr uint32_t NEXT_CAND = 0, NEXT_INDELS = 1, NEXT_STOP = 2;
 
 constexpr uint32_t WALK_ROT_BYTES = (ROT_WORDS * 8u + 127u) & ~127u;
+constexpr uint32_t WALK_CLS_BYTES = 256u; // class byte of every text byte: seed codes of both strands + accepted flag
 constexpr uint32_t WALK_KP_BYTES = (sizeof(KParams) + 127u) & ~127u; // device: the CTA's copy of the parameters sits in front of the team states
 
 // COMMON = the configuration nearly every polishing run uses -- bit filter, no secondary filter (-e), not -s 1, not -a 1 --
@@ -352,11 +353,17 @@ struct Walker
 	// offset 0).  Every member function re-derives its address from the __shared__ symbol instead of keeping a reference in
 	// the object: a reference would be a generic pointer once `this` escapes into a non-inlined call, and every state access
 	// a generic LD/ST; this way they are LDS/STS.
-	// Layout of the dynamic shared memory: [KParams copy, WALK_KP_BYTES][rotation table, WALK_ROT_BYTES][team states].
+	// Layout of the dynamic shared memory:
+	//   [KParams copy, WALK_KP_BYTES][rotation table, WALK_ROT_BYTES][class table, WALK_CLS_BYTES][team states].
 	__device__ __forceinline__ WalkerState<NCAP>& state_() const
 	{
 		extern __shared__ __align__(16) uint8_t ntb_walk_smem[];
-		return reinterpret_cast<WalkerState<NCAP>*>(ntb_walk_smem + WALK_KP_BYTES + WALK_ROT_BYTES)[threadIdx.x / NTB_TEAM];
+		return reinterpret_cast<WalkerState<NCAP>*>(ntb_walk_smem + WALK_KP_BYTES + WALK_ROT_BYTES + WALK_CLS_BYTES)[threadIdx.x / NTB_TEAM];
+	}
+	__device__ __forceinline__ const uint8_t* cls_tab_() const
+	{
+		extern __shared__ __align__(16) uint8_t ntb_walk_smem[];
+		return ntb_walk_smem + WALK_KP_BYTES + WALK_ROT_BYTES;
 	}
 	__device__ __forceinline__ const uint64_t* rot_() const
 	{
@@ -385,6 +392,22 @@ struct Walker
 	NTB_FN int mask_() const { return COMMON ? 0 : P.mask; }
 	NTB_FN uint32_t fcounting_(const FilterView& f) const { return COMMON ? 0u : f.counting; }
 	NTB_FN uint64_t slot_(const FilterView& f, uint64_t x) const { return POW2 ? (x & f.mask) : filter_slot(f, x); }
+
+	// Class byte of a text byte: bits 0-2 code of the forward seed, bits 3-5 code of the reverse-strand seed (btllib's
+	// SEED_TAB[c & 7] path; code 4 = no seed), bit 6 accepted base (ntedit.cpp:493-499).  On the device one load from a
+	// 256-byte table in shared memory (the arithmetic forms of nthash.h cost 15-20 instructions at every one of ~40
+	// inlined sites, and the walker is bound by instruction fetch); on the host computed.
+	NTB_FN uint32_t cls8(unsigned char c) const
+	{
+#if defined(__CUDA_ARCH__)
+		return cls_tab_()[c];
+#else
+		return base_code(c) | (rev_code(c) << 3) | (is_accepted_any_case(c) ? 0x40u : 0u);
+#endif
+	}
+	NTB_FN uint32_t code_f(unsigned char c) const { return cls8(c) & 7u; }
+	NTB_FN uint32_t code_r(unsigned char c) const { return (cls8(c) >> 3) & 7u; }
+	NTB_FN bool is_acc(unsigned char c) const { return ((cls8(c) >> 6) & 1u) != 0; }
 
 	// ---------------------------------------------------------------- text / rope access
 	NTB_FN unsigned char rd(uint32_t pos) const
@@ -615,7 +638,16 @@ struct Walker
 	// ---------------------------------------------------------------- probing a group of sampled k-mers
 	// class byte of a base: bits 0-2 code of the forward seed, bits 3-5 code of the reverse-strand seed (btllib's
 	// SEED_TAB[c & 7] path); code 4 = no seed
-	NTB_FN static uint8_t cls_of(unsigned char c) { return (uint8_t)(base_code(c) | (rev_code(c) << 3)); }
+	NTB_FN uint8_t cls_of(unsigned char c) const { return (uint8_t)(cls8(c) & 0x3Fu); }
+
+	// NTMC64_changelast (ntedit.cpp:434-452) through the class table
+	NTB_FN void w_changelast(HashState& s, unsigned char out, unsigned char in) const
+	{
+		const uint32_t co = cls8(out), ci = cls8(in);
+		s.fh ^= S.seed_tab[co & 7u] ^ S.seed_tab[ci & 7u];
+		const uint32_t ro = (co >> 3) & 7u, ri = (ci >> 3) & 7u;
+		s.rh ^= (ro < 4u ? P.seed_rot_k1[ro & 3u] : 0ULL) ^ (ri < 4u ? P.seed_rot_k1[ri & 3u] : 0ULL);
+	}
 
 	// NTMC64 rolling form (ntedit.cpp:418-432) on class bytes, seeds from the per-warp tables
 	NTB_FN void roll_cls(HashState& s, uint32_t co, uint32_t ci) const
@@ -752,7 +784,7 @@ struct Walker
 	{
 		HashState s = S.hs;
 		if (cd.change) {
-			hash_changelast(s, S.draft, cd.X, P);
+			w_changelast(s, S.draft, cd.X);
 		}
 		const uint32_t ln = lane_id();
 		const uint32_t Q = cd.Q, nsyn = cd.c, d = cd.d, period = cd.period, kind = cd.kind;
@@ -856,7 +888,7 @@ struct Walker
 		}
 		while (ni < S.nn && S.ty[ni] == 1 && n < (uint32_t)PREVCAP - 8) {
 			const unsigned char c = S.ch[ni];
-			const unsigned cc = base_code(c);
+			const unsigned cc = code_f(c);
 			out[n++] = cc == 0 ? 'T' : cc == 1 ? 'G' : cc == 2 ? 'C' : (cc == 3 && (c | 0x20) == 't') ? 'A' : 'N';
 			ni--;
 		}
@@ -902,7 +934,7 @@ struct Walker
 			for (uint32_t q = np; q > 0; q--) {
 				prev[q] = prev[q - 1];
 			}
-			const unsigned cc = base_code((unsigned char)s.indel[w]);
+			const unsigned cc = code_f((unsigned char)s.indel[w]);
 			prev[0] = cc == 0 ? 'T' : cc == 1 ? 'G' : cc == 2 ? 'C' : (cc == 3 && (s.indel[w] | 0x20) == 't') ? 'A' : 'N';
 			np++;
 			if (is_repeat(prev, (int)np)) {
@@ -946,7 +978,7 @@ struct Walker
 		default: break;
 		}
 		if (snv_()) {
-			return is_accepted_any_case(draft) || draft == 'N' ? NTB_PACK('A', 'T', 'C', 'G') : 0u;
+			return is_acc(draft) || draft == 'N' ? NTB_PACK('A', 'T', 'C', 'G') : 0u;
 		}
 		switch (draft) {
 		case 'R': return NTB_PACK('T', 'C', 0, 0);
@@ -1007,7 +1039,7 @@ struct Walker
 				S.lin_in[m] = in;
 				S.lin_out_c[m] = cls_of(out);
 				S.lin_in_c[m] = cls_of(in);
-				if (m < k && !is_accepted_any_case(in) && m < bad) {
+				if (m < k && !is_acc(in) && m < bad) {
 					bad = m;
 				}
 			} else if (m < k && m < bad) {
@@ -1071,7 +1103,7 @@ struct Walker
 			S.lin_in_c[m] = cls_of(in);
 			S.n_rolls = m + 1;
 			if (check_open) {
-				if (!is_accepted_any_case(in)) {
+				if (!is_acc(in)) {
 					S.dnf = true;
 					check_open = false;
 				} else {
@@ -1161,7 +1193,7 @@ struct Walker
 		// (ntedit.cpp:1960-1968), all of them are the windows the main loop visits next if the candidate is accepted
 		const uint32_t per_cand = 1 + n_sub;
 		const uint32_t njobs = nC + ncand * per_cand;
-		const uint32_t df = base_code(S.draft), dr = rev_code(S.draft);
+		const uint32_t df = code_f(S.draft), dr = code_r(S.draft);
 		const uint64_t* rot = rot_();
 		warp_sync();
 		for (uint32_t j0 = 0; j0 < njobs; j0 += lane_count() * PROBE_G) {
@@ -1179,8 +1211,8 @@ struct Walker
 					f = S.plain_f[R];
 					r = S.plain_r[R];
 					if (R < k) {
-						f ^= rot[df * ROT_STRIDE + R] ^ rot[base_code(X) * ROT_STRIDE + R];
-						r ^= rot[dr * ROT_STRIDE + (k - 1 - R)] ^ rot[rev_code(X) * ROT_STRIDE + (k - 1 - R)];
+						f ^= rot[df * ROT_STRIDE + R] ^ rot[code_f(X) * ROT_STRIDE + R];
+						r ^= rot[dr * ROT_STRIDE + (k - 1 - R)] ^ rot[code_r(X) * ROT_STRIDE + (k - 1 - R)];
 					}
 				}
 				S.hb[ng][ln] = f + r;
@@ -1347,11 +1379,11 @@ struct Walker
 		uint32_t fcode[5], rcode[5];
 		for (uint32_t q = 0; q < L; q++) {
 			const unsigned char c = q + 1 < L ? (unsigned char)((packed >> (8 * (q + 1))) & 0xFF) : S.draft;
-			fcode[q] = base_code(c);
-			rcode[q] = rev_code(c);
+			fcode[q] = code_f(c);
+			rcode[q] = code_r(c);
 		}
-		const uint32_t xf = base_code(S.index_char), xr = rev_code(S.index_char);
-		const uint32_t df = base_code(S.draft), dr = rev_code(S.draft);
+		const uint32_t xf = code_f(S.index_char), xr = code_r(S.index_char);
+		const uint32_t df = code_f(S.draft), dr = code_r(S.draft);
 		const uint64_t* rot = rot_();
 		const uint32_t nv = S.ins_nvalid[L - 1];
 		uint32_t pre_ok = 0, count = 0, nchk = 0;
@@ -1388,11 +1420,11 @@ struct Walker
 #pragma unroll
 		for (uint32_t q = 0; q < 5; q++) {
 			const unsigned char c = q + 1 < L ? (unsigned char)((packed >> (8 * (q + 1))) & 0xFF) : S.draft;
-			fc[q] = base_code(c) * ROT_STRIDE;
-			rc[q] = rev_code(c) * ROT_STRIDE;
+			fc[q] = code_f(c) * ROT_STRIDE;
+			rc[q] = code_r(c) * ROT_STRIDE;
 		}
-		const uint32_t xf = base_code(S.index_char) * ROT_STRIDE, xr = rev_code(S.index_char) * ROT_STRIDE;
-		const uint32_t df = base_code(S.draft) * ROT_STRIDE, dr = rev_code(S.draft) * ROT_STRIDE;
+		const uint32_t xf = code_f(S.index_char) * ROT_STRIDE, xr = code_r(S.index_char) * ROT_STRIDE;
+		const uint32_t df = code_f(S.draft) * ROT_STRIDE, dr = code_r(S.draft) * ROT_STRIDE;
 		const uint64_t* rot = rot_();
 		const uint64_t* bf = S.ins_base_f[L - 1];
 		const uint64_t* br = S.ins_base_r[L - 1];
@@ -1836,7 +1868,7 @@ struct Walker
 			} else if (S.tail_is_chr) {
 				S.ch[S.t.ni] = s.best_sub;
 			}
-			hash_changelast(S.hs, draft, s.best_sub, P);
+			w_changelast(S.hs, draft, s.best_sub);
 			S.la_n = 0;
 			if (S.p1_fast && !snv_() && S.lin_simple && S.tail_is_pos && !S.dnf && S.n_check == P.k && S.n_rolls >= P.k) {
 				// The next k-1 windows contain the substituted base, the k-th is clean again.  Phase 1 probed all of them
@@ -1868,14 +1900,14 @@ struct Walker
 				return;
 			}
 			rope_insert(S.t.ni, S.t.pos, s.indel, s.indel_len);
-			hash_changelast(S.hs, draft, (unsigned char)s.indel[0], P);
+			w_changelast(S.hs, draft, (unsigned char)s.indel[0]);
 			S.la_n = 0;
 			break;
 		}
 		case 3:
 			emit(3, fl, draft, s);
 			rope_delete(S.t.ni, S.t.pos, s.indel_len);
-			hash_changelast(S.hs, draft, cchar(S.t), P);
+			w_changelast(S.hs, draft, cchar(S.t));
 			S.la_n = 0;
 			break;
 		default:
@@ -2041,7 +2073,17 @@ struct Walker
 		S.h.pos = head;
 		S.t.pos = tail;
 		const Walker* self = this;
-		hash_seed(S.hs, P.k, [self, head](unsigned i) { return self->text_at(head + i); });
+		{
+			// NTMC64 seeding form (ntedit.cpp:403-416) on class bytes
+			const uint32_t k = P.k;
+			uint64_t f = 0, r = 0;
+			for (uint32_t i = 0; i < k; i++) {
+				f = srol1(f) ^ S.seed_tab[cls8(self->text_at(head + i)) & 7u];
+				r = srol1(r) ^ S.seed_tab[(cls8(self->text_at(head + k - 1 - i)) >> 3) & 7u];
+			}
+			S.hs.fh = f;
+			S.hs.rh = r;
+		}
 		S.char_in = text_at(tail);
 	}
 
@@ -2059,10 +2101,10 @@ struct Walker
 	{
 		const uint32_t k = P.k;
 		for (uint32_t i = 0; (uint64_t)i + k < S.io.len;) {
-			if (is_accepted_any_case(S.io.text[i])) {
+			if (is_acc(S.io.text[i])) {
 				bool good = true;
 				for (uint32_t j = i + 1; j < i + k; j++) {
-					if (!is_accepted_any_case(S.io.text[j])) {
+					if (!is_acc(S.io.text[j])) {
 						good = false;
 						i = j + 1;
 						break;
@@ -2264,11 +2306,11 @@ struct Walker
 				S.char_in = in;
 				S.adv++;
 				S.la_used++;
-				if (!is_accepted_any_case(in)) {
+				if (!is_acc(in)) {
 					target = (int64_t)(int32_t)S.t.pos + (int64_t)(int32_t)k;
 					S.la_n = 0;
 				}
-				hash_roll(S.hs, out, in, P);
+				roll_cls(S.hs, cls8(out), cls8(in));
 			} else {
 				S.status |= ST_CONTIG_END;
 				S.act = ACT_STOP;
@@ -2341,7 +2383,7 @@ struct Walker
 		const uint32_t J = S.la_J;
 		uint32_t blocked = J == 0 ? 1u : 0u;
 		for (uint32_t m = lane_id(); m < J; m += lane_count()) {
-			if (!is_accepted_any_case(S.lin_in[m])) {
+			if (!is_acc(S.lin_in[m])) {
 				blocked = 1;
 			}
 		}
@@ -2411,8 +2453,8 @@ struct Walker
 				const uint64_t* rot = rot_();
 				for (uint32_t i = lane_id(); i < k; i += lane_count()) {
 					const unsigned char c = text_at(head + i);
-					seed_f ^= rot[base_code(c) * ROT_STRIDE + (k - 1 - i)];
-					seed_r ^= rot[rev_code(c) * ROT_STRIDE + i];
+					seed_f ^= rot[code_f(c) * ROT_STRIDE + (k - 1 - i)];
+					seed_r ^= rot[code_r(c) * ROT_STRIDE + i];
 				}
 				seed_f = warp_xor64(seed_f);
 				seed_r = warp_xor64(seed_r);

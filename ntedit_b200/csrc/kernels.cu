@@ -737,8 +737,11 @@ walk_kernel(const uint8_t* text, const uint32_t* visit, FilterView bloom, Filter
             const Task* tasks, const uint32_t* order, TaskResult* results, uint32_t n_tasks, Event* events, uint32_t ev_cap, Counters* ctr)
 {
 	extern __shared__ __align__(16) uint8_t walk_smem[];
-	// [KParams copy][rotation table][team states] -- engine.h's Walker finds all three by this layout
-	WalkerState<NCAP>* states = reinterpret_cast<WalkerState<NCAP>*>(walk_smem + WALK_KP_BYTES + WALK_ROT_BYTES);
+	// [KParams copy][rotation table][class table][team states] -- engine.h's Walker finds all of them by this layout
+	WalkerState<NCAP>* states = reinterpret_cast<WalkerState<NCAP>*>(walk_smem + WALK_KP_BYTES + WALK_ROT_BYTES + WALK_CLS_BYTES);
+	for (uint32_t q = threadIdx.x; q < 256; q += WALK_THREADS) {
+		walk_smem[WALK_KP_BYTES + WALK_ROT_BYTES + q] = class_of(q);
+	}
 	WalkerState<NCAP>& S = states[threadIdx.x / NTB_TEAM];
 	uint64_t* rot = reinterpret_cast<uint64_t*>(walk_smem + WALK_KP_BYTES);
 	for (uint32_t q = threadIdx.x; q < sizeof(KParams) / 4; q += WALK_THREADS) {
@@ -883,7 +886,7 @@ launch_walk_n(const uint8_t* text, const uint32_t* visit, const FilterView& bloo
               cudaStream_t stream)
 {
 	static int blocks_per_sm = 0;
-	const size_t smem = WALK_KP_BYTES + WALK_ROT_BYTES + (size_t)WALK_TEAMS * sizeof(WalkerState<NCAP>);
+	const size_t smem = WALK_KP_BYTES + WALK_ROT_BYTES + WALK_CLS_BYTES + (size_t)WALK_TEAMS * sizeof(WalkerState<NCAP>);
 	if (blocks_per_sm == 0) {
 		cudaError_t e = cudaFuncSetAttribute(walk_kernel<NCAP, COMMON, POW2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 		if (e != cudaSuccess) {
