@@ -417,6 +417,9 @@ def main():
                                      "walk_kernel": float(np.mean([s["ms_walk"] for s in e2e_stats])),
                                      "host_stitch_replay": float(np.mean([s["ms_host"] for s in e2e_stats]))}},
             "gpu_launches": int(sum(s["kernel_launches"] for s in stats)),
+            "timing": "steps bracketed by torch.cuda.synchronize() (+ dist.barrier) on both sides, max over ranks; a step "
+                      "contains host work (stitch + rope replay), so the bracket is timed on the host clock; the per-stage "
+                      "numbers in breakdown_ms / roofline are CUDA-event times on the library's own stream",
             "clocks": clocks,
             # the HBM-bound stage of the path: K1b = bin_kernel<3,false> + probe_bin_kernel<false>, one pair per text chunk;
             # "launch" = one pass of that stage over the whole batch (CUDA events on its stream around all its launches)
