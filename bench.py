@@ -343,6 +343,11 @@ def main():
         last = step_resident()
     sampler = ClockSampler(local_rank)
     sampler.start()
+    # let nvidia-smi come up before the timed region: forking it out of a process with GBs of pinned mappings takes
+    # 100+ ms on a slow host and holds the interpreter lock, which used to land inside the first timed step
+    t_wait = time.perf_counter()
+    while not sampler.rows and time.perf_counter() - t_wait < 3.0:
+        time.sleep(0.01)
     barrier()
     t0 = time.perf_counter()
     stats = []
