@@ -333,12 +333,15 @@ struct CudaBackend
 	ntb_batch* batch;
 	Workspace* ws = nullptr;
 	size_t ev_used = 0; // events of earlier rounds kept in ws->h_events
+	std::vector<size_t> round_off; // first event of every round inside ws->h_events (offsets: the arena may move when it grows)
 	float ms_scan = 0, ms_walk = 0, ms_d2h = 0;
 	uint32_t launches = 0;
 	std::string err;
 	int rc = NTB_OK;
 
 	const std::string& error() const { return err; }
+
+	const Event* round_events(size_t r) const { return ws->h_events + round_off[r]; }
 
 	int cuda_err(cudaError_t e, const char* what)
 	{
@@ -623,6 +626,7 @@ struct CudaBackend
 		*ev_out = ws->h_events + ev_used;
 		*n_ev_out = 0;
 		if (n == 0) {
+			round_off.push_back(ev_used);
 			return NTB_OK;
 		}
 		if (n > 0xFFFFFFF0ULL) {
@@ -685,7 +689,10 @@ struct CudaBackend
 			}
 			// the events of this round go behind those of the earlier rounds in the pinned arena
 			if (ev_used + ctr.n_events > ws->cap_h_events) {
-				const size_t want = std::max<size_t>((ev_used + ctr.n_events) * 5 / 4 + 4096, ws->cap_events / 2);
+				// NTB_TEST_TIGHT_EVENT_ARENA (testing aid): no slack, so every later round with events moves the arena
+				const size_t want = std::getenv("NTB_TEST_TIGHT_EVENT_ARENA")
+				                        ? ev_used + ctr.n_events
+				                        : std::max<size_t>((ev_used + ctr.n_events) * 5 / 4 + 4096, ws->cap_events / 2);
 				Event* grown = nullptr;
 				NTB_BE(cudaHostAlloc((void**)&grown, want * sizeof(Event), cudaHostAllocDefault));
 				if (ev_used) {
@@ -711,6 +718,7 @@ struct CudaBackend
 			*res_out = ws->h_results;
 			*ev_out = ws->h_events + ev_used;
 			*n_ev_out = ctr.n_events;
+			round_off.push_back(ev_used);
 			ev_used += ctr.n_events;
 			if (std::getenv("NTB_DEBUG_TASKS")) {
 				debug_tasks(n, ctr);

@@ -8,9 +8,11 @@
 //   void  scan_end();                                      -- ... wait for it
 //   Task* task_buffer(size_t n);                           -- host buffer (pinned in the CUDA backend) for n tasks
 //   int   walk(const KParams&, size_t n_tasks, const TaskResult** results, const Event** events, size_t* n_events);
-//         -- K2 over the tasks in task_buffer(); results stay valid until the next walk(), the events of every
-//            round until the backend is destroyed.  The events of task i are events[results[i].last_event ..
-//            + results[i].n_events), in the order the walker emitted them
+//         -- K2 over the tasks in task_buffer(); results and the returned events pointer stay valid until the next walk().
+//            The events of task i are events[results[i].last_event .. + results[i].n_events), in the order the walker
+//            emitted them
+//   const Event* round_events(size_t r) const;             -- the events of round r (the r-th walk() call), valid until the
+//            next walk(): a backend may move earlier rounds when its arena grows, so the driver never keeps the pointers
 // The product instantiates this with the CUDA backend (capi.cu); tests/hostsim instantiates it with a CPU
 // simulator of the same engine so the stitch/replay logic can be fuzzed without a GPU.
 #pragma once
@@ -258,7 +260,7 @@ polish_run(Backend& be, const KParams& kp_in, const ntb_params& up, char* host_b
 	};
 
 	// ---- rounds of walkers + stitching
-	std::vector<const Event*> arenas; // events of each round (owned by the backend)
+	size_t n_arenas = 0; // rounds walked so far; their events are fetched through be.round_events() when they are replayed
 	std::vector<uint64_t> pending; // segment indices to (re)run
 	pending.reserve(segs.size());
 	for (uint64_t i = 0; i < segs.size(); i++) {
@@ -316,7 +318,7 @@ polish_run(Backend& be, const KParams& kp_in, const ntb_params& up, char* host_b
 			err = be.error();
 			return rc;
 		}
-		arenas.push_back(round_events);
+		n_arenas++;
 		out.stats.rounds++;
 		out.stats.segments += pending.size();
 		if (out.stats.rounds > 1) {
@@ -330,7 +332,7 @@ polish_run(Backend& be, const KParams& kp_in, const ntb_params& up, char* host_b
 			const uint64_t n_chunks = (n_pending + chunk - 1) / chunk;
 			std::vector<uint64_t> chunk_sites(n_chunks, 0);
 			std::atomic<int> bad(0);
-			const int32_t arena_idx = (int32_t)arenas.size() - 1;
+			const int32_t arena_idx = (int32_t)n_arenas - 1;
 			run_parallel(n_chunks, [&](uint64_t q) {
 				uint64_t sites = 0;
 				const uint64_t e = std::min<uint64_t>(n_pending, (q + 1) * chunk);
@@ -512,6 +514,11 @@ polish_run(Backend& be, const KParams& kp_in, const ntb_params& up, char* host_b
 		std::fprintf(stderr, "[ntb] host:   replay (A) accept + cut %.1f ms\n", since(t1));
 	}
 	const auto t_b = clk::now();
+	// no walk() follows: the rounds' event pointers are stable from here on
+	std::vector<const Event*> arena_base(n_arenas);
+	for (size_t r = 0; r < n_arenas; r++) {
+		arena_base[r] = be.round_events(r);
+	}
 	// (B) every piece on its own
 	run_parallel(pieces.size(), [&](uint64_t w) {
 		Piece& pc = pieces[w];
@@ -540,7 +547,7 @@ polish_run(Backend& be, const KParams& kp_in, const ntb_params& up, char* host_b
 		for (uint64_t a = pc.a0; a < pc.a1 && !rp.ended; a++) {
 			const Segment& sg = segs[acc[a]];
 			// the backend hands every walker's events over as one contiguous run, first event first
-			const Event* run = sg.res.n_events ? arenas[(size_t)sg.arena] + sg.res.last_event : nullptr;
+			const Event* run = sg.res.n_events ? arena_base[(size_t)sg.arena] + sg.res.last_event : nullptr;
 			for (uint32_t q = 0; q < sg.res.n_events; q++) {
 				Event ev = run[q];
 				ev.base = resolve(ev.base);

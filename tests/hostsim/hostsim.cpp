@@ -76,6 +76,8 @@ struct HostBackend
 	std::vector<TaskResult> results;
 	std::vector<std::unique_ptr<std::vector<Event>>> rounds;
 
+	const Event* round_events(size_t r) const { return rounds[r]->data(); }
+
 	Task* task_buffer(size_t n)
 	{
 		tasks.resize(n);

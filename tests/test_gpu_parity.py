@@ -156,3 +156,20 @@ def test_piecewise_replay_on_device_results(nb, oracle, monkeypatch):
         ofa, otsv, ovcf = oracle.polish(inp["contigs"], ofilt, op, bloomrep=orep)
         assert fa == ofa and tsv == otsv and vcf == ovcf
         ofilt.free()
+
+
+def test_rerun_rounds_survive_a_moving_event_arena(nb, oracle, monkeypatch):
+    """Several walker rounds, and the pinned event arena is re-allocated (moved) by every round after the first: the
+    events of segments accepted in earlier rounds must still be the ones replayed (round-1 ADVICE: stored pointers)."""
+    monkeypatch.setenv("NTB_NO_BORDER_ADJUST", "1")       # nominal borders: successors start inside dirty stretches
+    monkeypatch.setenv("NTB_TEST_TIGHT_EVENT_ARENA", "1")  # no slack in the arena: every later round moves it
+    case = [c for c in tc.CASES if c["name"] == "m1"][0]
+    inp = tc.make_inputs(4242, n=60000, sub_rate=1.5e-2, indel_rate=3e-3)
+    ofilt, orep = tc.oracle_filters(oracle, inp)
+    bloom, rep = device_filters(nb, inp)
+    fa, tsv, vcf, st = nb.polish(inp["contigs"], bloom, nb.default_params(segment_len=100, **case["p"]), bloomrep=rep)
+    assert st["rounds"] >= 3 and st["reruns"] > 0
+    op = oracle.default_params(inp["k"], inp["h"], **tc.oracle_param_overrides(case["p"]))
+    ofa, otsv, ovcf = oracle.polish(inp["contigs"], ofilt, op, bloomrep=orep)
+    assert fa == ofa and tsv == otsv and vcf == ovcf
+    ofilt.free()
