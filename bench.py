@@ -435,7 +435,8 @@ def main():
                          "gather_ceiling_note": "a direct 1-byte probe costs a 128-byte DRAM line on B200 (37.9 G probes/s "
                                                 "ceiling, profiles/r01_gather_*); K1b serves probes from L2-resident filter regions"},
             "cpu_baseline": cpu,
-            "breakdown_ms": {"scan_kernel": ms_scan, "walk_kernel": ms_walk, "host_stitch_replay": ms_host,
+            "breakdown_ms": {"scan_kernel": ms_scan, "presite_kernels": float(np.mean([s["ms_pre"] for s in stats])),
+                             "walk_kernel": ms_walk, "host_stitch_replay": ms_host,
                              "d2h_events": float(np.mean([s["ms_d2h"] for s in stats])), "rounds": stats[-1]["rounds"],
                              "segments": stats[-1]["segments"], "reruns": stats[-1]["reruns"], "sites": stats[-1]["sites"],
                              "edits": stats[-1]["edits"], "setup_s": setup_s},

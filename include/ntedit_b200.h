@@ -145,6 +145,8 @@ typedef struct ntb_stats {
 	float ms_walk;           /* K2 device time, all rounds */
 	float ms_h2d, ms_d2h;
 	float ms_host;           /* host replay + stitch wall time */
+	float ms_pre;            /* K2p device time: site pre-evaluation passes in front of the first walker round */
+	uint32_t pad_;
 } ntb_stats;
 
 /* Replaces the kmerizeAndCorrect calls of readAndCorrect's loop (ntedit.cpp:2220-2245) for a whole batch.

@@ -240,6 +240,14 @@ struct Workspace
 	uint64_t* d_records = nullptr; // K1b: probe records, n_buckets x bucket_cap
 	size_t cap_records = 0;
 	uint32_t* d_cursor = nullptr;  // K1b: BIN_MAX_BUCKETS record counters + the probe kernel's pacing counter
+	SiteRec* d_table = nullptr;    // pre-evaluated sites (open addressing, power-of-two slots)
+	size_t cap_table = 0;
+	uint2* d_items = nullptr;      // heads of flagged runs (task, position)
+	size_t cap_items = 0;
+	PendingSite* d_pending = nullptr;
+	size_t cap_pending = 0;
+	cudaEvent_t ev_pre0 = nullptr, ev_pre1 = nullptr;
+	Counters* h_ctr_pre = nullptr; // pinned: the counters after the pre-evaluation passes (diagnostics)
 	// pinned host mirrors
 	Task* h_tasks = nullptr;
 	TaskResult* h_results = nullptr;
@@ -261,6 +269,16 @@ struct Workspace
 		cudaFree(d_records);
 		cudaFree(d_cursor);
 		cudaFree(d_text);
+		cudaFree(d_table);
+		cudaFree(d_items);
+		cudaFree(d_pending);
+		cudaFreeHost(h_ctr_pre);
+		if (ev_pre0) {
+			cudaEventDestroy(ev_pre0);
+		}
+		if (ev_pre1) {
+			cudaEventDestroy(ev_pre1);
+		}
 		cudaFreeHost(h_tasks);
 		cudaFreeHost(h_results);
 		cudaFreeHost(h_events);
@@ -334,7 +352,9 @@ struct CudaBackend
 	Workspace* ws = nullptr;
 	size_t ev_used = 0; // events of earlier rounds kept in ws->h_events
 	std::vector<size_t> round_off; // first event of every round inside ws->h_events (offsets: the arena may move when it grows)
-	float ms_scan = 0, ms_walk = 0, ms_d2h = 0;
+	float ms_scan = 0, ms_walk = 0, ms_d2h = 0, ms_pre = 0;
+	bool pre_timed = false;       // ev_pre0 / ev_pre1 bracket this call's pre-evaluation passes
+	size_t table_slots = 0;       // slots of ws->d_table that hold this call's records (0: no pre-evaluation)
 	uint32_t launches = 0;
 	std::string err;
 	int rc = NTB_OK;
@@ -617,6 +637,68 @@ struct CudaBackend
 		return ws->h_tasks;
 	}
 
+	// Pre-evaluation in front of the first walker round (kernels.cuh: launch_heads / launch_presite): fills ws->d_table.
+	// Sized from the batch: a head every ~800 bases at the usual error rates; lists and table that run full only cost speed
+	// (the walkers evaluate what has no record).
+	int presites(WalkArgs& a, cudaStream_t stream)
+	{
+		if (a.kp.snv || env_u64("NTB_NO_PRESITE", 0)) {
+			return NTB_OK; // -s 1: every position is a site, nothing to run ahead of
+		}
+		const uint64_t total = batch->total;
+		const size_t want_items = (size_t)std::min<uint64_t>(0x7FFFFFF0ull, std::max<uint64_t>(1u << 14, total / 96));
+		const size_t want_pending = (size_t)std::min<uint64_t>(0x7FFFFFF0ull, std::max<uint64_t>(1u << 12, total / 384));
+		size_t slots = 1u << 12;
+		const uint64_t want_slots = std::min<uint64_t>(1ull << 31, env_u64("NTB_SITE_TABLE_SLOTS", total / 64));
+		while (slots < want_slots) {
+			slots <<= 1;
+		}
+		if (slots > ws->cap_table) {
+			cudaFree(ws->d_table);
+			ws->d_table = nullptr;
+			ws->cap_table = 0;
+			NTB_BE(cudaMalloc((void**)&ws->d_table, slots * sizeof(SiteRec)));
+			ws->cap_table = slots;
+		}
+		if (want_items > ws->cap_items) {
+			cudaFree(ws->d_items);
+			ws->d_items = nullptr;
+			ws->cap_items = 0;
+			NTB_BE(cudaMalloc((void**)&ws->d_items, want_items * sizeof(uint2)));
+			ws->cap_items = want_items;
+		}
+		if (want_pending > ws->cap_pending) {
+			cudaFree(ws->d_pending);
+			ws->d_pending = nullptr;
+			ws->cap_pending = 0;
+			NTB_BE(cudaMalloc((void**)&ws->d_pending, want_pending * sizeof(PendingSite)));
+			ws->cap_pending = want_pending;
+		}
+		if (!ws->ev_pre0) {
+			NTB_BE(cudaEventCreate(&ws->ev_pre0));
+			NTB_BE(cudaEventCreate(&ws->ev_pre1));
+			NTB_BE(cudaHostAlloc((void**)&ws->h_ctr_pre, sizeof(Counters), cudaHostAllocDefault));
+		}
+		a.table = ws->d_table;
+		a.table_mask = (uint32_t)(slots - 1);
+		a.items = ws->d_items;
+		a.items_cap = (uint32_t)ws->cap_items;
+		a.pending = ws->d_pending;
+		a.pending_cap = (uint32_t)ws->cap_pending;
+		NTB_BE(cudaEventRecord(ws->ev_pre0, stream));
+		NTB_BE(cudaMemsetAsync(ws->d_table, 0, slots * sizeof(SiteRec), stream));
+		NTB_BE(cudaMemsetAsync(ws->d_ctr, 0, sizeof(Counters), stream));
+		NTB_BE(launch_heads(a, stream));
+		NTB_BE(launch_presite(a, false, stream));
+		NTB_BE(launch_presite(a, true, stream));
+		NTB_BE(cudaMemcpyAsync(ws->h_ctr_pre, ws->d_ctr, sizeof(Counters), cudaMemcpyDeviceToHost, stream));
+		NTB_BE(cudaEventRecord(ws->ev_pre1, stream));
+		launches += 3;
+		pre_timed = true;
+		table_slots = slots;
+		return NTB_OK;
+	}
+
 	int walk(const KParams& kp, size_t n, const TaskResult** res_out, const Event** ev_out, size_t* n_ev_out)
 	{
 		if (rc != NTB_OK) {
@@ -662,11 +744,36 @@ struct CudaBackend
 		if (rep) {
 			fr = rep->view();
 		}
+		WalkArgs wa;
+		std::memset(&wa, 0, sizeof wa);
+		wa.text = batch->d_text;
+		wa.visit = ws->d_visit;
+		wa.bloom = fb;
+		wa.rep = fr;
+		wa.kp = kp;
+		wa.tasks = ws->d_tasks;
+		wa.order = ws->d_order;
+		wa.results = ws->d_results;
+		wa.n_tasks = (uint32_t)n;
+		wa.ctr = ws->d_ctr;
+		wa.sm_count = sm_count(batch->device);
+		if (round_off.empty()) {
+			// first round: its tasks cover every contig
+			if (presites(wa, stream) != NTB_OK) {
+				return rc;
+			}
+		}
+		if (table_slots) {
+			// (later rounds look the same records up)
+			wa.table = ws->d_table;
+			wa.table_mask = (uint32_t)(table_slots - 1);
+		}
 		for (;;) {
+			wa.events = ws->d_events;
+			wa.ev_cap = (uint32_t)std::min<size_t>(ws->cap_events, 0xFFFFFFF0u);
 			NTB_BE(cudaMemsetAsync(ws->d_ctr, 0, sizeof(Counters), stream));
 			NTB_BE(cudaEventRecord(ws->ev0, stream));
-			NTB_BE(launch_walk(batch->d_text, ws->d_visit, fb, fr, kp, ws->d_tasks, ws->d_order, ws->d_results, (uint32_t)n, ws->d_events,
-			                   (uint32_t)std::min<size_t>(ws->cap_events, 0xFFFFFFF0u), ws->d_ctr, sm_count(batch->device), stream));
+			NTB_BE(launch_walk(wa, stream));
 			launches += 2; // order_tasks_kernel + walk_kernel
 			NTB_BE(cudaEventRecord(ws->ev1, stream));
 			NTB_BE(cudaMemcpyAsync(ws->h_ctr, ws->d_ctr, sizeof(Counters), cudaMemcpyDeviceToHost, stream));
@@ -675,6 +782,16 @@ struct CudaBackend
 			float ms = 0;
 			NTB_BE(cudaEventElapsedTime(&ms, ws->ev0, ws->ev1));
 			ms_walk += ms;
+			if (pre_timed) {
+				pre_timed = false;
+				NTB_BE(cudaEventElapsedTime(&ms, ws->ev_pre0, ws->ev_pre1));
+				ms_pre += ms;
+				if (std::getenv("NTB_DEBUG_TASKS")) {
+					const Counters& pc = *ws->h_ctr_pre;
+					std::fprintf(stderr, "[ntb] pre-evaluation: %.2f ms, %u heads (cap %zu), %u pending (cap %zu), %u records dropped, table %zu slots\n", ms,
+					             pc.n_items, ws->cap_items, pc.n_pending, ws->cap_pending, pc.n_dropped, table_slots);
+				}
+			}
 			if (ctr.overflow) {
 				cudaFree(ws->d_events);
 				cudaFree(ws->d_events_sorted);
@@ -825,6 +942,7 @@ polish_common(ntb_filter* bloom, ntb_filter* rep, const ntb_params* p, ntb_batch
 	}
 	res->impl.stats.ms_scan = be.ms_scan;
 	res->impl.stats.ms_walk = be.ms_walk;
+	res->impl.stats.ms_pre = be.ms_pre;
 	res->impl.stats.ms_d2h = be.ms_d2h;
 	if (batch->up_src && batch->up_end && batch->up_issued == batch->total && cudaEventSynchronize(batch->up_end) == cudaSuccess) {
 		cudaEventElapsedTime(&batch->ms_h2d, batch->up_begin, batch->up_end); // includes the waits between pieces

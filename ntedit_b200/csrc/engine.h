@@ -184,7 +184,40 @@ struct WalkerIO
 	uint32_t ev_cap;
 	Counters* ctr;
 	const uint64_t* rot;       // ROT_WORDS entries, see rot_entry()
+	SiteRec* table;            // pre-evaluated sites (ntb_common.h: SiteRec), table_mask + 1 slots; nullptr = none
+	uint32_t table_mask;
+	PendingSite* pending;      // pre-evaluation, first pass: sites left for the second pass
+	uint32_t pending_cap;
 };
+
+// slot a key starts probing at
+NTB_FN inline uint32_t
+site_hash(uint64_t key)
+{
+	key *= 0x9E3779B97F4A7C15ULL;
+	return (uint32_t)(key >> 32);
+}
+
+// claims a slot for `key` (no key is inserted twice: every position is pre-evaluated by one item only); NONE32 = no room
+NTB_FN inline uint32_t
+site_table_insert(SiteRec* table, uint32_t mask, uint64_t key)
+{
+	uint32_t slot = site_hash(key) & mask;
+	for (uint32_t i = 0; i < SITE_TABLE_PROBES; i++, slot = (slot + 1) & mask) {
+#if defined(__CUDA_ARCH__)
+		const unsigned long long seen = atomicCAS(reinterpret_cast<unsigned long long*>(&table[slot].key), 0ULL, (unsigned long long)key);
+		if (seen == 0ULL || seen == (unsigned long long)key) {
+			return slot;
+		}
+#else
+		if (table[slot].key == 0 || table[slot].key == key) {
+			table[slot].key = key;
+			return slot;
+		}
+#endif
+	}
+	return NONE32;
+}
 
 constexpr uint32_t MAX_INS_TRIES = 341;   // num_tries[5], ntedit.cpp:172
 constexpr uint32_t MAX_DELETIONS = 10;    // ntedit.cpp:2489-2493
@@ -312,8 +345,14 @@ struct WalkerState
 	uint32_t n_plain;
 	uint8_t tsolid[4][KMAX + 1]; // substitution trial, k-mer after R rolls (index R-1): present && solid
 	uint8_t tsite[4][KMAX + 1];  // ... the main loop would enter its edit block at that k-mer
-	bool p1_fast;                // phase 1 took the table path (tsolid / tsite are filled for every roll)
+	bool p1_fast;                // phase 1 took the table path (tsolid / tsite are filled for every roll of the tried candidates)
+	bool quiet;                  // accepted substitution, none of the k-1 windows behind it is a site (see evaluate_site_core)
 	bool skip_advance;           // site_commit already moved the window to the next clean position
+	uint32_t use_rec;            // this site's decision comes from a pre-evaluated record (its SITE_* state; 0 = evaluate here)
+	bool rec_hash;               // ... and committing it needs the window's hash and the text cache
+	uint8_t rec_fl;              // ... its EV_TOUCHED flag
+	uint32_t rec_slot;           // pre-evaluation: slot of the record being written
+	bool pre_more;               // pre-evaluation: the chain goes on with the next position
 	// insertion candidates without rolling: hash state after q+1 rolls of an insertion of length L whose inserted chars
 	// contribute nothing (ins_base_*[L-1][sample]); the candidates add their chars' terms from the rotation table
 	static constexpr int NSMAX = NCAP <= 160 ? 16 : 32;
@@ -1175,59 +1214,119 @@ struct Walker
 		warp_sync();
 	}
 
-	// phase 1 without rolling: every k-mer of the check-missing subset (ntedit.cpp:1826-1858), of the substitution gates
-	// (ntedit.cpp:1923-1928) and of the substitution trials (ntedit.cpp:1936-1981) as one job, jobs dealt round-robin to
-	// the lanes.  A trial k-mer after R rolls is the plain k-mer plus the NTMC64_changelast terms rotated R times; after
-	// k rolls the substituted base has left the window and the k-mer is the plain one.
+	// Phase 1 without rolling, in dependent steps so that nothing is probed that the decision does not read:
+	//   phase_fast_check : the check-missing subset (ntedit.cpp:1826-1858)                               -> S.chk[]
+	//   phase_fast_subs  : the substitution gates (ntedit.cpp:1923-1928)                                 -> S.gate[]
+	//                      then, for the candidates whose gate passed (all of them in mode 2), the trial
+	//                      (ntedit.cpp:1936-1981) with EVERY following window                            -> S.tsolid / S.tsite / S.sup
+	// Most sites stop after the first step (no attempt) or try one candidate: ~40 k-mers instead of 9 + 3 * 26.  The
+	// k-mers of the first two steps are mostly absent and are probed one hash function per pass (btllib's early exit,
+	// ntedit.cpp:368-371); a direct probe costs a 128-byte DRAM line on B200.
+	// Every k-mer is a plain one (compute_plain) plus, for a trial after R rolls, the NTMC64_changelast terms rotated R
+	// times; after k rolls the substituted base has left the window and the k-mer is the plain one.
 	// Requires patch_idx == k-1 (the tail's slot leaves the window with the k-th roll), which every consistent rope gives.
-	NTB_FN void phase_check_and_subs_fast()
+	NTB_FN void phase_fast_check()
+	{
+		const uint32_t jump = P.jump, ln = lane_id();
+		const uint32_t nC = S.n_check ? (S.n_check - 1) / jump + 1 : 0;   // samples q = 0, jump, .. < n_check
+		warp_sync();
+		for (uint32_t j0 = 0; j0 < nC; j0 += lane_count() * PROBE_G) {
+			uint32_t ng = 0;
+			for (uint32_t j = j0 + ln; j < nC && ng < (uint32_t)PROBE_G; j += lane_count()) {
+				const uint32_t R = j * jump + 1;
+				S.hb[ng][ln] = S.plain_f[R] + S.plain_r[R];
+				ng++;
+			}
+			if (ng) {
+				probe_values(S.io.bloom, ng, (1u << ng) - 1u, 1);
+				uint32_t g = 0;
+				for (uint32_t j = j0 + ln; j < nC && g < ng; j += lane_count(), g++) {
+					S.chk[j] = S.pval[g][ln];
+				}
+			}
+		}
+		warp_sync();
+		NTB_LEADER_BEGIN
+		S.chk_n = nC;
+		S.p1_fast = true;
+		NTB_LEADER_END
+	}
+
+	NTB_FN void phase_fast_subs()
 	{
 		const uint32_t k = P.k, jump = P.jump, ln = lane_id();
 		const uint32_t n_sub = S.n_rolls < k ? S.n_rolls : k;
-		const uint32_t nC = S.n_check ? (S.n_check - 1) / jump + 1 : 0;   // samples q = 0, jump, .. < n_check
 		uint32_t ncand = 0;
 		while (ncand < 4 && ((S.cands >> (8 * ncand)) & 0xFF) != 0) {
 			ncand++;
 		}
-		// per candidate: the gate (R = 0) and the k-mer after every roll R = 1 .. n_sub -- the sampled ones are the trial
-		// (ntedit.cpp:1960-1968), all of them are the windows the main loop visits next if the candidate is accepted
-		const uint32_t per_cand = 1 + n_sub;
-		const uint32_t njobs = nC + ncand * per_cand;
 		const uint32_t df = code_f(S.draft), dr = code_r(S.draft);
 		const uint64_t* rot = rot_();
 		warp_sync();
+		// ---- gates: the window with its last base replaced (mode 2 tries every candidate: no gate is read)
+		if (P.mode != 2) {
+			for (uint32_t j0 = 0; j0 < ncand; j0 += lane_count() * PROBE_G) {
+				uint32_t ng = 0;
+				for (uint32_t j = j0 + ln; j < ncand && ng < (uint32_t)PROBE_G; j += lane_count()) {
+					const unsigned char X = (unsigned char)((S.cands >> (8 * j)) & 0xFF);
+					const uint64_t f = S.plain_f[0] ^ rot[df * ROT_STRIDE] ^ rot[code_f(X) * ROT_STRIDE];
+					const uint64_t r = S.plain_r[0] ^ rot[dr * ROT_STRIDE + (k - 1)] ^ rot[code_r(X) * ROT_STRIDE + (k - 1)];
+					S.hb[ng][ln] = f + r;
+					ng++;
+				}
+				if (ng) {
+					probe_values(S.io.bloom, ng, (1u << ng) - 1u, 1);
+					uint32_t solid = 0;
+					for (uint32_t g = 0; g < ng; g++) {
+						if (solid_value(S.pval[g][ln])) {
+							solid |= 1u << g;
+						}
+					}
+					if (h_rep_() && solid) {
+						// solid k-mers additionally must be absent from the secondary filter (-e), ntedit.cpp:467-468
+						probe_values(S.io.rep, ng, solid, 1);
+						for (uint32_t q = 0; q < ng; q++) {
+							if (((solid >> q) & 1u) && S.pval[q][ln] != 0) {
+								solid &= ~(1u << q);
+							}
+						}
+					}
+					uint32_t g = 0;
+					for (uint32_t j = j0 + ln; j < ncand && g < ng; j += lane_count(), g++) {
+						S.gate[j] = (uint8_t)((solid >> g) & 1u);
+					}
+				}
+			}
+			warp_sync();
+		}
+		// ---- trials: the k-mer after every roll R = 1 .. n_sub of every tried candidate -- the sampled ones are the trial
+		// (ntedit.cpp:1960-1968), all of them are the windows the main loop visits next if the candidate is accepted
+		uint32_t act[4], nact = 0;
+		for (uint32_t c = 0; c < ncand; c++) {
+			if (P.mode == 2 || S.gate[c]) {
+				act[nact++] = c;
+			}
+		}
+		const uint32_t njobs = nact * n_sub;
 		for (uint32_t j0 = 0; j0 < njobs; j0 += lane_count() * PROBE_G) {
-			// this lane's jobs of the round: j0 + ln, j0 + ln + lanes, ...
 			uint32_t ng = 0;
 			for (uint32_t j = j0 + ln; j < njobs && ng < (uint32_t)PROBE_G; j += lane_count()) {
-				uint64_t f, r;
-				if (j < nC) {
-					const uint32_t R = j * jump + 1;
-					f = S.plain_f[R];
-					r = S.plain_r[R];
-				} else {
-					const uint32_t c = (j - nC) / per_cand, R = (j - nC) % per_cand;
-					const unsigned char X = (unsigned char)((S.cands >> (8 * c)) & 0xFF);
-					f = S.plain_f[R];
-					r = S.plain_r[R];
-					if (R < k) {
-						f ^= rot[df * ROT_STRIDE + R] ^ rot[code_f(X) * ROT_STRIDE + R];
-						r ^= rot[dr * ROT_STRIDE + (k - 1 - R)] ^ rot[code_r(X) * ROT_STRIDE + (k - 1 - R)];
-					}
+				const uint32_t c = act[j / n_sub], R = j % n_sub + 1;
+				const unsigned char X = (unsigned char)((S.cands >> (8 * c)) & 0xFF);
+				uint64_t f = S.plain_f[R], r = S.plain_r[R];
+				if (R < k) {
+					f ^= rot[df * ROT_STRIDE + R] ^ rot[code_f(X) * ROT_STRIDE + R];
+					r ^= rot[dr * ROT_STRIDE + (k - 1 - R)] ^ rot[code_r(X) * ROT_STRIDE + (k - 1 - R)];
 				}
 				S.hb[ng][ln] = f + r;
 				ng++;
 			}
 			if (ng) {
 				probe_values(S.io.bloom, ng, (1u << ng) - 1u, PROBE_HU);
-				// solid k-mers additionally must be absent from the secondary filter (-e), ntedit.cpp:467-468
 				uint32_t solid = 0, site = 0;
-				uint32_t g = 0;
-				uint32_t raw[PROBE_G];
-				for (uint32_t j = j0 + ln; j < njobs && g < ng; j += lane_count(), g++) {
+				for (uint32_t g = 0; g < ng; g++) {
 					const uint32_t v = S.pval[g][ln];
-					raw[g] = v;
-					if (j >= nC && solid_value(v)) {
+					if (solid_value(v)) {
 						solid |= 1u << g;
 					}
 					if (is_site_value(v)) {
@@ -1242,30 +1341,20 @@ struct Walker
 						}
 					}
 				}
-				g = 0;
+				uint32_t g = 0;
 				for (uint32_t j = j0 + ln; j < njobs && g < ng; j += lane_count(), g++) {
-					if (j < nC) {
-						S.chk[j] = (uint8_t)raw[g];
-					} else {
-						const uint32_t c = (j - nC) / per_cand, R = (j - nC) % per_cand;
-						const uint8_t ok = (uint8_t)((solid >> g) & 1u);
-						if (R == 0) {
-							S.gate[c] = ok;
-						} else {
-							S.tsolid[c][R - 1] = ok;
-							S.tsite[c][R - 1] = (uint8_t)((site >> g) & 1u);
-						}
-					}
+					const uint32_t c = act[j / n_sub], R = j % n_sub + 1;
+					S.tsolid[c][R - 1] = (uint8_t)((solid >> g) & 1u);
+					S.tsite[c][R - 1] = (uint8_t)((site >> g) & 1u);
 				}
 			}
 		}
 		warp_sync();
 		NTB_LEADER_BEGIN
-		S.chk_n = nC;
-		S.p1_fast = true;
 		for (uint32_t c = 0; c < 4; c++) {
 			uint32_t cnt = 0;
-			if (c < ncand) {
+			const bool tried = c < ncand && (P.mode == 2 || S.gate[c]);
+			if (tried) {
 				for (uint32_t q = 0; q < n_sub; q += jump) {
 					cnt += S.tsolid[c][q];
 				}
@@ -1824,7 +1913,7 @@ struct Walker
 	}
 
 	// leader: makeEdit, ntedit.cpp:1250-1448.  site_ok = false when the contig is finished (insertion guard fired)
-	NTB_FN void site_commit()
+	NTB_FN void site_commit(const uint8_t fl)
 	{
 		Site& s = S.s;
 		const unsigned char draft = S.draft;
@@ -1832,7 +1921,6 @@ struct Walker
 		S.stale_alt1 = s.altbase1;
 		S.stale_alt2 = s.altbase2;
 		S.stale_alt3 = s.altbase3;
-		const uint8_t fl = (S.touched && S.raw != draft) ? EV_TOUCHED : 0;
 		switch (s.best_type) {
 		case 1:
 			emit(1, fl, draft, s);
@@ -1870,27 +1958,13 @@ struct Walker
 			}
 			w_changelast(S.hs, draft, s.best_sub);
 			S.la_n = 0;
-			if (S.p1_fast && !snv_() && S.lin_simple && S.tail_is_pos && !S.dnf && S.n_check == P.k && S.n_rolls >= P.k) {
-				// The next k-1 windows contain the substituted base, the k-th is clean again.  Phase 1 probed all of them
-				// for every candidate: when none is a site for the accepted base (and the k incoming bases are accepted --
-				// n_check == k), rolling through them one by one (ntedit.cpp:2118-2138) has no observable effect: jump.
-				uint32_t c = 0;
-				while (c < 4 && ((S.cands >> (8 * c)) & 0xFF) != s.best_sub) {
-					c++;
-				}
-				bool quiet = c < 4;
-				for (uint32_t R = 1; quiet && R + 1 <= P.k; R++) {
-					if (S.tsite[c][R - 1]) {
-						quiet = false;
-					}
-				}
-				if (quiet) {
-					S.h.pos += P.k;
-					S.t.pos += P.k;
-					S.adv += P.k;
-					S.need_seed = true; // the window is clean: the hash is re-seeded at the next flagged position
-					S.skip_advance = true;
-				}
+			if (S.quiet) {
+				// none of the k-1 windows that contain the new base is a site (evaluate_site_core): jump behind them
+				S.h.pos += P.k;
+				S.t.pos += P.k;
+				S.adv += P.k;
+				S.need_seed = true; // the window is clean: the hash is re-seeded at the next flagged position
+				S.skip_advance = true;
 			}
 			break;
 		case 2: {
@@ -1919,8 +1993,10 @@ struct Walker
 		}
 	}
 
-	// returns false when the contig is finished (insertion guard fired)
-	NTB_FN bool evaluate_site()
+	// One site up to, not including, makeEdit (ntedit.cpp:1808-2116).  Returns SITE_NONE when no attempt is made (nothing to
+	// commit), SITE_DONE when S.s / S.touched / S.quiet hold the decision, SITE_PENDING when `allow_indels` is false and the
+	// candidate loop reached a tryIndels call (pre-evaluation, first pass).
+	NTB_FN uint32_t evaluate_site_core(bool allow_indels)
 	{
 		NTB_PROF_T0
 		NTB_LEADER_BEGIN
@@ -1929,12 +2005,13 @@ struct Walker
 		linearise(P.k + MAX_DELETIONS + 1, true);
 		NTB_PROF(8);
 		if (!snv_() && S.dnf) {
-			return true; // no attempt is possible (ntedit.cpp:1865): the subset counts are not needed
+			return SITE_NONE; // no attempt is possible (ntedit.cpp:1865): the subset counts are not needed
 		}
-		if (S.patch_idx == P.k - 1 && P.k + 1 < ROT_STRIDE) {
+		const bool fast = S.patch_idx == P.k - 1 && P.k + 1 < ROT_STRIDE;
+		if (fast) {
 			compute_plain(P.k);
 			NTB_PROF(9);
-			phase_check_and_subs_fast();
+			phase_fast_check();
 		} else {
 			phase_check_and_subs();
 		}
@@ -1943,7 +2020,11 @@ struct Walker
 		S.next = site_after_check() ? NEXT_CAND : NEXT_STOP;
 		NTB_LEADER_END
 		if (S.next == NEXT_STOP) {
-			return true;
+			return SITE_NONE;
+		}
+		if (fast) {
+			phase_fast_subs();
+			NTB_PROF(10);
 		}
 		NTB_LEADER_BEGIN
 		S.ci = 0;
@@ -1963,6 +2044,9 @@ struct Walker
 			if (S.next != NEXT_INDELS) {
 				break;
 			}
+			if (!allow_indels) {
+				return SITE_PENDING;
+			}
 			NTB_PROF(11);
 #if defined(NTB_PHASE_PROF) && defined(__CUDA_ARCH__)
 			if (lane_id() == 0) {
@@ -1980,10 +2064,281 @@ struct Walker
 		}
 		NTB_PROF(11);
 		NTB_LEADER_BEGIN
-		site_commit();
+		// An accepted substitution leaves k-1 windows that contain the new base; the k-th is clean again.  Phase 1 probed
+		// all of them for the accepted candidate: when none is a site (and the k incoming bases are accepted --
+		// n_check == k), rolling through them one by one (ntedit.cpp:2118-2138) has no observable effect.
+		S.quiet = false;
+		if (S.s.best_type == 1 && S.p1_fast && !snv_() && S.lin_simple && S.tail_is_pos && !S.dnf && S.n_check == P.k && S.n_rolls >= P.k) {
+			uint32_t c = 0;
+			while (c < 4 && ((S.cands >> (8 * c)) & 0xFF) != S.s.best_sub) {
+				c++;
+			}
+			bool quiet = c < 4;
+			for (uint32_t R = 1; quiet && R + 1 <= P.k; R++) {
+				if (S.tsite[c][R - 1]) {
+					quiet = false;
+				}
+			}
+			S.quiet = quiet;
+		}
+		NTB_LEADER_END
+		return SITE_DONE;
+	}
+
+	// returns false when the contig is finished (insertion guard fired)
+	NTB_FN bool evaluate_site()
+	{
+		if (evaluate_site_core(true) != SITE_DONE) {
+			return true;
+		}
+		NTB_PROF_T0
+		NTB_LEADER_BEGIN
+		site_commit((S.touched && S.raw != S.draft) ? EV_TOUCHED : 0);
 		NTB_LEADER_END
 		NTB_PROF(13);
 		return S.site_ok;
+	}
+
+	// ---------------------------------------------------------------- pre-evaluation (see ntb_common.h: SiteRec)
+	// all lanes: put the walker on the clean window that ends at `pos`, as the main loop's clean branch would (step())
+	NTB_FN void pre_seed(uint32_t pos)
+	{
+		const uint32_t k = P.k, head = pos + 1 - k;
+		NTB_LEADER_BEGIN
+		S.t.pos = pos;
+		S.h.pos = head;
+		reset_rope(head);
+		S.stale_best_sub = STALE_REF | 0;
+		S.stale_alt1 = STALE_REF | 1;
+		S.stale_alt2 = STALE_REF | 2;
+		S.stale_alt3 = STALE_REF | 3;
+		S.la_n = 0;
+		NTB_LEADER_END
+		if (!cache_covers_window()) {
+			fill_cache(head);
+		}
+		uint64_t seed_f = 0, seed_r = 0;
+		const uint64_t* rot = rot_();
+		for (uint32_t i = lane_id(); i < k; i += lane_count()) {
+			const unsigned char c = text_at(head + i);
+			seed_f ^= rot[code_f(c) * ROT_STRIDE + (k - 1 - i)];
+			seed_r ^= rot[code_r(c) * ROT_STRIDE + i];
+		}
+		seed_f = warp_xor64(seed_f);
+		seed_r = warp_xor64(seed_r);
+		NTB_LEADER_BEGIN
+		S.hs.fh = seed_f;
+		S.hs.rh = seed_r;
+		S.char_in = text_at(pos);
+		NTB_LEADER_END
+	}
+
+	// leader: the decision of the site just evaluated, as a record
+	NTB_FN void pre_fill(SiteRec& r, uint32_t state) const
+	{
+		const Site& s = S.s;
+		r.state = (uint8_t)state;
+		r.draft = S.draft;
+		r.flags = 0;
+		r.pad_[0] = r.pad_[1] = 0;
+		r.best_type = 0;
+		r.best_sub = 0;
+		r.support = 0;
+		r.indel_len = 0;
+		for (int i = 0; i < 3; i++) {
+			r.altsupp[i] = 0;
+			r.altbase[i] = 0;
+		}
+		for (int i = 0; i < 5; i++) {
+			r.indel[i] = 0;
+		}
+		if (state != SITE_DONE) {
+			return;
+		}
+		r.flags = (uint8_t)(((S.touched && S.raw != S.draft) ? SITE_FL_TOUCHED : 0) | (S.quiet ? SITE_FL_QUIET : 0));
+		r.best_type = (uint8_t)s.best_type;
+		r.best_sub = s.best_sub;
+		r.support = (uint16_t)s.best_support;
+		r.altsupp[0] = (uint16_t)s.altsupp1;
+		r.altsupp[1] = (uint16_t)s.altsupp2;
+		r.altsupp[2] = (uint16_t)s.altsupp3;
+		r.altbase[0] = s.altbase1;
+		r.altbase[1] = s.altbase2;
+		r.altbase[2] = s.altbase3;
+		r.indel_len = s.indel_len;
+		for (int i = 0; i < 5; i++) {
+			r.indel[i] = s.indel[i];
+		}
+	}
+
+	// Which flagged positions are pre-evaluated.  An error makes (up to) k consecutive windows absent; once the first of
+	// them is corrected the main loop never evaluates the others, so a flagged position with another one less than k in
+	// front of it is usually not a site at all.  Items therefore start at HEADS -- flagged positions with no flagged
+	// position among the pre_gap() = k-1 positions in front of them -- and follow the main loop from there: while a site
+	// ends without an edit, the next flagged position is evaluated too if it lies within pre_gap() (a farther one is a head
+	// of its own).
+	NTB_FN uint32_t pre_gap() const { return P.k - 1; }
+
+	// is `pos` (a flagged tail position of the contig at text offset goff) a head?
+	NTB_FN static bool is_head(const uint32_t* visit, uint64_t goff, uint32_t pos, uint32_t gap)
+	{
+		const uint64_t g1 = goff + pos;
+		const uint64_t g0 = goff + (pos > gap ? pos - gap : 0);
+		if (g0 >= g1) {
+			return true;
+		}
+		for (uint64_t w = g0 >> 5; (w << 5) < g1; w++) {
+			uint32_t bits = visit[w];
+			if (w == (g0 >> 5)) {
+				bits &= 0xFFFFFFFFu << (g0 & 31);
+			}
+			if (((w + 1) << 5) > g1) {
+				bits &= 0xFFFFFFFFu >> (32 - (g1 & 31));
+			}
+			if (bits) {
+				return false;
+			}
+		}
+		return true;
+	}
+
+	// all lanes; first pass: the site at head `pos` and the chain behind it.  Sites that reach tryIndels are left to the
+	// second pass and the chain goes on as if they had failed; if they do not, the records behind them are simply never
+	// looked up.
+	NTB_FN void pre_run(uint32_t task_idx, uint32_t pos)
+	{
+		for (uint32_t n = 0; n < SITE_CHAIN_MAX; n++) {
+			pre_seed(pos);
+			const uint32_t st = evaluate_site_core(false);
+			NTB_LEADER_BEGIN
+			const uint32_t slot = site_table_insert(S.io.table, S.io.table_mask, S.io.goff + pos + 1);
+			S.rec_slot = slot;
+			if (slot == NONE32) {
+#if defined(__CUDA_ARCH__)
+				atomicAdd(&S.io.ctr->n_dropped, 1u);
+#else
+				S.io.ctr->n_dropped++;
+#endif
+			} else {
+				SiteRec r;
+				r.key = S.io.goff + pos + 1;
+				pre_fill(r, st);
+				if (st == SITE_PENDING) {
+					uint32_t idx;
+#if defined(__CUDA_ARCH__)
+					idx = atomicAdd(&S.io.ctr->n_pending, 1u);
+#else
+					idx = S.io.ctr->n_pending++;
+#endif
+					if (idx < S.io.pending_cap) {
+						PendingSite ps;
+						ps.task = task_idx;
+						ps.pos = pos;
+						ps.slot = slot;
+						S.io.pending[idx] = ps;
+					}
+				}
+				S.io.table[slot] = r;
+			}
+			// go on behind a site that made no edit (or whose tryIndels are still to come)
+			S.pre_more = slot != NONE32 && (st != SITE_DONE || S.s.best_type == 0);
+			NTB_LEADER_END
+			if (!S.pre_more) {
+				break;
+			}
+			const uint32_t lim = S.io.len - pos - 1 < pre_gap() ? S.io.len : pos + 1 + pre_gap();
+			pos = next_visit(pos + 1, lim);
+			if (pos == NONE32) {
+				break;
+			}
+		}
+	}
+
+	// all lanes; second pass: the whole evaluation of a site the first pass left in front of tryIndels
+	NTB_FN void pre_finish(uint32_t pos, uint32_t slot)
+	{
+		pre_seed(pos);
+		const uint32_t st = evaluate_site_core(true);
+		NTB_LEADER_BEGIN
+		SiteRec r;
+		r.key = S.io.goff + pos + 1;
+		pre_fill(r, st);
+		S.io.table[slot] = r;
+		NTB_LEADER_END
+	}
+
+	// all lanes: the record of text position g (nullptr when there is none or it is not complete)
+	NTB_FN const SiteRec* find_record(uint64_t g) const
+	{
+		const SiteRec* table = S.io.table;
+		if (!table) {
+			return nullptr;
+		}
+		const uint64_t key = g + 1;
+		const uint32_t mask = S.io.table_mask;
+		const uint32_t h0 = site_hash(key);
+		for (uint32_t i0 = 0; i0 < SITE_TABLE_PROBES; i0 += lane_count()) {
+			const uint32_t slot = (h0 + i0 + lane_id()) & mask;
+			const uint64_t seen = table[slot].key;
+#if defined(__CUDA_ARCH__)
+			// an inserted key sits in front of the first empty slot of its probe sequence
+			const uint32_t hit = __ballot_sync(team_mask(), seen == key) >> team_base();
+			const uint32_t empty = __ballot_sync(team_mask(), seen == 0) >> team_base();
+			if (hit) {
+				const uint32_t src = (uint32_t)__ffs((int)hit) - 1u;
+				const SiteRec* r = &table[(h0 + i0 + src) & mask];
+				return r->state == SITE_NONE || r->state == SITE_DONE ? r : nullptr;
+			}
+			if (empty) {
+				return nullptr;
+			}
+#else
+			if (seen == key) {
+				return table[slot].state == SITE_NONE || table[slot].state == SITE_DONE ? &table[slot] : nullptr;
+			}
+			if (seen == 0) {
+				return nullptr;
+			}
+#endif
+		}
+		return nullptr;
+	}
+
+	// leader: take the decision of the site at the tail from record r (evaluate_site_core ran ahead of the walk)
+	NTB_FN void load_record(const SiteRec& r)
+	{
+		S.n_sites++;
+		if (S.first_touch == NONE32) {
+			S.first_touch = S.t.pos;
+		}
+		S.site_ok = true;
+		S.skip_advance = false;
+		S.use_rec = r.state;
+		S.rec_hash = r.state == SITE_DONE && (r.best_type >= 2 || (r.best_type == 1 && !(r.flags & SITE_FL_QUIET)));
+		if (r.state != SITE_DONE) {
+			return;
+		}
+		const uint8_t stale[4] = { S.stale_best_sub, S.stale_alt1, S.stale_alt2, S.stale_alt3 };
+		Site& s = S.s;
+		s.best_type = r.best_type;
+		s.best_support = r.support;
+		s.altsupp1 = r.altsupp[0];
+		s.altsupp2 = r.altsupp[1];
+		s.altsupp3 = r.altsupp[2];
+		// bytes the record left symbolic are the ones this walker's previous site left behind (STALE_REF)
+		s.best_sub = (r.best_sub & STALE_REF) ? stale[r.best_sub & 3] : r.best_sub;
+		s.altbase1 = (r.altbase[0] & STALE_REF) ? stale[r.altbase[0] & 3] : r.altbase[0];
+		s.altbase2 = (r.altbase[1] & STALE_REF) ? stale[r.altbase[1] & 3] : r.altbase[1];
+		s.altbase3 = (r.altbase[2] & STALE_REF) ? stale[r.altbase[2] & 3] : r.altbase[2];
+		s.indel_len = r.indel_len;
+		for (int i = 0; i < 5; i++) {
+			s.indel[i] = r.indel[i];
+		}
+		S.draft = r.draft;
+		S.rec_fl = (r.flags & SITE_FL_TOUCHED) ? EV_TOUCHED : 0;
+		S.quiet = (r.flags & SITE_FL_QUIET) != 0;
+		S.tail_is_pos = true;
+		S.tail_is_chr = false;
 	}
 
 	// ---------------------------------------------------------------- clean-window handling
@@ -2193,6 +2548,38 @@ struct Walker
 		return b;
 	}
 
+	// leader: the per-walker seed tables
+	NTB_FN void init_tables()
+	{
+		for (unsigned c = 0; c < 8; c++) {
+			S.seed_tab[c] = c < 4 ? seed_of_code(c) : 0;
+			S.rotk_tab[c] = c < 4 ? P.seed_rot_k[c] : 0;
+		}
+	}
+
+	// every lane: get ready for pre_run() / pre_finish() on the contig S.io describes
+	NTB_FN void pre_begin()
+	{
+		NTB_LEADER_BEGIN
+		init_tables();
+		S.nn = 0;
+		S.ov_n = 0;
+		S.adv = 0;
+		S.anchored = true;
+		S.last_event = NONE32;
+		S.n_events = S.n_sites = 0;
+		S.first_touch = NONE32;
+		S.status = 0;
+		S.tc_base = 0;
+		S.tc_n = 0;
+		S.la_n = S.la_used = S.la_bits = 0;
+		S.use_rec = 0;
+		S.quiet = false;
+		S.need_seed = false;
+		S.h.ni = S.t.ni = 0;
+		NTB_LEADER_END
+	}
+
 	// ---------------------------------------------------------------- the main loop, ntedit.cpp:1797-2139
 	// leader: start of a task
 	NTB_FN void task_begin(const Task& task)
@@ -2224,13 +2611,12 @@ struct Walker
 		S.la_used = 0;
 		S.la_bits = 0;
 		S.act = ACT_CLEAN;
+		S.use_rec = 0;
+		S.quiet = false;
 		S.h.ni = S.t.ni = 0;
 		S.t_start = (P.boundary_lim && (task.flags & TASK_ADJUST_START)) ? safe_boundary(task.start) : task.start;
 		S.t_end = (P.boundary_lim && (task.flags & TASK_ADJUST_END)) ? safe_boundary(task.end) : task.end;
-		for (unsigned c = 0; c < 8; c++) {
-			S.seed_tab[c] = c < 4 ? seed_of_code(c) : 0;
-			S.rotk_tab[c] = c < 4 ? P.seed_rot_k[c] : 0;
-		}
+		init_tables();
 		if (task.flags & TASK_CONTIG_START) {
 			const uint32_t h0 = first_accepted_kmer();
 			if ((uint64_t)h0 + k - 1 >= S.io.len) {
@@ -2283,6 +2669,7 @@ struct Walker
 				return;
 			}
 		}
+		S.use_rec = 0;
 		S.act = ACT_DIRTY;
 	}
 
@@ -2431,6 +2818,7 @@ struct Walker
 			} else {
 				S.do_seed = nv != S.t.pos || S.need_seed;
 				S.visit_hit = nv;
+				S.use_rec = 0;
 				if (S.do_seed) {
 					S.t.pos = nv;
 					S.h.pos = nv + 1 - P.k;
@@ -2441,12 +2829,20 @@ struct Walker
 			if (S.act == ACT_STOP) {
 				return false;
 			}
-			if (!cache_covers_window()) {
+			// decided ahead of the walk (pre-evaluation pass)?  Most such sites commit without the window's hash or its text
+			const SiteRec* rec = find_record(S.io.goff + S.visit_hit);
+			if (rec) {
+				NTB_LEADER_BEGIN
+				load_record(*rec);
+				NTB_LEADER_END
+			}
+			const bool need_hash = !S.use_rec || S.rec_hash;
+			if (need_hash && !cache_covers_window()) {
 				fill_cache(S.h.pos);
 			}
 			NTB_PROF(2);
 			uint64_t seed_f = 0, seed_r = 0;
-			if (S.do_seed) {
+			if (S.do_seed && need_hash) {
 				// NTMC64 seeding form (ntedit.cpp:403-416) of the unedited window that ends at the flagged position:
 				// every lane contributes its bases' terms from the rotation table
 				const uint32_t k = P.k, head = S.visit_hit + 1 - k;
@@ -2463,11 +2859,15 @@ struct Walker
 			if (S.do_seed) {
 				S.h.pos = S.visit_hit + 1 - P.k;
 				S.t.pos = S.visit_hit;
-				S.hs.fh = seed_f;
-				S.hs.rh = seed_r;
-				S.char_in = text_at(S.visit_hit);
+				if (need_hash) {
+					S.hs.fh = seed_f;
+					S.hs.rh = seed_r;
+					S.char_in = text_at(S.visit_hit);
+				}
 				reset_rope(S.h.pos);
 				S.site_now = true; // K1 flagged this very window
+			} else if (S.use_rec) {
+				S.site_now = true;
 			} else if (snv_()) {
 				S.site_now = true;
 			} else if (counting_()) {
@@ -2500,7 +2900,23 @@ struct Walker
 		}
 		NTB_PROF(5);
 		if (S.site_now) {
-			if (!evaluate_site()) {
+			bool ok;
+			if (S.use_rec) {
+				NTB_LEADER_BEGIN
+				if (S.use_rec == SITE_DONE) {
+					site_commit(S.rec_fl);
+				}
+#if defined(NTB_PHASE_PROF) && defined(__CUDA_ARCH__)
+				atomicAdd(&S.io.ctr->n_rec_used, 1u);
+#elif !defined(__CUDA_ARCH__)
+				S.io.ctr->n_rec_used++;
+#endif
+				NTB_LEADER_END
+				ok = S.site_ok;
+			} else {
+				ok = evaluate_site();
+			}
+			if (!ok) {
 				NTB_LEADER_BEGIN
 				S.status |= ST_CONTIG_END;
 				S.act = ACT_STOP;

@@ -2,6 +2,7 @@
 #include "kernels.cuh"
 
 #include <cstdlib>
+#include <mutex>
 
 namespace ntb {
 
@@ -55,6 +56,47 @@ ld_filter_u8(const uint8_t* p)
 	uint32_t v;
 	asm volatile("ld.global.nc.L1::no_allocate.u8 %0, [%1];" : "=r"(v) : "l"(p));
 	return v;
+}
+
+// Resident CTAs per SM of a kernel on the CURRENT device (after raising its dynamic shared memory limit to `smem`).  cudaFuncSetAttribute is per device (and per
+// context), so the result is cached per (kernel, device): a process that drives several GPUs from several host threads
+// (ntedit-b200 --gpus N) sets the attribute on each of them.
+constexpr int NTB_MAX_DEVICES = 64;
+struct OccCache
+{
+	std::mutex lock;
+	int per_sm[NTB_MAX_DEVICES] = {};
+};
+
+template<class Kernel>
+static cudaError_t
+walker_occupancy(Kernel kernel, OccCache& cache, size_t smem, int threads, int* out)
+{
+	int dev = 0;
+	cudaError_t e = cudaGetDevice(&dev);
+	if (e != cudaSuccess) {
+		return e;
+	}
+	if (dev < 0 || dev >= NTB_MAX_DEVICES) {
+		return cudaErrorInvalidDevice;
+	}
+	std::lock_guard<std::mutex> guard(cache.lock);
+	if (cache.per_sm[dev] == 0) {
+		if (smem > 0) {
+			e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+			if (e != cudaSuccess) {
+				return e;
+			}
+		}
+		int n = 0;
+		e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, threads, smem);
+		if (e != cudaSuccess) {
+			return e;
+		}
+		cache.per_sm[dev] = n > 0 ? n : 1;
+	}
+	*out = cache.per_sm[dev];
+	return cudaSuccess;
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -707,20 +749,17 @@ launch_probe_bin(const BinArgs& a, bool counting, int grid_probe, cudaStream_t s
 {
 	cudaError_t e;
 	// cooperative launch: all CTAs resident (the kernel paces itself across CTAs); grid_probe = CTAs per SM wanted
-	static int per_sm[2] = { 0, 0 };
+	static OccCache cache[2];
 	const void* fn = counting ? (const void*)probe_bin_kernel<true> : (const void*)probe_bin_kernel<false>;
-	if (per_sm[counting ? 1 : 0] == 0) {
-		int n = 0;
-		e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fn, 256, 0);
-		if (e != cudaSuccess) {
-			return e;
-		}
-		per_sm[counting ? 1 : 0] = n > 0 ? n : 1;
+	int per_sm = 0;
+	e = walker_occupancy(fn, cache[counting ? 1 : 0], 0, 256, &per_sm);
+	if (e != cudaSuccess) {
+		return e;
 	}
 	int dev = 0, sms = 148;
 	cudaGetDevice(&dev);
 	cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-	const int want = grid_probe > 0 && grid_probe < per_sm[counting ? 1 : 0] ? grid_probe : per_sm[counting ? 1 : 0];
+	const int want = grid_probe > 0 && grid_probe < per_sm ? grid_probe : per_sm;
 	BinArgs args = a;
 	void* params[1] = { (void*)&args };
 	return cudaLaunchCooperativeKernel(fn, dim3((unsigned)(sms * want)), dim3(256), params, 0, stream);
@@ -731,26 +770,158 @@ launch_probe_bin(const BinArgs& a, bool counting, int grid_probe, cudaStream_t s
 // K2: persistent warps, one task (contig segment) per warp at a time, tasks handed out through an atomic counter.
 // The walker state of every warp lives in shared memory (engine.h: WalkerState); lane 0 is the leader.
 // NCAP (capacity of the local rope copy) is 2.5 k + 32 rounded up: 160 serves k <= 48, 352 serves k <= KMAX.
+// the CTA's copy of the parameters, the rotation table and the class table in front of the team states (engine.h finds them
+// by this layout); ends with a CTA barrier
+__device__ __forceinline__ void
+walk_smem_init(uint8_t* walk_smem, const KParams& kp)
+{
+	for (uint32_t q = threadIdx.x; q < 256; q += blockDim.x) {
+		walk_smem[WALK_KP_BYTES + WALK_ROT_BYTES + q] = class_of(q);
+	}
+	uint64_t* rot = reinterpret_cast<uint64_t*>(walk_smem + WALK_KP_BYTES);
+	for (uint32_t q = threadIdx.x; q < sizeof(KParams) / 4; q += blockDim.x) {
+		reinterpret_cast<uint32_t*>(walk_smem)[q] = reinterpret_cast<const uint32_t*>(&kp)[q];
+	}
+	for (uint32_t q = threadIdx.x; q < ROT_WORDS; q += blockDim.x) {
+		rot[q] = rot_entry(q);
+	}
+	__syncthreads();
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Pre-evaluation (ntb_common.h: SiteRec; engine.h: pre_run / pre_finish).
+// heads_kernel: one warp per task lists the heads of its nominal range [start, end) -- the ranges partition every contig.
+__global__ void __launch_bounds__(256)
+heads_kernel(const uint32_t* visit, const Task* tasks, uint32_t n_tasks, uint32_t gap, uint2* items, uint32_t cap, Counters* ctr)
+{
+	const uint32_t lane = threadIdx.x & 31u;
+	const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+	for (uint32_t ti = warp; ti < n_tasks; ti += n_warps) {
+		const Task t = tasks[ti];
+		const uint64_t g0 = t.text_off + t.start, g1 = t.text_off + t.end;
+		for (uint64_t w0 = g0 >> 5; (w0 << 5) < g1; w0 += 32) {
+			const uint64_t w = w0 + lane;
+			uint32_t bits = (w << 5) < g1 ? visit[w] : 0u;
+			if (w == (g0 >> 5)) {
+				bits &= 0xFFFFFFFFu << (g0 & 31);
+			}
+			if (((w + 1) << 5) > g1 && (w << 5) < g1) {
+				bits &= 0xFFFFFFFFu >> (32 - (g1 & 31));
+			}
+			// keep the flagged positions that are heads
+			uint32_t heads = 0;
+			for (uint32_t rest = bits; rest; rest &= rest - 1) {
+				const uint32_t b = (uint32_t)__ffs((int)rest) - 1u;
+				const uint32_t pos = (uint32_t)((w << 5) + b - t.text_off);
+				if (Walker<160>::is_head(visit, t.text_off, pos, gap)) {
+					heads |= 1u << b;
+				}
+			}
+			// warp-aggregated append
+			const uint32_t n = (uint32_t)__popc(heads);
+			uint32_t incl = n;
+#pragma unroll
+			for (int o = 1; o < 32; o <<= 1) {
+				const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+				if (lane >= (uint32_t)o) {
+					incl += v;
+				}
+			}
+			const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+			if (total == 0) {
+				continue;
+			}
+			uint32_t base = 0;
+			if (lane == 0) {
+				base = atomicAdd(&ctr->n_items, total);
+			}
+			base = __shfl_sync(0xFFFFFFFFu, base, 0) + incl - n;
+			for (uint32_t rest = heads; rest; rest &= rest - 1, base++) {
+				if (base < cap) {
+					items[base] = make_uint2(ti, (uint32_t)((w << 5) + ((uint32_t)__ffs((int)rest) - 1u) - t.text_off));
+				}
+			}
+		}
+	}
+}
+
+// presite_kernel<.., SECOND = false>: first pass, one item (head + chain) per warp at a time, tryIndels left out of the code;
+// <.., SECOND = true>: second pass over the sites the first one left pending.  Same shared-memory layout and persistent-warp
+// scheme as walk_kernel.
+template<int NCAP, bool COMMON, bool POW2, bool SECOND>
+__global__ void __launch_bounds__(WALK_THREADS, NTB_WALK_MIN_CTAS)
+presite_kernel(const uint8_t* text, const uint32_t* visit, FilterView bloom, FilterView rep, const __grid_constant__ KParams kp,
+               const Task* tasks, const uint2* items, uint32_t items_cap, SiteRec* table, uint32_t table_mask, PendingSite* pending,
+               uint32_t pending_cap, Counters* ctr)
+{
+	extern __shared__ __align__(16) uint8_t walk_smem[];
+	WalkerState<NCAP>* states = reinterpret_cast<WalkerState<NCAP>*>(walk_smem + WALK_KP_BYTES + WALK_ROT_BYTES + WALK_CLS_BYTES);
+	walk_smem_init(walk_smem, kp);
+	WalkerState<NCAP>& S = states[threadIdx.x / NTB_TEAM];
+	const uint64_t* rot = reinterpret_cast<const uint64_t*>(walk_smem + WALK_KP_BYTES);
+	const uint32_t lane = lane_id();
+	Walker<NCAP, COMMON, POW2> w(S, kp);
+	const uint32_t n_units = SECOND ? min(ctr->n_pending, pending_cap) : min(ctr->n_items, items_cap);
+	for (;;) {
+		uint32_t i = 0;
+		if (lane == 0) {
+			i = atomicAdd(SECOND ? &ctr->next_pending : &ctr->next_item, 1u);
+		}
+		i = __shfl_sync(team_mask(), i, (int)team_base());
+		if (i >= n_units) {
+			break;
+		}
+		uint32_t ti, pos, slot = 0;
+		if (SECOND) {
+			const PendingSite ps = pending[i];
+			ti = ps.task;
+			pos = ps.pos;
+			slot = ps.slot;
+		} else {
+			const uint2 it = items[i];
+			ti = it.x;
+			pos = it.y;
+		}
+		const Task task = tasks[ti];
+		warp_sync();
+		if (lane == 0) {
+			S.io.text = text + task.text_off;
+			S.io.len = task.len;
+			S.io.visit = visit;
+			S.io.goff = task.text_off;
+			S.io.bloom = bloom;
+			S.io.rep = rep;
+			S.io.events = nullptr;
+			S.io.ev_cap = 0;
+			S.io.ctr = ctr;
+			S.io.rot = rot;
+			S.io.table = table;
+			S.io.table_mask = table_mask;
+			S.io.pending = pending;
+			S.io.pending_cap = pending_cap;
+		}
+		warp_sync();
+		w.pre_begin();
+		if (SECOND) {
+			w.pre_finish(pos, slot);
+		} else {
+			w.pre_run(ti, pos);
+		}
+	}
+}
+
 template<int NCAP, bool COMMON, bool POW2>
 __global__ void __launch_bounds__(WALK_THREADS, NTB_WALK_MIN_CTAS)
 walk_kernel(const uint8_t* text, const uint32_t* visit, FilterView bloom, FilterView rep, const __grid_constant__ KParams kp,
-            const Task* tasks, const uint32_t* order, TaskResult* results, uint32_t n_tasks, Event* events, uint32_t ev_cap, Counters* ctr)
+            const Task* tasks, const uint32_t* order, TaskResult* results, uint32_t n_tasks, Event* events, uint32_t ev_cap, Counters* ctr,
+            SiteRec* table, uint32_t table_mask)
 {
 	extern __shared__ __align__(16) uint8_t walk_smem[];
 	// [KParams copy][rotation table][class table][team states] -- engine.h's Walker finds all of them by this layout
 	WalkerState<NCAP>* states = reinterpret_cast<WalkerState<NCAP>*>(walk_smem + WALK_KP_BYTES + WALK_ROT_BYTES + WALK_CLS_BYTES);
-	for (uint32_t q = threadIdx.x; q < 256; q += WALK_THREADS) {
-		walk_smem[WALK_KP_BYTES + WALK_ROT_BYTES + q] = class_of(q);
-	}
+	walk_smem_init(walk_smem, kp);
 	WalkerState<NCAP>& S = states[threadIdx.x / NTB_TEAM];
-	uint64_t* rot = reinterpret_cast<uint64_t*>(walk_smem + WALK_KP_BYTES);
-	for (uint32_t q = threadIdx.x; q < sizeof(KParams) / 4; q += WALK_THREADS) {
-		reinterpret_cast<uint32_t*>(walk_smem)[q] = reinterpret_cast<const uint32_t*>(&kp)[q];
-	}
-	for (uint32_t q = threadIdx.x; q < ROT_WORDS; q += WALK_THREADS) {
-		rot[q] = rot_entry(q);
-	}
-	__syncthreads();
+	const uint64_t* rot = reinterpret_cast<const uint64_t*>(walk_smem + WALK_KP_BYTES);
 	const uint32_t lane = lane_id();
 	Walker<NCAP, COMMON, POW2> w(S, kp);
 	bool have = false;
@@ -781,6 +952,10 @@ walk_kernel(const uint8_t* text, const uint32_t* visit, FilterView bloom, Filter
 					S.io.ev_cap = ev_cap;
 					S.io.ctr = ctr;
 					S.io.rot = rot;
+					S.io.table = table;
+					S.io.table_mask = table_mask;
+					S.io.pending = nullptr;
+					S.io.pending_cap = 0;
 				}
 				warp_sync();
 				c0 = clock64();
@@ -879,68 +1054,123 @@ launch_compact_events(const Event* in, Event* out, TaskResult* results, uint32_t
 	return cudaGetLastError();
 }
 
+template<int NCAP>
+static size_t
+walk_smem_bytes()
+{
+	return WALK_KP_BYTES + WALK_ROT_BYTES + WALK_CLS_BYTES + (size_t)WALK_TEAMS * sizeof(WalkerState<NCAP>);
+}
+
 template<int NCAP, bool COMMON, bool POW2>
 static cudaError_t
-launch_walk_n(const uint8_t* text, const uint32_t* visit, const FilterView& bloom, const FilterView& rep, const KParams& kp, const Task* tasks,
-              const uint32_t* order, TaskResult* results, uint32_t n_tasks, Event* events, uint32_t ev_cap, Counters* ctr, int sm_count,
-              cudaStream_t stream)
+launch_walk_n(const WalkArgs& a, cudaStream_t stream)
 {
-	static int blocks_per_sm = 0;
-	const size_t smem = WALK_KP_BYTES + WALK_ROT_BYTES + WALK_CLS_BYTES + (size_t)WALK_TEAMS * sizeof(WalkerState<NCAP>);
-	if (blocks_per_sm == 0) {
-		cudaError_t e = cudaFuncSetAttribute(walk_kernel<NCAP, COMMON, POW2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-		if (e != cudaSuccess) {
-			return e;
-		}
-		int n = 0;
-		e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, walk_kernel<NCAP, COMMON, POW2>, WALK_THREADS, smem);
-		if (e != cudaSuccess) {
-			return e;
-		}
-		blocks_per_sm = n > 0 ? n : 1;
-		if (const char* cap = std::getenv("NTB_WALK_BLOCKS_PER_SM")) { // tuning aid
-			const int c = std::atoi(cap);
-			if (c > 0 && c < blocks_per_sm) {
-				blocks_per_sm = c;
-			}
+	static OccCache cache;
+	const size_t smem = walk_smem_bytes<NCAP>();
+	int blocks_per_sm = 0;
+	cudaError_t e = walker_occupancy(walk_kernel<NCAP, COMMON, POW2>, cache, smem, WALK_THREADS, &blocks_per_sm);
+	if (e != cudaSuccess) {
+		return e;
+	}
+	if (const char* cap = std::getenv("NTB_WALK_BLOCKS_PER_SM")) { // tuning aid
+		const int c = std::atoi(cap);
+		if (c > 0 && c < blocks_per_sm) {
+			blocks_per_sm = c;
 		}
 	}
-	const uint64_t want = ((uint64_t)n_tasks + WALK_TEAMS - 1) / WALK_TEAMS;
-	const uint64_t cap = (uint64_t)sm_count * (uint64_t)blocks_per_sm;
+	const uint64_t want = ((uint64_t)a.n_tasks + WALK_TEAMS - 1) / WALK_TEAMS;
+	const uint64_t cap = (uint64_t)a.sm_count * (uint64_t)blocks_per_sm;
 	const unsigned grid = (unsigned)(want < cap ? want : cap);
 	if (grid == 0) {
 		return cudaSuccess;
 	}
-	walk_kernel<NCAP, COMMON, POW2><<<grid, WALK_THREADS, smem, stream>>>(text, visit, bloom, rep, kp, tasks, order, results, n_tasks, events, ev_cap, ctr);
+	walk_kernel<NCAP, COMMON, POW2><<<grid, WALK_THREADS, smem, stream>>>(a.text, a.visit, a.bloom, a.rep, a.kp, a.tasks, a.order, a.results,
+	                                                                      a.n_tasks, a.events, a.ev_cap, a.ctr, a.table, a.table_mask);
 	return cudaGetLastError();
 }
 
-cudaError_t
-launch_walk(const uint8_t* text, const uint32_t* visit, const FilterView& bloom, const FilterView& rep, const KParams& kp, const Task* tasks,
-            uint32_t* order, TaskResult* results, uint32_t n_tasks, Event* events, uint32_t ev_cap, Counters* ctr, int sm_count,
-            cudaStream_t stream)
+template<int NCAP, bool COMMON, bool POW2, bool SECOND>
+static cudaError_t
+launch_presite_n(const WalkArgs& a, cudaStream_t stream)
 {
-	if (order && n_tasks) {
-		order_tasks_kernel<<<(n_tasks + 255) / 256, 256, 0, stream>>>(visit, tasks, n_tasks, 24u, order, ctr);
+	static OccCache cache;
+	const size_t smem = walk_smem_bytes<NCAP>();
+	int blocks_per_sm = 0;
+	cudaError_t e = walker_occupancy(presite_kernel<NCAP, COMMON, POW2, SECOND>, cache, smem, WALK_THREADS, &blocks_per_sm);
+	if (e != cudaSuccess) {
+		return e;
+	}
+	// persistent grid: the number of items is only known on the device
+	const unsigned grid = (unsigned)(a.sm_count * blocks_per_sm);
+	presite_kernel<NCAP, COMMON, POW2, SECOND><<<grid, WALK_THREADS, smem, stream>>>(a.text, a.visit, a.bloom, a.rep, a.kp, a.tasks, a.items,
+	                                                                                a.items_cap, a.table, a.table_mask, a.pending,
+	                                                                                a.pending_cap, a.ctr);
+	return cudaGetLastError();
+}
+
+// the specialised instantiations serve the common configuration (see engine.h: Walker<NCAP, COMMON, POW2>)
+#define NTB_WALK_DISPATCH(FN, ...)                                                                   \
+	do {                                                                                             \
+		const bool common = !a.kp.counting && !a.kp.h_rep && !a.kp.snv && !a.kp.mask;                \
+		const bool pow2 = common && a.bloom.mask != 0;                                               \
+		if (a.kp.k <= 48) {                                                                          \
+			return pow2     ? FN<160, true, true __VA_ARGS__>(a, stream)                             \
+			       : common ? FN<160, true, false __VA_ARGS__>(a, stream)                            \
+			                : FN<160, false, false __VA_ARGS__>(a, stream);                          \
+		}                                                                                            \
+		return pow2     ? FN<352, true, true __VA_ARGS__>(a, stream)                                 \
+		       : common ? FN<352, true, false __VA_ARGS__>(a, stream)                                \
+		                : FN<352, false, false __VA_ARGS__>(a, stream);                              \
+	} while (0)
+
+cudaError_t
+launch_walk(const WalkArgs& a, cudaStream_t stream)
+{
+	if (a.order && a.n_tasks) {
+		order_tasks_kernel<<<(a.n_tasks + 255) / 256, 256, 0, stream>>>(a.visit, a.tasks, a.n_tasks, 24u, a.order, a.ctr);
 		cudaError_t e = cudaGetLastError();
 		if (e != cudaSuccess) {
 			return e;
 		}
 	}
-	// the specialised instantiations serve the common configuration (see engine.h: Walker<NCAP, COMMON, POW2>)
-	const bool common = !kp.counting && !kp.h_rep && !kp.snv && !kp.mask;
-	const bool pow2 = common && bloom.mask != 0;
-#define NTB_WALK_ARGS text, visit, bloom, rep, kp, tasks, order, results, n_tasks, events, ev_cap, ctr, sm_count, stream
-	if (kp.k <= 48) {
-		return pow2     ? launch_walk_n<160, true, true>(NTB_WALK_ARGS)
-		       : common ? launch_walk_n<160, true, false>(NTB_WALK_ARGS)
-		                : launch_walk_n<160, false, false>(NTB_WALK_ARGS);
-	}
-	return pow2     ? launch_walk_n<352, true, true>(NTB_WALK_ARGS)
-	       : common ? launch_walk_n<352, true, false>(NTB_WALK_ARGS)
-	                : launch_walk_n<352, false, false>(NTB_WALK_ARGS);
-#undef NTB_WALK_ARGS
+	NTB_WALK_DISPATCH(launch_walk_n);
 }
+
+cudaError_t
+launch_heads(const WalkArgs& a, cudaStream_t stream)
+{
+	if (a.n_tasks == 0) {
+		return cudaSuccess;
+	}
+	const unsigned warps_per_cta = 8;
+	const unsigned want = (a.n_tasks + warps_per_cta - 1) / warps_per_cta;
+	const unsigned cap = (unsigned)a.sm_count * 8u;
+	heads_kernel<<<want < cap ? want : cap, warps_per_cta * 32, 0, stream>>>(a.visit, a.tasks, a.n_tasks, a.kp.k - 1, a.items, a.items_cap, a.ctr);
+	return cudaGetLastError();
+}
+
+static cudaError_t
+launch_presite_first(const WalkArgs& a, cudaStream_t stream)
+{
+#define NTB_COMMA_FALSE , false
+	NTB_WALK_DISPATCH(launch_presite_n, NTB_COMMA_FALSE);
+#undef NTB_COMMA_FALSE
+}
+
+static cudaError_t
+launch_presite_second(const WalkArgs& a, cudaStream_t stream)
+{
+#define NTB_COMMA_TRUE , true
+	NTB_WALK_DISPATCH(launch_presite_n, NTB_COMMA_TRUE);
+#undef NTB_COMMA_TRUE
+}
+
+cudaError_t
+launch_presite(const WalkArgs& a, bool second, cudaStream_t stream)
+{
+	return second ? launch_presite_second(a, stream) : launch_presite_first(a, stream);
+}
+#undef NTB_WALK_DISPATCH
 
 // ------------------------------------------------------------------------------------------------------------------
 // K5: filter construction.  One thread per strip of INSERT_STRIP positions.

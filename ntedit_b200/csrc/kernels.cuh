@@ -4,8 +4,10 @@
 //   K1b bin_kernel + probe_bin_kernel : the same bitmap for filters larger than L2 -- probes become records bucketed by filter
 //                           region, then are served bucket by bucket from the L2-resident region (a direct probe costs a 128-byte
 //                           DRAM line on B200)
-//   K2  walk_kernel       : one warp per contig segment replays the edit state machine (engine.h) at the flagged positions, one
-//                           candidate k-mer series per lane
+//   K2p heads_kernel + presite_kernel (two passes) : the evaluation of every site the walk can reach with a clean window,
+//                           ahead of the walk, into a table of site records (ntb_common.h: SiteRec)
+//   K2  walk_kernel       : one warp per contig segment replays the edit state machine (engine.h) at the flagged positions:
+//                           commits pre-evaluated sites, evaluates the others (dirty windows) one candidate k-mer series per lane
 //                           replaces ntedit.cpp:1808-2116 (check-missing, substitutions, tryIndels, tryDeletion, makeEdit decisions)
 //       order_tasks_kernel, compact_events_kernel : work-queue order in front of K2, per-walker grouping of its events behind it
 //   K4  occupancy_kernel  : popcount / non-zero count of the filter (btllib get_fpr, printed by ntedit.cpp:387-395)
@@ -108,11 +110,40 @@ constexpr int WALK_WARPS = NTB_WALK_WARPS;
 constexpr int WALK_THREADS = WALK_WARPS * 32;
 constexpr int WALK_TEAMS = WALK_THREADS / NTB_TEAM;   // walkers per CTA (engine.h: a team of NTB_TEAM lanes runs one walker)
 
-// orders the tasks (dense ones first) into `order` (n_tasks entries, may be NULL = queue order) and launches the walker
-// kernel on a persistent grid sized from its occupancy; 2 launches
-cudaError_t launch_walk(const uint8_t* text, const uint32_t* visit, const FilterView& bloom, const FilterView& rep, const KParams& kp,
-                        const Task* tasks, uint32_t* order, TaskResult* results, uint32_t n_tasks, Event* events, uint32_t ev_cap,
-                        Counters* ctr, int sm_count, cudaStream_t stream);
+// arguments of the walker-layout kernels (K2 and the pre-evaluation passes in front of it)
+struct WalkArgs
+{
+	const uint8_t* text;
+	const uint32_t* visit;
+	FilterView bloom, rep;
+	KParams kp;
+	const Task* tasks;
+	uint32_t* order;          // n_tasks entries, may be NULL = queue order
+	TaskResult* results;
+	uint32_t n_tasks;
+	Event* events;
+	uint32_t ev_cap;
+	Counters* ctr;
+	int sm_count;
+	// pre-evaluated sites (ntb_common.h: SiteRec); table == NULL: none
+	SiteRec* table;
+	uint32_t table_mask;
+	uint2* items;             // heads listed by launch_heads: (task, tail position)
+	uint32_t items_cap;
+	PendingSite* pending;
+	uint32_t pending_cap;
+};
+
+// orders the tasks (dense ones first) into `order` and launches the walker kernel on a persistent grid sized from its
+// occupancy; 2 launches
+cudaError_t launch_walk(const WalkArgs& a, cudaStream_t stream);
+
+// pre-evaluation in front of the first walker round: launch_heads lists the heads of every task's nominal range
+// (ctr->n_items), launch_presite(second = false) evaluates them and the chains behind them into the table, leaving the
+// sites that reach tryIndels in `pending` (ctr->n_pending), launch_presite(second = true) completes those.  The counters
+// must be zero before launch_heads.
+cudaError_t launch_heads(const WalkArgs& a, cudaStream_t stream);
+cudaError_t launch_presite(const WalkArgs& a, bool second, cudaStream_t stream);
 
 // lays every walker's events out contiguously in `out`, in emission order; results[i].last_event becomes the index of the first
 cudaError_t launch_compact_events(const Event* in, Event* out, TaskResult* results, uint32_t n_tasks, Counters* ctr, cudaStream_t stream);

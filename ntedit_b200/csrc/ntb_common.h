@@ -115,6 +115,46 @@ static_assert(sizeof(Event) == 36, "Event layout");
 constexpr uint8_t STALE_REF = 0x80;
 constexpr uint8_t EV_TOUCHED = 1;  // a substitution trial patched and reverted the tail char: it is now draft (upper case), ntedit.cpp:1975-1981
 
+// Pre-evaluated sites.  A site the main loop reaches with a CLEAN window (k unedited, consecutive draft bases; the rope a
+// single position node) is a pure function of the contig text right of the window and of the filter: its whole
+// evaluation (ntedit.cpp:1808-2116 up to, not including, makeEdit) can run ahead of the sequential walk, for all such
+// candidate sites at once.  The pre-evaluation kernels (presite_kernel) do that for the first position of every run of
+// flagged positions -- and, while a site ends without an edit, for the flagged position right behind it -- and leave one
+// record per site in an open-addressing table keyed by the text position; a walker that arrives at a flagged position
+// with a clean window looks the record up and only commits it.  A missing record is not an error: the walker then
+// evaluates the site itself.
+struct SiteRec
+{
+	uint64_t key;         // text position of the site's tail + 1; 0 = empty slot
+	uint16_t support;     // best_num_support
+	uint16_t altsupp[3];
+	uint8_t state;        // SITE_*
+	uint8_t best_type;    // best_edit_type: 0 none, 1 substitution, 2 insertion, 3 deletion
+	uint8_t best_sub;     // may be STALE_REF | j, like the alternates (resolved by the walker that commits the record)
+	uint8_t altbase[3];
+	uint8_t indel_len;
+	char indel[5];
+	uint8_t flags;        // SITE_FL_*
+	uint8_t draft;        // draft_char (upper case)
+	uint8_t pad_[2];
+};
+static_assert(sizeof(SiteRec) == 32, "SiteRec layout");
+constexpr uint8_t SITE_NONE = 1;    // no attempt (do_not_fix / too few missing k-mers): nothing is committed
+constexpr uint8_t SITE_DONE = 2;    // the decision is in the record
+constexpr uint8_t SITE_PENDING = 3; // stopped in front of tryIndels; completed by the second pre-evaluation pass (else ignored)
+constexpr uint8_t SITE_FL_TOUCHED = 1; // makeEdit's `touched && raw != draft` (EV_TOUCHED of the event)
+constexpr uint8_t SITE_FL_QUIET = 2;   // accepted substitution whose k-1 following windows are no sites: the walker jumps k
+constexpr uint32_t SITE_TABLE_PROBES = 64;  // linear probing gives up after this many slots (insert: the record is dropped)
+constexpr uint32_t SITE_CHAIN_MAX = 64;     // flagged positions one pre-evaluation item follows behind a failed site
+
+// a site whose pre-evaluation stopped in front of tryIndels
+struct PendingSite
+{
+	uint32_t task;  // index of the task (contig segment) the position lies in
+	uint32_t pos;   // tail position inside the contig
+	uint32_t slot;  // the record's slot in the table
+};
+
 // Per-launch device counters.
 struct Counters
 {
@@ -124,6 +164,12 @@ struct Counters
 	uint32_t n_front;    // order_tasks_kernel: dense tasks placed so far (from the front of the queue)
 	uint32_t n_back;     // ... the others (from the back)
 	uint32_t n_compact;  // compact_events_kernel: events placed so far
+	uint32_t n_items;    // pre-evaluation: run heads listed so far
+	uint32_t next_item;  // ... work queue of the first pass
+	uint32_t n_pending;  // ... sites waiting for the second pass (tryIndels)
+	uint32_t next_pending;
+	uint32_t n_dropped;  // ... records that found no slot / list entry (the walkers evaluate those sites themselves)
+	uint32_t n_rec_used; // walkers: sites committed from a record
 	unsigned long long prof[16]; // -DNTB_PHASE_PROF: leader cycles per phase of the walker
 };
 

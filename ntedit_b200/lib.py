@@ -80,7 +80,8 @@ class Stats(C.Structure):
     _fields_ = [("bases", C.c_uint64), ("contigs", C.c_uint64), ("sites", C.c_uint64), ("edits", C.c_uint64),
                 ("segments", C.c_uint64), ("reruns", C.c_uint64), ("rounds", C.c_uint32),
                 ("kernel_launches", C.c_uint32), ("ms_scan", C.c_float), ("ms_walk", C.c_float),
-                ("ms_h2d", C.c_float), ("ms_d2h", C.c_float), ("ms_host", C.c_float)]
+                ("ms_h2d", C.c_float), ("ms_d2h", C.c_float), ("ms_host", C.c_float), ("ms_pre", C.c_float),
+                ("pad_", C.c_uint32)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

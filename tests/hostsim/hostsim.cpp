@@ -84,6 +84,77 @@ struct HostBackend
 		return tasks.data();
 	}
 
+	std::vector<SiteRec> table;
+	uint64_t pre_records = 0, pre_pending = 0, pre_dropped = 0;
+
+	template<class W>
+	void presites_with(const KParams& kp, size_t n_tasks, const std::vector<uint64_t>& rot)
+	{
+		// HOSTSIM_TABLE_SLOTS: tiny tables exercise dropped records (the walkers then evaluate those sites themselves)
+		size_t slots = 1;
+		const char* ts = std::getenv("HOSTSIM_TABLE_SLOTS");
+		const size_t want = ts ? (size_t)std::strtoull(ts, nullptr, 10) : std::max<size_t>(1024, (size_t)(total / 16));
+		while (slots < want) {
+			slots <<= 1;
+		}
+		table.assign(slots, SiteRec());
+		std::memset(table.data(), 0, slots * sizeof(SiteRec));
+		std::vector<PendingSite> pending(ts ? 8 : (size_t)(total / 32 + 64));
+		Counters ctr = {};
+		WalkerState<352>* st = new WalkerState<352>();
+		W w(*st, kp);
+		for (int pass = 0; pass < 2; pass++) {
+			const size_t n_units = pass == 0 ? n_tasks : std::min<size_t>(ctr.n_pending, pending.size());
+			for (size_t u = 0; u < n_units; u++) {
+				const size_t ti = pass == 0 ? u : pending[u].task;
+				const Task& t = tasks[ti];
+				WalkerIO& io = st->io;
+				io.text = bases + t.text_off;
+				io.len = t.len;
+				io.visit = visit.data();
+				io.goff = t.text_off;
+				io.bloom = bloom;
+				io.rep = rep;
+				io.events = nullptr;
+				io.ev_cap = 0;
+				io.ctr = &ctr;
+				io.rot = rot.data();
+				io.table = table.data();
+				io.table_mask = (uint32_t)slots - 1;
+				io.pending = pending.data();
+				io.pending_cap = (uint32_t)pending.size();
+				w.pre_begin();
+				if (pass == 1) {
+					w.pre_finish(pending[u].pos, pending[u].slot);
+					continue;
+				}
+				// heads among the flagged positions of [start, end)
+				for (uint64_t p = t.start; p < t.end; p++) {
+					const uint64_t g = t.text_off + p;
+					const bool f = (visit[g >> 5] >> (g & 31)) & 1u;
+					if (f && W::is_head(visit.data(), t.text_off, (uint32_t)p, w.pre_gap())) {
+						pre_records++;
+						w.pre_run((uint32_t)ti, (uint32_t)p);
+					}
+				}
+			}
+		}
+		pre_pending = ctr.n_pending;
+		pre_dropped = ctr.n_dropped;
+		delete st;
+	}
+
+	void presites(const KParams& kp, size_t n_tasks, const std::vector<uint64_t>& rot)
+	{
+		if (!kp.counting && !kp.h_rep && !kp.snv && !kp.mask && bloom.mask != 0) {
+			presites_with<Walker<352, true, true>>(kp, n_tasks, rot);
+		} else if (!kp.counting && !kp.h_rep && !kp.snv && !kp.mask) {
+			presites_with<Walker<352, true, false>>(kp, n_tasks, rot);
+		} else {
+			presites_with<Walker<352, false, false>>(kp, n_tasks, rot);
+		}
+	}
+
 	int walk(const KParams& kp, size_t n_tasks, const TaskResult** res_out, const Event** ev_out, size_t* n_ev_out)
 	{
 		results.resize(n_tasks);
@@ -93,11 +164,20 @@ struct HostBackend
 		for (uint32_t q = 0; q < ROT_WORDS; q++) {
 			rot[q] = rot_entry(q);
 		}
+		// the pre-evaluation pass of the first round, as the CUDA backend runs it (capi.cu: CudaBackend::presites): heads of
+		// flagged runs per task, first pass (no tryIndels), second pass (the pending ones); HOSTSIM_NO_PRESITE=1 turns it off
+		if (rounds.size() == 1 && !kp.snv && !std::getenv("HOSTSIM_NO_PRESITE")) {
+			presites(kp, n_tasks, rot);
+		}
 		for (;;) {
 			Counters ctr = {};
 			WalkerState<352>* st = new WalkerState<352>();
 			for (size_t i = 0; i < n_tasks; i++) {
 				WalkerIO& io = st->io;
+				io.table = table.empty() ? nullptr : table.data();
+				io.table_mask = table.empty() ? 0 : (uint32_t)table.size() - 1;
+				io.pending = nullptr;
+				io.pending_cap = 0;
 				io.text = bases + tasks[i].text_off;
 				io.len = tasks[i].len;
 				io.visit = visit.data();
@@ -121,6 +201,10 @@ struct HostBackend
 				}
 			}
 			delete st;
+			if (std::getenv("HOSTSIM_DEBUG")) {
+				std::fprintf(stderr, "[hostsim] round %zu: %zu tasks, run heads %llu, pending %llu, dropped %llu, sites from records %u\n", rounds.size(),
+				             n_tasks, (unsigned long long)pre_records, (unsigned long long)pre_pending, (unsigned long long)pre_dropped, ctr.n_rec_used);
+			}
 			if (!ctr.overflow) {
 				events.resize(ctr.n_events);
 				// Backend contract: last_event = index of the walker's first event, its events contiguous and in order.
