@@ -1,25 +1,35 @@
 #!/usr/bin/env python
-"""bench.py -- bases polished / second on BASELINE.json's headline configuration.
+"""bench.py -- bases polished / second on BASELINE.json's configurations (default: configs[2], the one the metric is
+quoted on).
 
-Workload (configs[2] of BASELINE.json, the one the metric is quoted on): a synthetic 3 Gbp human-like draft
-(24 contigs of 50-250 Mbp + 2000 x 100 kbp, substitution rate 1e-3, indel rate 1e-4, 0.2 % lower case, N runs), a
-4 GiB k=25 h=3 Bloom filter holding every k-mer of the error-free genome, ntEdit mode 1.  A "step" is one pass of the
-whole hot path (scan kernel, walker kernel rounds, host stitch + rope replay) over the whole draft.
+Workloads (NTB_BENCH_WORKLOAD / --workload; SURVEY.md 8d recipe: substitution 1e-3, indel 1e-4 of length 1-5, 0.2 % lower
+case, N runs; the filter holds every k-mer of the error-free genome):
+  100Mbp_k25_1GiB_m0           configs[1]  100 x 1 Mbp, 1 GiB k=25 Bloom filter, mode 0
+  3Gbp_k25_4GiB_m1  (default)  configs[2]  24 contigs of 50-250 Mbp + 2000 x 100 kbp, 4 GiB k=25 Bloom filter, mode 1
+  3Gbp_k32_8GiB_cbf_m2_snv     configs[3]  same draft shape, 8 GiB k=32 counting filter (counts x30), mode 2, -s 1
+  2.5Gbp_conifer_k25_16GiB_m0  configs[4]  one GPU's share (1/8) of the 20 Gbp / 4 M-contig conifer-like draft: 500 k contigs,
+                                           log-normal lengths (N50 ~ 20 kbp), 16 GiB filter filled to the occupancy the
+                                           whole 20 Gbp genome gives it, mode 0
+A "step" is one pass of the whole hot path (scan stage, site pre-evaluation, walker rounds, host stitch + rope replay) over
+the whole draft.
 
   value : bases/s, batch already resident in HBM when the timed region starts (K steps in one bracket)
   e2e   : bases/s through the C-ABI call a binding makes (ntb_polish_batch) with the draft in pinned HOST memory --
           host->device copy of the bases and device->host copy of the edit events inside the timed region
-  roofline : the scan stage (K1b: bin_kernel + probe_bin_kernel per text chunk), algorithmic bytes = (1 + 32*h) per base
-          (one text byte + h random 32-byte sectors), duration from CUDA events on its stream
-  cpu_baseline : the UNMODIFIED reference (oracle/_ref/ntedit_ref, OpenMP over contigs) on a bounded sample of the
-          same draft with the same filter file, on this box's host cores
+  roofline : the whole path against the HBM roofline: achieved = bases/s x A, A = SURVEY.md 8d's algorithmic bytes per base
+          (97 B for the polishing modes at h = 3, 1 + 32 h (1 + 3 (1 + ceil(k/j))) for -s 1); `stages` holds the same figure per
+          device stage (CUDA-event times on the library's stream) with the DRAM traffic of the committed ncu capture
+  cpu_baseline : the UNMODIFIED reference (oracle/_ref/ntedit_ref, OpenMP over contigs) on a bounded sample of the same
+          draft with the same filter file, on this box's host cores
+  verified : the product's three output files for that same sample, byte-compared per contig with the reference's
 
 `--impl reference` times that reference binary as the measured arm (same config, bounded sample per step).
-Multi-GPU (torchrun): every rank polishes its own 3 Gbp draft (a different error realisation of the same genome)
-against the same filter -- built on rank 0 and broadcast once over NCCL; no collective on the hot path (weak scaling).
+Multi-GPU (torchrun): every rank polishes its own draft (a different error realisation of the same genome) against the
+same filter -- built on rank 0 and broadcast once over NCCL; no collective on the hot path (weak scaling).
 """
 import argparse
 import json
+import math
 import os
 import shutil
 import subprocess
@@ -34,23 +44,54 @@ sys.path.insert(0, ROOT)
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
-K, H = 25, 3
 SEED = 20261017
-# dram__bytes_read.sum + dram__bytes_write.sum of the scan stage from the committed ncu --set full capture of this command
-# (profiles/): per-chunk bin + probe traffic x chunks; None until captured for the current kernels
-NCU_TRAFFIC_BYTES_PER_STAGE = int((0.688038e9 + 16.137119e9 + 22.335070e9 + 0.884871e9) * 88796 / 19982)
-NCU_TRAFFIC_SOURCE = ("profiles/r01y_ncu_full_bin_probe_summary.csv: (bin_kernel 16.83 GB + probe_bin_kernel 23.22 GB) per "
-                      "19982-tile chunk x 88796/19982 chunks; the direct scan kernel moved 1146 GB for the same work")
 
 WORKLOADS = {
-    # name: (total bases, filter bytes, large contigs, small contigs, mode)
-    "3Gbp_k25_4GiB_m1": dict(total=3_000_000_000, fbytes=4 << 30, n_large=24, n_small=2000, small_len=100_000, mode=1),
-    "100Mbp_k25_1GiB_m0": dict(total=100_000_000, fbytes=1 << 30, n_large=100, n_small=0, small_len=0, mode=0),
-    "tiny": dict(total=20_000_000, fbytes=1 << 26, n_large=8, n_small=40, small_len=50_000, mode=1),
+    "3Gbp_k25_4GiB_m1": dict(baseline_config=2, total=3_000_000_000, fbytes=4 << 30, k=25, h=3, shape="human", n_large=24,
+                             n_small=2000, small_len=100_000, mode=1),
+    "100Mbp_k25_1GiB_m0": dict(baseline_config=1, total=100_000_000, fbytes=1 << 30, k=25, h=3, shape="human", n_large=100,
+                               n_small=0, small_len=0, mode=0),
+    "3Gbp_k32_8GiB_cbf_m2_snv": dict(baseline_config=3, total=3_000_000_000, fbytes=8 << 30, k=32, h=3, shape="human",
+                                     n_large=24, n_small=2000, small_len=100_000, mode=2, snv=1, counting=True, count_scale=30),
+    "2.5Gbp_conifer_k25_16GiB_m0": dict(baseline_config=4, total=2_500_000_000, fbytes=16 << 30, k=25, h=3, shape="conifer",
+                                        n_contigs=500_000, mode=0, background_genome=20_000_000_000),
+    "tiny": dict(baseline_config=None, total=20_000_000, fbytes=1 << 26, k=25, h=3, shape="human", n_large=8, n_small=40,
+                 small_len=50_000, mode=1),
+    "tiny_snv": dict(baseline_config=None, total=4_000_000, fbytes=1 << 25, k=32, h=3, shape="human", n_large=4, n_small=10,
+                     small_len=50_000, mode=2, snv=1, counting=True, count_scale=30),
+    "tiny_conifer": dict(baseline_config=None, total=30_000_000, fbytes=1 << 27, k=25, h=3, shape="conifer", n_contigs=6000,
+                         mode=0, background_genome=240_000_000),
+}
+
+# dram__bytes_read.sum + dram__bytes_write.sum per stage and step from the committed `ncu --set full` capture of this command
+# (profiles/); None = not captured for the current kernels
+NCU_TRAFFIC = {
+    "3Gbp_k25_4GiB_m1": {
+        "scan": (int((0.688038e9 + 16.137119e9 + 22.335070e9 + 0.884871e9) * 88796 / 19982),
+                 "profiles/r01y_ncu_full_bin_probe_summary.csv: (bin_kernel 16.83 GB + probe_bin_kernel 23.22 GB) per "
+                 "19982-tile chunk x 88796/19982 chunks"),
+    },
 }
 
 
-def contig_lengths(w):
+def algorithmic_bytes_per_base(w, jump=3):
+    """A = 1 + 32 h L, L = distinct k-mer look-ups per base."""
+    look_ups = 1
+    if w.get("snv"):
+        look_ups = 1 + 3 * (1 + math.ceil(w["k"] / jump))
+    return 1 + 32 * w["h"] * look_ups
+
+
+def contig_lengths(w, rng=None):
+    if w["shape"] == "conifer":
+        # log-normal lengths scaled to the total: N50 / mean = exp(sigma^2 / 2), sigma 1.665 puts N50 at 4x the mean (5 kbp -> 20 kbp)
+        rng = np.random.default_rng(SEED)
+        x = rng.lognormal(0.0, 1.665, w["n_contigs"])
+        lens = np.maximum(200, (x / x.sum() * w["total"]).astype(np.int64))
+        lens[-1] += w["total"] - int(lens.sum())
+        if lens[-1] < 200:
+            lens[-1] = 200
+        return [int(v) for v in lens]
     small = w["n_small"] * w["small_len"]
     big_total = w["total"] - small
     n = w["n_large"]
@@ -110,40 +151,8 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def build_workload(w, dev, rank, bloom, nb):
-    """Returns (draft buffer uint8 tensor on device with NUL separators, offsets np.uint64).  When `bloom` is given,
-    every k-mer of the error-free genome is inserted into it (filter construction kernel)."""
-    lens = contig_lengths(w)
-    drafts = []
-    for ci, n in enumerate(lens):
-        g = torch.Generator(device=dev)
-        g.manual_seed(SEED + ci)          # genome: same on every rank
-        # the error realisation differs per rank: re-seed after the genome part by deriving a second generator
-        truth, draft = gen_contig_rank(n, g, dev, rank, ci)
-        if bloom is not None:
-            tb = torch.cat([truth, torch.zeros(1, dtype=torch.uint8, device=dev)])
-            offs = np.array([0, len(tb)], dtype=np.uint64)
-            b = nb.Batch.wrap_device(tb.data_ptr(), offs, device=dev.index)
-            bloom.insert_batch(b)
-            b.free()
-            del tb
-        drafts.append(draft)
-        del truth
-    total = sum(len(d) + 1 for d in drafts)
-    buf = torch.zeros(total, dtype=torch.uint8, device=dev)
-    offs = np.zeros(len(drafts) + 1, dtype=np.uint64)
-    o = 0
-    for i, d in enumerate(drafts):
-        buf[o:o + len(d)] = d
-        o += len(d) + 1
-        offs[i + 1] = o
-    del drafts
-    torch.cuda.empty_cache()
-    return buf, offs
-
-
-def gen_contig_rank(n, g, dev, rank, ci):
-    """Genome from generator g (rank independent); errors from a rank-specific generator."""
+def gen_sequence(n, g, dev, rank, ci):
+    """Genome from generator g (rank independent); errors from a rank-specific generator.  Returns (truth, draft) uint8."""
     lut = torch.tensor(list(b"ACGT"), dtype=torch.uint8, device=dev)
     code = torch.randint(0, 4, (n,), dtype=torch.uint8, device=dev, generator=g)
     n_dup = min(2000, int(n * 0.05 / 5000)) if n > 100_000 else 0
@@ -189,11 +198,123 @@ def gen_contig_rank(n, g, dev, rank, ci):
     return truth, draft
 
 
+def insert_truth(nb, bloom, truth, dev):
+    tb = torch.cat([truth, torch.zeros(1, dtype=torch.uint8, device=dev)])
+    offs = np.array([0, len(tb)], dtype=np.uint64)
+    b = nb.Batch.wrap_device(tb.data_ptr(), offs, device=dev.index)
+    bloom.insert_batch(b)
+    b.free()
+
+
+def build_workload(w, dev, rank, bloom, nb):
+    """Returns (draft buffer uint8 tensor on device with NUL separators, offsets np.uint64).  When `bloom` is given,
+    every k-mer of the error-free genome is inserted into it (filter construction kernel)."""
+    lens = contig_lengths(w)
+    if w["shape"] == "conifer":
+        # the genome is generated in 100 Mbp pieces, each cut into contigs of the drawn lengths
+        pieces, piece, acc = [], [], 0
+        for n in lens:
+            piece.append(n)
+            acc += n
+            if acc >= 100_000_000:
+                pieces.append(piece)
+                piece, acc = [], 0
+        if piece:
+            pieces.append(piece)
+        bufs, all_lens = [], []
+        for pi, plens in enumerate(pieces):
+            n = sum(plens)
+            g = torch.Generator(device=dev)
+            g.manual_seed(SEED + pi)
+            truth, draft = gen_sequence(n, g, dev, rank, pi)
+            if bloom is not None:
+                # contig borders of the truth: k-mers across them do not exist in the genome, but a few hundred thousand extra
+                # k-mers in a 16 GiB filter change nothing measurable
+                insert_truth(nb, bloom, truth, dev)
+            del truth
+            # cut the draft (its length differs from n by the indels) proportionally
+            m = len(draft)
+            cuts = np.floor(np.cumsum(np.array(plens, dtype=np.float64)) * (m / n)).astype(np.int64)
+            cuts[-1] = m
+            dl = np.diff(np.concatenate([[0], cuts]))
+            dl = dl[dl > 0]
+            cid = torch.repeat_interleave(torch.arange(len(dl), device=dev), torch.tensor(dl, device=dev))
+            out = torch.zeros(m + len(dl), dtype=torch.uint8, device=dev)
+            out[torch.arange(m, device=dev) + cid] = draft
+            bufs.append(out)
+            all_lens.extend(int(x) for x in dl)
+            del draft, cid
+        buf = torch.cat(bufs)
+        del bufs
+        offs = np.zeros(len(all_lens) + 1, dtype=np.uint64)
+        offs[1:] = np.cumsum(np.array(all_lens, dtype=np.uint64) + np.uint64(1))
+        torch.cuda.empty_cache()
+        return buf, offs
+    drafts = []
+    for ci, n in enumerate(lens):
+        g = torch.Generator(device=dev)
+        g.manual_seed(SEED + ci)          # genome: same on every rank
+        truth, draft = gen_sequence(n, g, dev, rank, ci)
+        if bloom is not None:
+            insert_truth(nb, bloom, truth, dev)
+        drafts.append(draft)
+        del truth
+    total = sum(len(d) + 1 for d in drafts)
+    buf = torch.zeros(total, dtype=torch.uint8, device=dev)
+    offs = np.zeros(len(drafts) + 1, dtype=np.uint64)
+    o = 0
+    for i, d in enumerate(drafts):
+        buf[o:o + len(d)] = d
+        o += len(d) + 1
+        offs[i + 1] = o
+    del drafts
+    torch.cuda.empty_cache()
+    return buf, offs
+
+
+def finish_filter(w, filt, dev):
+    """Post-processing of the fabricated filter (rank 0, before the broadcast)."""
+    n = w["fbytes"]
+    step = 1 << 28
+    if w.get("count_scale"):
+        # coverage: every k-mer of the genome was inserted once; scale the counters as count_scale-fold read coverage would
+        for o in range(0, n, step):
+            v = filt[o:min(n, o + step)]
+            v.copy_((v.to(torch.int16) * int(w["count_scale"])).clamp_(max=255).to(torch.uint8))
+    if w.get("background_genome"):
+        # one GPU's share of a larger genome: the other shares' k-mers are, for this share, independent random bits.  Fill the
+        # filter to the occupancy the whole genome gives it: background density d with 1-(1-d)(1-d_own) = 1-exp(-h N / m),
+        # built from ANDs / ORs of random bytes (two terms: 2^-a + 2^-b - 2^-(a+b))
+        m_bits = n * 8.0
+        d_all = 1.0 - math.exp(-w["h"] * w["background_genome"] / m_bits)
+        d_own = 1.0 - math.exp(-w["h"] * w["total"] / m_bits)
+        d_bg = 1.0 - (1.0 - d_all) / (1.0 - d_own)
+        best = None
+        for a in range(1, 7):
+            for b in range(a, 9):
+                d = 1.0 - (1.0 - 2.0 ** -a) * (1.0 - 2.0 ** -b)
+                if best is None or abs(d - d_bg) < abs(best[0] - d_bg):
+                    best = (d, a, b)
+        g = torch.Generator(device=dev)
+        g.manual_seed(SEED + 99)
+
+        def and_of(cnt, size):
+            r = torch.randint(0, 256, (size,), dtype=torch.uint8, device=dev, generator=g)
+            for _ in range(cnt - 1):
+                r &= torch.randint(0, 256, (size,), dtype=torch.uint8, device=dev, generator=g)
+            return r
+        for o in range(0, n, step):
+            v = filt[o:min(n, o + step)]
+            v |= and_of(best[1], len(v)) | and_of(best[2], len(v))
+        return {"background_density_target": d_bg, "background_density_built": best[0]}
+    return {}
+
+
 def write_sample_fasta(path, host_buf, offs, target_bases, chunk=1_000_000):
     """Bounded sample for the CPU reference: the draft cut into <=1 Mbp pseudo-contigs (the reference parallelises
-    over contigs only, ntedit.cpp:2213-2252) until target_bases are written.  Returns bases written."""
+    over contigs only, ntedit.cpp:2213-2252) until target_bases are written.  Returns (bases written, [(header, start, end)])."""
     written = 0
-    n = 0
+    contigs = []
     with open(path, "wb") as fh:
         for c in range(len(offs) - 1):
             s, e = int(offs[c]), int(offs[c + 1]) - 1
@@ -201,27 +322,51 @@ def write_sample_fasta(path, host_buf, offs, target_bases, chunk=1_000_000):
             while p < e and written < target_bases:
                 q = min(e, p + chunk)
                 if q - p >= 1000:
-                    fh.write(b">sample%d\n" % n)
+                    hdr = b"sample%d" % len(contigs)
+                    fh.write(b">" + hdr + b"\n")
                     fh.write(host_buf[p:q].tobytes())
                     fh.write(b"\n")
                     written += q - p
-                    n += 1
+                    contigs.append((hdr, p, q))
                 p = q
             if written >= target_bases:
                 break
-    return written
+    return written, contigs
 
 
-def time_reference(ref_bin, draft_path, tiny_path, filter_path, threads, mode, workdir):
+def reference_flags(w):
+    f = ["-m", str(w["mode"])]
+    if w.get("snv"):
+        f += ["-s", "1"]
+    return f
+
+
+def time_reference(ref_bin, draft_path, tiny_path, filter_path, threads, w, workdir):
     """wall(sample) - wall(200 bp draft): isolates filter load + FPR popcount."""
     def run(dp, tag):
         t0 = time.perf_counter()
-        subprocess.run([ref_bin, "-f", dp, "-r", filter_path, "-b", os.path.join(workdir, tag), "-t", str(threads),
-                        "-m", str(mode)], check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        subprocess.run([ref_bin, "-f", dp, "-r", filter_path, "-b", os.path.join(workdir, tag), "-t", str(threads)]
+                       + reference_flags(w), check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
         return time.perf_counter() - t0
     t_load = run(tiny_path, "tiny")
     t_all = run(draft_path, "sample")
     return max(1e-6, t_all - t_load), t_load, t_all
+
+
+def split_fasta(data):
+    out = {}
+    lines = data.split(b"\n")
+    for i in range(0, len(lines) - 1, 2):
+        out[lines[i][1:].split(b" ")[0]] = lines[i + 1]
+    return out
+
+
+def split_rows(data, skip_header):
+    out = {}
+    for ln in data.split(b"\n")[1 if skip_header else 0:]:
+        if ln and not ln.startswith(b"#"):
+            out.setdefault(ln.split(b"\t")[0], []).append(ln)
+    return out
 
 
 def main():
@@ -230,7 +375,7 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default=os.environ.get("NTB_BENCH_WORKLOAD", "3Gbp_k25_4GiB_m1"))
+    ap.add_argument("--workload", default=os.environ.get("NTB_BENCH_WORKLOAD", "3Gbp_k25_4GiB_m1"), choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--sample-mbp", type=float, default=0.0, help="CPU reference sample size (0 = from core count)")
     args = ap.parse_args()
@@ -239,6 +384,8 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     w = WORKLOADS[args.workload]
+    K, H = w["k"], w["h"]
+    counting = bool(w.get("counting"))
     cores = os.cpu_count() or 1
 
     if args.impl == "reference" and rank != 0:
@@ -260,8 +407,10 @@ def main():
     # the filter lives in a torch tensor so that it can be replicated with one NCCL broadcast at load time -- the only
     # collective of the design; the library wraps the device pointer
     filt = torch.zeros(w["fbytes"] + 64, dtype=torch.uint8, device=dev)
-    bloom = nb.BloomFilter.wrap_device(filt.data_ptr(), w["fbytes"], K, H, counting=False, device=dev.index)
-    buf, offs = build_workload(w, dev, rank, bloom if (rank == 0 or dist is None) else None, nb)
+    bloom = nb.BloomFilter.wrap_device(filt.data_ptr(), w["fbytes"], K, H, counting=counting, device=dev.index)
+    builder = rank == 0 or dist is None
+    buf, offs = build_workload(w, dev, rank, bloom if builder else None, nb)
+    filter_notes = finish_filter(w, filt, dev) if builder else {}
     if dist is not None:
         torch.cuda.synchronize()
         dist.broadcast(filt, src=0)
@@ -271,14 +420,14 @@ def main():
     fpr = bloom.get_fpr()
     setup_s = time.perf_counter() - t_setup
 
-    params = nb.default_params(mode=w["mode"])
+    params = nb.default_params(mode=w["mode"], snv=int(w.get("snv", 0)))
     host = torch.empty(len(buf), dtype=torch.uint8, pin_memory=True)
     host.copy_(buf)
     torch.cuda.synchronize()
     host_np = host.numpy()
 
     # ------------------------------------------------------------------ reference arm / cpu baseline helper
-    def reference_run(steps, warmup):
+    def reference_run(steps, warmup, verify):
         from oracle import pyoracle as po
         if not po.have_ref():
             return None
@@ -286,34 +435,55 @@ def main():
         try:
             fpath = os.path.join(tmp, "filter.bf")
             bloom.save(fpath)
-            target = int(args.sample_mbp * 1e6) if args.sample_mbp > 0 else int(min(bases, cores * 1.0e6 * 12))
+            per_core = 1.0e6 * (12 if not w.get("snv") else 1.5)
+            target = int(args.sample_mbp * 1e6) if args.sample_mbp > 0 else int(min(bases, cores * per_core))
             dpath = os.path.join(tmp, "sample.fa")
-            sample_bases = write_sample_fasta(dpath, host_np, offs, target)
+            sample_bases, sample = write_sample_fasta(dpath, host_np, offs, target)
             tiny = os.path.join(tmp, "tiny.fa")
             with open(tiny, "wb") as fh:
                 fh.write(b">tiny\n" + host_np[:200].tobytes() + b"\n")
             times = []
             for i in range(warmup + steps):
-                dt, t_load, t_all = time_reference(po.REF_BIN, dpath, tiny, fpath, cores, w["mode"], tmp)
+                dt, t_load, t_all = time_reference(po.REF_BIN, dpath, tiny, fpath, cores, w, tmp)
                 if i >= warmup:
                     times.append(dt)
-            return dict(value=sample_bases * len(times) / sum(times), sample_bases=sample_bases, times=times,
-                        t_load=t_load)
+            out = dict(value=sample_bases * len(times) / sum(times), sample_bases=sample_bases, times=times, t_load=t_load,
+                       verified=None)
+            if verify:
+                # the product on the very same pseudo-contigs, through the host-buffer call, against the files the
+                # reference just wrote (per contig: with -t > 1 the reference's output order is its completion order)
+                contigs = [(h, host_np[p:q].tobytes()) for h, p, q in sample]
+                fa, tsv, vcf, _ = nb.polish(contigs, bloom, params)
+                rfa = open(os.path.join(tmp, "sample_edited.fa"), "rb").read()
+                rtsv = open(os.path.join(tmp, "sample_changes.tsv"), "rb").read()
+                rvcf = open(os.path.join(tmp, "sample_variants.vcf"), "rb").read()
+                ok_fa = split_fasta(fa) == split_fasta(rfa)
+                ok_tsv = split_rows(tsv, True) == split_rows(rtsv, True) and tsv.split(b"\n")[0] == rtsv.split(b"\n")[0]
+                ok_vcf = split_rows(vcf, False) == split_rows(rvcf, False)
+                out["verified"] = {"ok": bool(ok_fa and ok_tsv and ok_vcf), "edited_fa": bool(ok_fa), "changes_tsv": bool(ok_tsv),
+                                   "variants_vcf": bool(ok_vcf), "contigs": len(contigs), "bases": sample_bases,
+                                   "tsv_rows": tsv.count(b"\n") - 1,
+                                   "against": "oracle/_ref/ntedit_ref -t %d on the same pseudo-contigs and filter file, "
+                                              "byte-compared per contig" % cores}
+            return out
         finally:
             shutil.rmtree(tmp, ignore_errors=True)
 
-    config = {"workload": args.workload, "k": K, "hash_num": H, "filter_bytes": w["fbytes"], "filter_fpr": fpr,
-              "mode": w["mode"], "bases_per_gpu": bases, "contigs_per_gpu": n_contigs,
+    a_bytes = algorithmic_bytes_per_base(w)
+    config = {"workload": args.workload, "baseline_config": w["baseline_config"], "k": K, "hash_num": H,
+              "filter_bytes": w["fbytes"], "filter_kind": "counting (8-bit)" if counting else "bit", "filter_fpr": fpr,
+              "mode": w["mode"], "snv": int(w.get("snv", 0)), "bases_per_gpu": bases, "contigs_per_gpu": n_contigs,
               "errors": "substitution 1e-3, indel 1e-4 (len 1-5), 0.2% lower case, N runs",
-              "l2_note": "inputs (3 GB draft + 4 GiB filter) are far larger than the 126 MB L2",
+              "l2_note": "inputs (draft + filter, GBs) are far larger than the 126 MB L2",
               "parallelism": "contigs sharded per GPU, filter replicated (1 NCCL broadcast at load)" if world > 1 else "1 GPU"}
+    config.update(filter_notes)
 
     if args.impl == "reference":
-        r = reference_run(args.steps, max(0, min(args.warmup, 1)))
+        r = reference_run(args.steps, max(0, min(args.warmup, 1)), False)
         if r is None:
             print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/ntedit_ref not present on this box"}))
             return 0
-        sample = "%d bases of the same draft as <=1 Mbp pseudo-contigs, same 4 GiB filter file; time = wall - wall(200 bp draft)" % r["sample_bases"]
+        sample = "%d bases of the same draft as <=1 Mbp pseudo-contigs, same filter file; time = wall - wall(200 bp draft)" % r["sample_bases"]
         line = {"metric": "bases polished/sec", "value": r["value"], "unit": "bases/s", "n_gpus": args.gpus,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * sum(r["times"]) / len(r["times"]),
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
@@ -340,7 +510,7 @@ def main():
         return d
 
     for _ in range(args.warmup):
-        last = step_resident()
+        step_resident()
     sampler = ClockSampler(local_rank)
     sampler.start()
     # let nvidia-smi come up before the timed region: forking it out of a process with GBs of pinned mappings takes
@@ -382,13 +552,15 @@ def main():
     dt_max, e2e_max = float(dt_t[0]), float(dt_t[1])
 
     cpu = None
+    verified = None
     if rank == 0 and not args.no_cpu_baseline:
         try:
-            r = reference_run(1, 0)
+            r = reference_run(1, 0, True)
             if r is not None:
                 cpu = {"value": r["value"], "unit": "bases/s", "cores": cores, "kind": "reference",
                        "sample": "%d bases of the same draft as <=1 Mbp pseudo-contigs, same filter file, %d threads; "
                                  "time = wall - wall(200 bp draft, %.1f s load)" % (r["sample_bases"], cores, r["t_load"])}
+                verified = r["verified"]
         except Exception as ex:  # the baseline must never take the bench line down
             cpu = {"value": None, "unit": "bases/s", "cores": cores, "kind": "reference", "sample": "failed: %r" % (ex,)}
 
@@ -400,44 +572,63 @@ def main():
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
         peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
-        ms_scan = float(np.mean([s["ms_scan"] for s in stats]))
-        ms_walk = float(np.mean([s["ms_walk"] for s in stats]))
-        ms_host = float(np.mean([s["ms_host"] for s in stats]))
+        mean = lambda key, ss=stats: float(np.mean([s[key] for s in ss]))  # noqa: E731
+        ms_scan, ms_pre, ms_walk, ms_host, ms_d2h = mean("ms_scan"), mean("ms_pre"), mean("ms_walk"), mean("ms_host"), mean("ms_d2h")
         positions = int(offs[-1])
-        alg_bytes = (1 + 32 * H) * positions
-        achieved = alg_bytes / (ms_scan * 1e-3) / 1e9
+        value = world * bases * args.steps / dt_max
+        e2e_value = world * bases * n_e2e / e2e_max
+        traffic = NCU_TRAFFIC.get(args.workload, {})
+
+        def stage(name, kernels, ms, key):
+            t = traffic.get(key)
+            gbs = a_bytes * positions / (ms * 1e-3) / 1e9 if ms > 0 else None
+            return {"stage": name, "kernels": kernels, "ms_per_step": ms, "share_of_device_time": None,
+                    "achieved_if_alone": gbs, "frac_if_alone": gbs / peak if gbs else None,
+                    "traffic": t[0] if t else None, "traffic_source": t[1] if t else None}
+        stages = [
+            stage("scan", "K1b bin_kernel + probe_bin_kernel per text chunk (filters > L2), else K1 scan_kernel", ms_scan, "scan"),
+            stage("presite", "K2p heads_kernel + presite_kernel (2 passes)", ms_pre, "presite"),
+            stage("walk", "K2 order_tasks_kernel + walk_kernel + compact_events_kernel, all rounds", ms_walk, "walk"),
+        ]
+        dev_ms = ms_scan + ms_pre + ms_walk
+        for s in stages:
+            s["share_of_device_time"] = s["ms_per_step"] / dev_ms if dev_ms > 0 else None
+        dominant = max(stages, key=lambda s: s["ms_per_step"])
+        achieved = value / world * a_bytes / 1e9
         ev_bytes = 36
         d2h = int(np.mean([s["edits"] for s in e2e_stats]) * ev_bytes) + 36 * int(e2e_stats[0]["segments"])
         line = {
-            "metric": "bases polished/sec", "value": world * bases * args.steps / dt_max, "unit": "bases/s",
+            "metric": "bases polished/sec", "value": value, "unit": "bases/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * dt_max / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
             "config": config,
-            "e2e": {"value": world * bases * n_e2e / e2e_max, "unit": "bases/s", "h2d_bytes_per_step": int(offs[-1]),
+            "e2e": {"value": e2e_value, "unit": "bases/s", "h2d_bytes_per_step": int(offs[-1]),
                     "d2h_bytes_per_step": d2h, "steps": n_e2e,
                     "note": "ntb_polish_batch on pinned host memory; working copy restored between steps outside the timed region",
                     "breakdown_ms": {"wall": 1000.0 * e2e_max / n_e2e,
-                                     "h2d_stream": float(np.mean([s["ms_h2d"] for s in e2e_stats])),
-                                     "scan_stage_incl_upload_waits": float(np.mean([s["ms_scan"] for s in e2e_stats])),
-                                     "walk_kernel": float(np.mean([s["ms_walk"] for s in e2e_stats])),
-                                     "host_stitch_replay": float(np.mean([s["ms_host"] for s in e2e_stats]))}},
+                                     "h2d_stream": mean("ms_h2d", e2e_stats),
+                                     "scan_stage_incl_upload_waits": mean("ms_scan", e2e_stats),
+                                     "presite_kernels": mean("ms_pre", e2e_stats),
+                                     "walk_kernel": mean("ms_walk", e2e_stats),
+                                     "host_stitch_replay": mean("ms_host", e2e_stats)}},
             "gpu_launches": int(sum(s["kernel_launches"] for s in stats)),
             "timing": "steps bracketed by torch.cuda.synchronize() (+ dist.barrier) on both sides, max over ranks; a step "
                       "contains host work (stitch + rope replay), so the bracket is timed on the host clock; the per-stage "
-                      "numbers in breakdown_ms / roofline are CUDA-event times on the library's own stream",
+                      "numbers in breakdown_ms / roofline.stages are CUDA-event times on the library's own stream",
             "clocks": clocks,
-            # the HBM-bound stage of the path: K1b = bin_kernel<3,false> + probe_bin_kernel<false>, one pair per text chunk;
-            # "launch" = one pass of that stage over the whole batch (CUDA events on its stream around all its launches)
-            "roofline": {"bound": "hbm", "kernel": "K1b scan stage: bin_kernel<3,false> + probe_bin_kernel<false> per text chunk",
+            # the whole path against the HBM roofline: per GPU, bases/s x algorithmic bytes per base
+            "roofline": {"bound": "hbm", "kernel": "whole path (dominant stage: %s)" % dominant["stage"],
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": NCU_TRAFFIC_BYTES_PER_STAGE, "traffic_source": NCU_TRAFFIC_SOURCE, "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": ms_scan,
+                         "frac_e2e": e2e_value / world * a_bytes / 1e9 / peak,
+                         "algorithmic_bytes_per_base": a_bytes, "algorithmic_bytes_per_launch": a_bytes * positions,
+                         "traffic": dominant["traffic"], "traffic_source": dominant["traffic_source"],
+                         "peak_source": peak_src, "stages": stages,
                          "gather_ceiling_note": "a direct 1-byte probe costs a 128-byte DRAM line on B200 (37.9 G probes/s "
                                                 "ceiling, profiles/r01_gather_*); K1b serves probes from L2-resident filter regions"},
             "cpu_baseline": cpu,
-            "breakdown_ms": {"scan_kernel": ms_scan, "presite_kernels": float(np.mean([s["ms_pre"] for s in stats])),
-                             "walk_kernel": ms_walk, "host_stitch_replay": ms_host,
-                             "d2h_events": float(np.mean([s["ms_d2h"] for s in stats])), "rounds": stats[-1]["rounds"],
+            "verified": verified,
+            "breakdown_ms": {"scan_kernel": ms_scan, "presite_kernels": ms_pre, "walk_kernel": ms_walk,
+                             "host_stitch_replay": ms_host, "d2h_events": ms_d2h, "rounds": stats[-1]["rounds"],
                              "segments": stats[-1]["segments"], "reruns": stats[-1]["reruns"], "sites": stats[-1]["sites"],
                              "edits": stats[-1]["edits"], "setup_s": setup_s},
         }

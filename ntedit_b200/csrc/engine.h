@@ -2775,6 +2775,16 @@ struct Walker
 			}
 		}
 		blocked = warp_or(blocked);
+		// Otherwise: the windows in front of the first site of the pass are rolled through in one step, as far as the incoming
+		// bases are accepted (a non-accepted one starts the skip logic of ntedit.cpp:2119-2138, which advance() replays) --
+		// the same rolls the main loop would make one by one with nothing to observe in between.
+		uint32_t first_bad = n;
+		for (uint32_t m = lane_id(); m + 1 < n; m += lane_count()) {
+			if (!is_acc(S.lin_in[m]) && m < first_bad) {
+				first_bad = m;
+			}
+		}
+		first_bad = warp_min(first_bad);
 		NTB_LEADER_BEGIN
 		S.la_bits = bits;
 		S.la_n = n;
@@ -2787,6 +2797,30 @@ struct Walker
 			S.need_seed = true; // the window is clean: the hash is re-seeded at the next flagged position
 			S.la_n = 0;
 			S.jumped = true;
+		} else {
+			uint32_t first_site = 0;
+			while (first_site < n && !((bits >> first_site) & 1u)) {
+				first_site++;
+			}
+			uint32_t G = first_site < n ? first_site : n - 1;   // land on the first site, or on the last window of the pass
+			if (G > first_bad) {
+				G = first_bad;
+			}
+			if (G > S.n_plain) {
+				G = S.n_plain;
+			}
+			if (G > 0) {
+				for (uint32_t q = 0; q < G; q++) {
+					step(S.h);
+					step(S.t);
+				}
+				S.hs.fh = S.plain_f[G];
+				S.hs.rh = S.plain_r[G];
+				S.char_in = S.lin_in[G - 1];
+				S.adv += G;
+				S.la_used = G;
+				S.jumped = true; // back to the top of the main loop: the window may be clean again by now
+			}
 		}
 		NTB_LEADER_END
 	}
@@ -2890,7 +2924,7 @@ struct Walker
 					lookahead();
 					NTB_PROF(4);
 					if (S.jumped) {
-						return true; // now on a clean window: back to the top of the main loop
+						return true; // the window moved (possibly onto clean text): back to the top of the main loop
 					}
 				}
 				NTB_LEADER_BEGIN

@@ -53,7 +53,7 @@ def config1(nb, oracle, tmp_path_factory):
     w = bench.WORKLOADS["100Mbp_k25_1GiB_m0"]
     dev = torch.device("cuda", 0)
     filt = torch.zeros(w["fbytes"] + 64, dtype=torch.uint8, device=dev)
-    bloom = nb.BloomFilter.wrap_device(filt.data_ptr(), w["fbytes"], bench.K, bench.H, counting=False, device=0)
+    bloom = nb.BloomFilter.wrap_device(filt.data_ptr(), w["fbytes"], w["k"], w["h"], counting=False, device=0)
     buf, offs = bench.build_workload(w, dev, 0, bloom, nb)
     tmp = tmp_path_factory.mktemp("config1")
     fpath = str(tmp / "reads_k25.bf")

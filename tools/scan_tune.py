@@ -23,11 +23,12 @@ def main():
     dev = torch.device("cuda", 0)
     torch.cuda.set_device(0)
     filt = torch.zeros(w["fbytes"] + 64, dtype=torch.uint8, device=dev)
-    bloom = nb.BloomFilter.wrap_device(filt.data_ptr(), w["fbytes"], bench.K, bench.H, counting=False, device=0)
+    bloom = nb.BloomFilter.wrap_device(filt.data_ptr(), w["fbytes"], w["k"], w["h"], counting=bool(w.get("counting")), device=0)
     buf, offs = bench.build_workload(w, dev, 0, bloom, nb)
+    bench.finish_filter(w, filt, dev)
     torch.cuda.synchronize()
     batch = nb.Batch.wrap_device(buf.data_ptr(), offs, device=0)
-    params = nb.default_params(mode=w["mode"])
+    params = nb.default_params(mode=w["mode"], snv=int(w.get("snv", 0)))
     base_env = dict(os.environ)
     for cfg in (args or [""]):
         os.environ.clear()
@@ -62,7 +63,7 @@ def main():
                 print(json.dumps({"e2e_call_ms": round(1000 * (t2 - t1), 1), "free_ms": round(1000 * (t4 - t3), 1),
                                   "h2d": round(d["ms_h2d"], 1), "scan": round(d["ms_scan"], 1), "walk": round(d["ms_walk"], 1),
                                   "host": round(d["ms_host"], 1), "d2h": round(d["ms_d2h"], 1)}), flush=True)
-        print(json.dumps({"env": cfg, "ms_scan": [round(o["ms_scan"], 2) for o in out], "ms_walk": round(st["ms_walk"], 2), "ms_host": round(st["ms_host"], 2),
+        print(json.dumps({"env": cfg, "ms_scan": [round(o["ms_scan"], 2) for o in out], "ms_pre": round(st["ms_pre"], 2), "ms_walk": round(st["ms_walk"], 2), "ms_host": round(st["ms_host"], 2),
                           "launches": st["kernel_launches"], "sites": st["sites"], "edits": st["edits"]}), flush=True)
 
 
