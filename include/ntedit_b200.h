@@ -57,14 +57,23 @@ typedef struct ntb_filter_info {
 int ntb_filter_load(const char* path, int device, ntb_filter** out);
 /* Empty filter on the device (builder side; src/ntedit_make_genome_bf.cpp:143-150). */
 int ntb_filter_create(uint64_t bytes, uint32_t k, uint32_t hash_num, int counting, int device, ntb_filter** out);
-/* Wrap filter bytes that already live on `device` (e.g. received through a NCCL broadcast); not owned. */
+/* Wrap filter bytes that already live on `device` (e.g. received through a NCCL broadcast); not owned.  `dev_bytes` must be
+ * 16-byte aligned (NTB_EINVAL otherwise); inserting into a wrapped filter additionally needs `bytes` to be a multiple of 4
+ * (the builder updates whole 32-bit words). */
 int ntb_filter_wrap_device(void* dev_bytes, uint64_t bytes, uint32_t k, uint32_t hash_num, int counting, int device,
                            ntb_filter** out);
+/* A replica of `src` on another device of the same process: one device-to-device copy (NVLink / NVSwitch peer copy where the
+ * devices are peers) instead of reading the file once per GPU -- the "single broadcast at load" of a multi-GPU run
+ * (ntedit.cpp:2438 loads one filter that every OpenMP thread shares). */
+int ntb_filter_replicate(ntb_filter* src, int device, ntb_filter** out);
 int ntb_filter_get_info(ntb_filter* f, ntb_filter_info* info);
 void* ntb_filter_device_ptr(ntb_filter* f);
 /* Insert every canonical all-ACGT k-mer of the contigs (btllib KmerBloomFilter::insert(seq) as used by
- * src/ntedit_make_genome_bf.cpp:151-156).  Bit filter: atomic OR.  Counting filter: every one of the
- * hash_num counters is incremented, saturating at 255. */
+ * src/ntedit_make_genome_bf.cpp:151-156).  Bit filter: atomic OR -- the arrays btllib builds.  Counting filter (our addition;
+ * the reference builds none itself): EVERY one of the hash_num counters is incremented, saturating at 255.  This is NOT
+ * btllib's CountingBloomFilter::insert, which raises only the counters equal to the current minimum (an update whose
+ * result depends on the insertion order, so no parallel builder can reproduce a sequential one byte for byte): filters
+ * built here count collisions higher than ntStat / btllib ones do.  Polishing reads any counting filter the same way. */
 int ntb_filter_insert(ntb_filter* f, const char* bases, const uint64_t* offsets, uint64_t n_contigs);
 int ntb_filter_insert_batch(ntb_filter* f, const ntb_batch* b);
 /* Write the btllib on-disk format (src/ntedit_make_genome_bf.cpp:158-162). */

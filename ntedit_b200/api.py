@@ -67,6 +67,12 @@ class BloomFilter:
                                                   C.byref(h)))
         return cls(h)
 
+    def replicate(self, device):
+        """A copy of this filter on another device (one device-to-device copy)."""
+        h = C.c_void_p()
+        _l.check(_l.load().ntb_filter_replicate(self._h, device, C.byref(h)))
+        return BloomFilter(h)
+
     def info(self, refresh=False):
         if self._info is None or refresh:
             fi = _l.FilterInfo()

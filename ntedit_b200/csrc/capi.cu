@@ -437,7 +437,15 @@ struct CudaBackend
 		return NTB_OK;
 	}
 
-	~CudaBackend() { workspace_release(ws); }
+	~CudaBackend()
+	{
+		// streamed upload copies may still target the workspace's text buffer (error paths): let them land before another
+		// caller can check the workspace out
+		if (ws && batch && batch->up_stream && !batch->owns_text) {
+			cudaStreamSynchronize(batch->up_stream);
+		}
+		workspace_release(ws);
+	}
 
 	static uint64_t env_u64(const char* name, uint64_t dflt)
 	{
@@ -1057,6 +1065,9 @@ ntb_filter_wrap_device(void* dev_bytes, uint64_t bytes, uint32_t k, uint32_t has
 	if (!out || !dev_bytes || bytes == 0 || k == 0 || hash_num == 0 || hash_num > HMAX) {
 		return fail(NTB_EINVAL, "bad filter geometry");
 	}
+	if (((uintptr_t)dev_bytes & 15u) != 0) {
+		return fail(NTB_EINVAL, "wrapped filter bytes must be 16-byte aligned");
+	}
 	int rc = select_device(device);
 	if (rc != NTB_OK) {
 		return rc;
@@ -1077,6 +1088,36 @@ ntb_filter_wrap_device(void* dev_bytes, uint64_t bytes, uint32_t k, uint32_t has
 }
 
 int
+ntb_filter_replicate(ntb_filter* src, int device, ntb_filter** out)
+{
+	if (!src || !out) {
+		return fail(NTB_EINVAL, "NULL argument");
+	}
+	ntb_filter* f = nullptr;
+	int rc = ntb_filter_create(src->bytes, src->k, src->h, src->counting, device, &f); // selects `device`
+	if (rc != NTB_OK) {
+		return rc;
+	}
+	if (device != src->device) {
+		int can = 0;
+		if (cudaDeviceCanAccessPeer(&can, device, src->device) == cudaSuccess && can) {
+			const cudaError_t pe = cudaDeviceEnablePeerAccess(src->device, 0); // direct NVLink path; without it the copy is staged
+			if (pe != cudaSuccess) {
+				cudaGetLastError(); // already enabled (or refused): cudaMemcpyPeer works either way
+			}
+		}
+	}
+	const cudaError_t e = cudaMemcpyPeer(f->d, device, src->d, src->device, src->bytes);
+	if (e != cudaSuccess) {
+		ntb_filter_free(f);
+		return cuda_fail(e, "cudaMemcpyPeer(filter)");
+	}
+	f->fpr = src->fpr;
+	*out = f;
+	return NTB_OK;
+}
+
+int
 ntb_filter_load(const char* path, int device, ntb_filter** out)
 {
 	if (!path || !out) {
@@ -1092,33 +1133,64 @@ ntb_filter_load(const char* path, int device, ntb_filter** out)
 	if (rc != NTB_OK) {
 		return rc;
 	}
-	// stream the payload through a pinned staging buffer
+	// stream the payload through two pinned staging buffers: the file read of one piece overlaps the upload of the other
 	const size_t chunk = (size_t)64 << 20;
-	char* stage = nullptr;
-	cudaError_t e = cudaMallocHost((void**)&stage, chunk);
+	char* stage[2] = { nullptr, nullptr };
+	cudaStream_t cs = nullptr;
+	cudaEvent_t done_ev[2] = { nullptr, nullptr };
+	cudaError_t e = cudaMallocHost((void**)&stage[0], chunk);
+	if (e == cudaSuccess) {
+		e = cudaMallocHost((void**)&stage[1], chunk);
+	}
+	if (e == cudaSuccess) {
+		e = cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking);
+	}
+	for (int i = 0; i < 2 && e == cudaSuccess; i++) {
+		e = cudaEventCreateWithFlags(&done_ev[i], cudaEventDisableTiming);
+	}
+	auto cleanup = [&]() {
+		if (cs) {
+			cudaStreamSynchronize(cs);
+			cudaStreamDestroy(cs);
+		}
+		for (int i = 0; i < 2; i++) {
+			if (done_ev[i]) {
+				cudaEventDestroy(done_ev[i]);
+			}
+			cudaFreeHost(stage[i]);
+		}
+	};
 	if (e != cudaSuccess) {
+		cleanup();
 		ntb_filter_free(f);
 		return cuda_fail(e, "cudaMallocHost");
 	}
 	FILE* fp = std::fopen(path, "rb");
 	bool ok = fp && fseeko(fp, (off_t)hdr.data_offset, SEEK_SET) == 0;
 	uint64_t done = 0;
-	while (ok && done < hdr.bytes) {
+	for (int i = 0; ok && e == cudaSuccess && done < hdr.bytes; i ^= 1) {
+		e = cudaEventSynchronize(done_ev[i]); // the buffer's previous upload (a fresh event is complete)
+		if (e != cudaSuccess) {
+			break;
+		}
 		const size_t want = (size_t)std::min<uint64_t>(chunk, hdr.bytes - done);
-		if (std::fread(stage, 1, want, fp) != want) {
+		if (std::fread(stage[i], 1, want, fp) != want) {
 			ok = false;
 			break;
 		}
-		e = cudaMemcpy(f->d + done, stage, want, cudaMemcpyHostToDevice);
-		if (e != cudaSuccess) {
-			break;
+		e = cudaMemcpyAsync(f->d + done, stage[i], want, cudaMemcpyHostToDevice, cs);
+		if (e == cudaSuccess) {
+			e = cudaEventRecord(done_ev[i], cs);
 		}
 		done += want;
 	}
 	if (fp) {
 		std::fclose(fp);
 	}
-	cudaFreeHost(stage);
+	if (e == cudaSuccess) {
+		e = cudaStreamSynchronize(cs);
+	}
+	cleanup();
 	if (e != cudaSuccess) {
 		ntb_filter_free(f);
 		return cuda_fail(e, "cudaMemcpy(filter)");
@@ -1181,6 +1253,9 @@ ntb_filter_insert_batch(ntb_filter* f, const ntb_batch* b)
 	}
 	if (f->k < 2 || f->k > KMAX) {
 		return fail(NTB_EINVAL, "unsupported k");
+	}
+	if (!f->owned && (f->bytes & 3u) != 0) {
+		return fail(NTB_EINVAL, "inserting into a wrapped filter needs a size that is a multiple of 4 bytes");
 	}
 	int rc = select_device(f->device);
 	if (rc != NTB_OK) {

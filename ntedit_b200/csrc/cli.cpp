@@ -212,6 +212,8 @@ process_batch(std::unique_ptr<Batch> b, ntb_filter* bloom, ntb_filter* rep, cons
 	BatchOut out;
 	ntb_result* res = nullptr;
 	if (ntb_polish_batch(bloom, rep, &opt.p, &b->bases[0], b->offsets.data(), b->names.size(), &res) != NTB_OK) {
+		std::cerr << PROGRAM ": error: polishing failed in the batch of " << b->names.size() << " sequence(s) from `" << b->names.front() << "' to `"
+		          << b->names.back() << "'; the output files are incomplete\n";
 		die_ntb("ntb_polish_batch");
 	}
 	const size_t n = b->names.size();
@@ -360,11 +362,30 @@ main(int argc, char** argv)
 	// ---- filters: one replica per device (ntedit.cpp:2438-2461)
 	std::cout << "---------- loading Bloom filter from file           : " << now_str() << "\n";
 	std::vector<ntb_filter*> bloom((size_t)opt.gpus, nullptr), rep((size_t)opt.gpus, nullptr);
-	for (int d = 0; d < opt.gpus; d++) {
-		if (ntb_filter_load(opt.bloom.c_str(), d, &bloom[(size_t)d]) != NTB_OK) {
-			std::cerr << PROGRAM ": error: Bloom filter file supplied (-r) is incorrect: " << ntb_last_error() << "\n";
-			return EXIT_FAILURE;
+	// the file is read once; the other devices get device-to-device replicas (NVLink peer copies), all at the same time
+	auto load_replicated = [&](const std::string& path, std::vector<ntb_filter*>& fs, const char* what) -> bool {
+		if (ntb_filter_load(path.c_str(), 0, &fs[0]) != NTB_OK) {
+			std::cerr << PROGRAM ": error: " << what << " is incorrect: " << ntb_last_error() << "\n";
+			return false;
 		}
+		std::vector<std::future<std::string>> copies;
+		for (int d = 1; d < opt.gpus; d++) {
+			copies.push_back(std::async(std::launch::async, [&fs, d]() -> std::string {
+				return ntb_filter_replicate(fs[0], d, &fs[(size_t)d]) == NTB_OK ? std::string() : std::string(ntb_last_error());
+			}));
+		}
+		bool ok = true;
+		for (auto& c : copies) {
+			const std::string err = c.get();
+			if (!err.empty()) {
+				std::cerr << PROGRAM ": error: cannot replicate the Bloom filter: " << err << "\n";
+				ok = false;
+			}
+		}
+		return ok;
+	};
+	if (!load_replicated(opt.bloom, bloom, "Bloom filter file supplied (-r)")) {
+		return EXIT_FAILURE;
 	}
 	ntb_filter_info fi;
 	if (ntb_filter_get_info(bloom[0], &fi) != NTB_OK) {
@@ -430,11 +451,8 @@ main(int argc, char** argv)
 
 	if (!opt.bloomrep.empty()) { // ntedit.cpp:2566-2590
 		std::cout << "---------- loading secondary Bloom filter from file : " << now_str() << "\n";
-		for (int d = 0; d < opt.gpus; d++) {
-			if (ntb_filter_load(opt.bloomrep.c_str(), d, &rep[(size_t)d]) != NTB_OK) {
-				std::cerr << PROGRAM ": error: secondary Bloom filter file supplied (-e) is incorrect: " << ntb_last_error() << "\n";
-				return EXIT_FAILURE;
-			}
+		if (!load_replicated(opt.bloomrep, rep, "secondary Bloom filter file supplied (-e)")) {
+			return EXIT_FAILURE;
 		}
 		ntb_filter_info ri;
 		ntb_filter_get_info(rep[0], &ri);
@@ -512,6 +530,10 @@ main(int argc, char** argv)
 	dfout.close();
 	rfout.close();
 	vfout.close();
+	if (!dfout || !rfout || !vfout) {
+		std::cerr << PROGRAM ": error: writing the output files with prefix `" << opt.prefix << "' failed (disk full?)\n";
+		return EXIT_FAILURE;
+	}
 	const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_begin).count();
 	std::cout << "Processed " << n_read << " sequences: " << tot_contigs << " polished (" << tot_bases << " bases, " << tot_edits << " edits) in " << secs
 	          << " s" << std::endl;

@@ -383,6 +383,23 @@ policy_evict_last()
 	return p;
 }
 
+// a probe record leaves the SM once and is read once by the probe kernel much later: keep it from displacing the filter region
+// the probe kernel holds in L2 (NTB_BIN_STORE_HINT: 0 plain store, 1 st.global.cs, 2 L2 evict-first policy)
+#ifndef NTB_BIN_STORE_HINT
+#define NTB_BIN_STORE_HINT 0
+#endif
+__device__ __forceinline__ void
+st_record(uint64_t* p, uint64_t v, uint64_t policy)
+{
+#if NTB_BIN_STORE_HINT == 1
+	asm volatile("st.global.cs.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+#elif NTB_BIN_STORE_HINT == 2
+	asm volatile("st.global.L2::cache_hint.u64 [%0], %1, %2;" ::"l"(p), "l"(v), "l"(policy) : "memory");
+#else
+	*p = v;
+#endif
+}
+
 // the probe a record stands for, done on the spot: is the k-mer's bit clear / its counter below the threshold?
 template<bool COUNTING>
 __device__ __forceinline__ bool
@@ -442,6 +459,7 @@ bin_kernel(const __grid_constant__ BinArgs A)
 	const uint32_t nb = A.n_buckets;
 	const uint32_t cap = A.bucket_cap;
 	const uint32_t thr = a.min_threshold > 1u ? a.min_threshold : 1u;
+	const uint64_t pol_stream = NTB_BIN_STORE_HINT == 2 ? policy_evict_first() : 0;
 
 	uint64_t tile = blockIdx.x;
 	uint32_t phase[BIN_STAGES];
@@ -576,7 +594,7 @@ bin_kernel(const __grid_constant__ BinArgs A)
 				const uint64_t rec = sorted[j];
 				const uint32_t idx = gbase[bucket] + (j - off[bucket]);
 				if (idx < cap) {
-					A.records[(uint64_t)bucket * cap + idx] = rec;
+					st_record(&A.records[(uint64_t)bucket * cap + idx], rec, pol_stream);
 				} else {
 					// the bucket's rows are full (heavily repeated k-mers): probe directly
 					const uint64_t slot = ((uint64_t)bucket << rl) | (rec >> 32);

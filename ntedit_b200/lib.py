@@ -101,6 +101,7 @@ SYMBOLS = {
     "ntb_filter_load": (C.c_int, [C.c_char_p, C.c_int, C.POINTER(_VP)]),
     "ntb_filter_create": (C.c_int, [C.c_uint64, C.c_uint32, C.c_uint32, C.c_int, C.c_int, C.POINTER(_VP)]),
     "ntb_filter_wrap_device": (C.c_int, [_VP, C.c_uint64, C.c_uint32, C.c_uint32, C.c_int, C.c_int, C.POINTER(_VP)]),
+    "ntb_filter_replicate": (C.c_int, [_VP, C.c_int, C.POINTER(_VP)]),
     "ntb_filter_get_info": (C.c_int, [_VP, C.POINTER(FilterInfo)]),
     "ntb_filter_device_ptr": (_VP, [_VP]),
     "ntb_filter_insert": (C.c_int, [_VP, _VP, _U64P, C.c_uint64]),

@@ -1,12 +1,18 @@
 """BASELINE.json configurations as parity cases at (or scaled towards) their stated sizes.
 
+* configs[2] -- the configuration bench.py times by default: 3 Gbp human-like draft, 4 GiB k=25 Bloom filter, mode 1 -- at
+  FULL size, `ntedit-b200` against the unmodified reference binary, compared per contig through digests (set
+  NTB_SKIP_FULL_SIZE=1 to leave this one out of a quick run).
+
 * configs[1] -- synthetic 100 Mbp draft, 1 GiB k=25 Bloom filter, mode 0 -- at FULL size: `ntedit-b200` against the
   unmodified reference binary on the same FASTA and filter files (reference run with every host core; its output order
   is then nondeterministic, ntedit.cpp:2145-2150, so records are compared per contig).
 * configs[4] -- conifer-like draft of very many short contigs, mode 0 -- the same 100 Mbp re-cut into ~20 k log-normal
   contigs (N50 ~ 20 kbp, some below the -z cut-off), same filter.
-* configs[3] -- k=32 counting Bloom filter, mode 2, -s 1 -- scaled to a size the C oracle finishes in seconds.
+* configs[3] -- k=32 counting Bloom filter, mode 2, -s 1 -- at 100 Mbp with a 1 GiB counting filter against the reference
+  binary, and scaled to a size the C oracle finishes in seconds.
 """
+import hashlib
 import os
 import subprocess
 import sys
@@ -155,3 +161,146 @@ def test_config3_like_cbf_k32_snv_mode2(nb, oracle):
     assert fa == ofa and tsv == otsv and vcf == ovcf
     assert vcf.count(b"\n") > 300
     ofilt.free()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# full-size cases: files are compared through per-contig digests so that two 3 GB outputs never sit in memory as dicts
+def fasta_digests(path):
+    out = {}
+    with open(path, "rb") as fh:
+        while True:
+            hdr = fh.readline()
+            if not hdr:
+                break
+            seq = fh.readline()
+            out[hdr.rstrip(b"\n")] = hashlib.blake2b(seq, digest_size=16).digest()
+    return out
+
+
+def rows_digests(path, comment=b"#"):
+    """header line (first line, TSV only), {contig: digest of its rows in file order}"""
+    first = None
+    acc = {}
+    with open(path, "rb") as fh:
+        for ln in fh:
+            if first is None:
+                first = ln
+                if comment is None:
+                    continue
+            if comment is not None and ln.startswith(comment):
+                continue
+            key = ln.split(b"\t", 1)[0]
+            h = acc.get(key)
+            if h is None:
+                h = acc[key] = hashlib.blake2b(digest_size=16)
+            h.update(ln)
+    return first, {k: v.digest() for k, v in acc.items()}
+
+
+def write_workload_files(nb, name, tmp):
+    import torch
+    sys.path.insert(0, ROOT)
+    import bench
+    w = bench.WORKLOADS[name]
+    dev = torch.device("cuda", 0)
+    filt = torch.zeros(w["fbytes"] + 64, dtype=torch.uint8, device=dev)
+    bloom = nb.BloomFilter.wrap_device(filt.data_ptr(), w["fbytes"], w["k"], w["h"], counting=bool(w.get("counting")), device=0)
+    buf, offs = bench.build_workload(w, dev, 0, bloom, nb)
+    bench.finish_filter(w, filt, dev)
+    fpath = str(tmp / "reads.bf")
+    bloom.save(fpath)
+    host = buf.cpu().numpy()
+    del buf, filt, bloom
+    torch.cuda.empty_cache()
+    draft = str(tmp / "draft.fa")
+    with open(draft, "wb") as fh:
+        for i in range(len(offs) - 1):
+            s, e = int(offs[i]), int(offs[i + 1]) - 1
+            fh.write(b">contig%d len=%d\n" % (i, e - s))
+            fh.write(host[s:e].tobytes())
+            fh.write(b"\n")
+    return draft, fpath, len(offs) - 1, w
+
+
+def compare_files_per_contig(ours, ref):
+    gfa, rfa = fasta_digests(ours + "_edited.fa"), fasta_digests(ref + "_edited.fa")
+    assert gfa.keys() == rfa.keys()
+    bad = [h for h in gfa if gfa[h] != rfa[h]]
+    assert not bad, "contigs with different polished sequence: %r" % bad[:3]
+    gh, gt = rows_digests(ours + "_changes.tsv", comment=None)
+    rh, rt = rows_digests(ref + "_changes.tsv", comment=None)
+    assert gh == rh
+    assert gt.keys() == rt.keys()
+    bad = [h for h in gt if gt[h] != rt[h]]
+    assert not bad, "contigs with different change rows: %r" % bad[:3]
+    _, gv = rows_digests(ours + "_variants.vcf")
+    _, rv = rows_digests(ref + "_variants.vcf")
+    assert gv == rv
+    return len(gfa), len(gt)
+
+
+def run_cli_and_reference(oracle, lib, draft, filt, tmp, flags, gpus=1):
+    ours = str(tmp / "ours")
+    cmd = [lib.CLI, "-f", draft, "-r", filt, "-b", ours, "-t", "8"] + [str(x) for x in flags]
+    if gpus > 1:
+        cmd += ["--gpus", str(gpus)]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=1200)
+    assert r.returncode == 0, r.stderr.decode(errors="replace")[-2000:]
+    ref = str(tmp / "ref")
+    r = subprocess.run([oracle.REF_BIN, "-f", draft, "-r", filt, "-b", ref, "-t", str(os.cpu_count() or 4)] + [str(x) for x in flags],
+                       stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=2400)
+    assert r.returncode == 0, r.stderr.decode(errors="replace")[-2000:]
+    return ours, ref
+
+
+@pytest.mark.skipif(os.environ.get("NTB_SKIP_FULL_SIZE") == "1", reason="NTB_SKIP_FULL_SIZE=1")
+def test_config2_full_size_cli_vs_reference(nb, oracle, tmp_path):
+    """The workload bench.py times (3 Gbp, 24 contigs of 50-250 Mbp + 2000 x 100 kbp, 4 GiB filter, mode 1), every byte of the
+    three output files against the unmodified reference."""
+    if not oracle.have_ref():
+        pytest.skip("oracle/_ref/ntedit_ref not present")
+    import shutil
+    if shutil.disk_usage(str(tmp_path)).free < (24 << 30):
+        pytest.skip("needs 24 GB of scratch space")
+    from ntedit_b200 import lib
+    draft, filt, n, w = write_workload_files(nb, "3Gbp_k25_4GiB_m1", tmp_path)
+    ours, ref = run_cli_and_reference(oracle, lib, draft, filt, tmp_path, ("-m", w["mode"]))
+    n_contigs, n_changed = compare_files_per_contig(ours, ref)
+    assert n_contigs == n == 2024 and n_changed == n
+    for sfx in ("_edited.fa", "_changes.tsv", "_variants.vcf"):
+        os.remove(ours + sfx)
+        os.remove(ref + sfx)
+    os.remove(draft)
+    os.remove(filt)
+
+
+def test_config3_100Mbp_cbf_k32_snv_mode2_vs_reference(nb, oracle, tmp_path):
+    """configs[3] scaled to 100 Mbp / 1 GiB: k=32 counting filter (counts x30), -m 2 -s 1, against the reference binary."""
+    if not oracle.have_ref():
+        pytest.skip("oracle/_ref/ntedit_ref not present")
+    from ntedit_b200 import lib
+    sys.path.insert(0, ROOT)
+    import bench
+    bench.WORKLOADS["_c3_100Mbp"] = dict(bench.WORKLOADS["3Gbp_k32_8GiB_cbf_m2_snv"], total=100_000_000, fbytes=1 << 30, n_large=60,
+                                         n_small=400, small_len=50_000)
+    draft, filt, n, w = write_workload_files(nb, "_c3_100Mbp", tmp_path)
+    ours, ref = run_cli_and_reference(oracle, lib, draft, filt, tmp_path, ("-m", 2, "-s", 1))
+    n_contigs, n_changed = compare_files_per_contig(ours, ref)
+    assert n_contigs == n
+
+
+def test_config4_like_two_gpus(nb, oracle, config1):
+    """configs[4]-shaped: > 20 k short contigs sharded over two GPUs by the command line tool, merged in input order."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    from ntedit_b200 import lib
+    c = config1
+    draft = str(c["tmp"] / "draft_conifer_like.fa")
+    if not os.path.exists(draft):
+        pytest.skip("test_config4_like_many_short_contigs did not run")
+    tmp = c["tmp"] / "two"
+    tmp.mkdir()
+    ours, ref = run_cli_and_reference(oracle, lib, draft, c["filter"], tmp, ("-m", 0), gpus=2)
+    n_contigs, _ = compare_files_per_contig(ours, ref)
+    assert n_contigs > 10_000
