@@ -246,7 +246,7 @@ struct Workspace
 	size_t cap_items = 0;
 	PendingSite* d_pending = nullptr;
 	size_t cap_pending = 0;
-	cudaEvent_t ev_pre0 = nullptr, ev_pre1 = nullptr;
+	cudaEvent_t ev_pre0 = nullptr, ev_pre1 = nullptr, ev_pre_mid = nullptr;
 	Counters* h_ctr_pre = nullptr; // pinned: the counters after the pre-evaluation passes (diagnostics)
 	// pinned host mirrors
 	Task* h_tasks = nullptr;
@@ -278,6 +278,9 @@ struct Workspace
 		}
 		if (ev_pre1) {
 			cudaEventDestroy(ev_pre1);
+		}
+		if (ev_pre_mid) {
+			cudaEventDestroy(ev_pre_mid);
 		}
 		cudaFreeHost(h_tasks);
 		cudaFreeHost(h_results);
@@ -685,6 +688,7 @@ struct CudaBackend
 		if (!ws->ev_pre0) {
 			NTB_BE(cudaEventCreate(&ws->ev_pre0));
 			NTB_BE(cudaEventCreate(&ws->ev_pre1));
+			NTB_BE(cudaEventCreate(&ws->ev_pre_mid));
 			NTB_BE(cudaHostAlloc((void**)&ws->h_ctr_pre, sizeof(Counters), cudaHostAllocDefault));
 		}
 		a.table = ws->d_table;
@@ -698,6 +702,7 @@ struct CudaBackend
 		NTB_BE(cudaMemsetAsync(ws->d_ctr, 0, sizeof(Counters), stream));
 		NTB_BE(launch_heads(a, stream));
 		NTB_BE(launch_presite(a, false, stream));
+		NTB_BE(cudaEventRecord(ws->ev_pre_mid, stream));
 		NTB_BE(launch_presite(a, true, stream));
 		NTB_BE(cudaMemcpyAsync(ws->h_ctr_pre, ws->d_ctr, sizeof(Counters), cudaMemcpyDeviceToHost, stream));
 		NTB_BE(cudaEventRecord(ws->ev_pre1, stream));
@@ -796,6 +801,9 @@ struct CudaBackend
 				ms_pre += ms;
 				if (std::getenv("NTB_DEBUG_TASKS")) {
 					const Counters& pc = *ws->h_ctr_pre;
+					float ms1 = 0;
+					cudaEventElapsedTime(&ms1, ws->ev_pre0, ws->ev_pre_mid);
+					std::fprintf(stderr, "[ntb] pre-evaluation: first pass %.2f ms, second pass %.2f ms\n", ms1, ms - ms1);
 					std::fprintf(stderr, "[ntb] pre-evaluation: %.2f ms, %u heads (cap %zu), %u pending (cap %zu), %u records dropped, table %zu slots\n", ms,
 					             pc.n_items, ws->cap_items, pc.n_pending, ws->cap_pending, pc.n_dropped, table_slots);
 				}

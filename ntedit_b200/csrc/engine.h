@@ -300,7 +300,7 @@ struct WalkerState
 	bool need_seed, do_seed, site_now;
 
 	// contig text around the window
-	uint8_t tc[TEXT_CACHE];
+	alignas(4) uint8_t tc[TEXT_CACHE];
 	uint32_t tc_base, tc_n;
 
 	// ---- scratch of the site being evaluated
@@ -351,6 +351,7 @@ struct WalkerState
 	uint32_t use_rec;            // this site's decision comes from a pre-evaluated record (its SITE_* state; 0 = evaluate here)
 	bool rec_hash;               // ... and committing it needs the window's hash and the text cache
 	uint8_t rec_fl;              // ... its EV_TOUCHED flag
+	bool rec_second;             // ... it was completed by the second pre-evaluation pass (diagnostics)
 	uint32_t rec_slot;           // pre-evaluation: slot of the record being written
 	bool pre_more;               // pre-evaluation: the chain goes on with the next position
 	// insertion candidates without rolling: hash state after q+1 rolls of an insertion of length L whose inserted chars
@@ -2202,15 +2203,17 @@ struct Walker
 		return true;
 	}
 
-	// all lanes; first pass: the site at head `pos` and the chain behind it.  Sites that reach tryIndels are left to the
-	// second pass and the chain goes on as if they had failed; if they do not, the records behind them are simply never
-	// looked up.
-	NTB_FN void pre_run(uint32_t task_idx, uint32_t pos)
+	// all lanes: the site at `pos` and the chain behind it.  First pass (allow_indels false): `pos` is a head; a site that
+	// reaches tryIndels is left to the second pass as SITE_PENDING and ends the chain -- whether the main loop goes on
+	// behind it is only known once its indels have been tried.  Second pass (allow_indels true): `pos` is such a pending
+	// site; the chain goes on from it with everything evaluated in place.
+	NTB_FN void pre_run(uint32_t task_idx, uint32_t pos, bool allow_indels)
 	{
 		for (uint32_t n = 0; n < SITE_CHAIN_MAX; n++) {
 			pre_seed(pos);
-			const uint32_t st = evaluate_site_core(false);
+			const uint32_t st = evaluate_site_core(allow_indels);
 			NTB_LEADER_BEGIN
+			// (the second pass finds the slot its first site was given)
 			const uint32_t slot = site_table_insert(S.io.table, S.io.table_mask, S.io.goff + pos + 1);
 			S.rec_slot = slot;
 			if (slot == NONE32) {
@@ -2223,6 +2226,9 @@ struct Walker
 				SiteRec r;
 				r.key = S.io.goff + pos + 1;
 				pre_fill(r, st);
+				if (allow_indels) {
+					r.flags |= SITE_FL_SECOND;
+				}
 				if (st == SITE_PENDING) {
 					uint32_t idx;
 #if defined(__CUDA_ARCH__)
@@ -2240,8 +2246,8 @@ struct Walker
 				}
 				S.io.table[slot] = r;
 			}
-			// go on behind a site that made no edit (or whose tryIndels are still to come)
-			S.pre_more = slot != NONE32 && (st != SITE_DONE || S.s.best_type == 0);
+			// go on behind a site that made no edit
+			S.pre_more = slot != NONE32 && (st == SITE_NONE || (st == SITE_DONE && S.s.best_type == 0));
 			NTB_LEADER_END
 			if (!S.pre_more) {
 				break;
@@ -2252,19 +2258,6 @@ struct Walker
 				break;
 			}
 		}
-	}
-
-	// all lanes; second pass: the whole evaluation of a site the first pass left in front of tryIndels
-	NTB_FN void pre_finish(uint32_t pos, uint32_t slot)
-	{
-		pre_seed(pos);
-		const uint32_t st = evaluate_site_core(true);
-		NTB_LEADER_BEGIN
-		SiteRec r;
-		r.key = S.io.goff + pos + 1;
-		pre_fill(r, st);
-		S.io.table[slot] = r;
-		NTB_LEADER_END
 	}
 
 	// all lanes: the record of text position g (nullptr when there is none or it is not complete)
@@ -2314,6 +2307,7 @@ struct Walker
 		S.site_ok = true;
 		S.skip_advance = false;
 		S.use_rec = r.state;
+		S.rec_second = (r.flags & SITE_FL_SECOND) != 0;
 		S.rec_hash = r.state == SITE_DONE && (r.best_type >= 2 || (r.best_type == 1 && !(r.flags & SITE_FL_QUIET)));
 		if (r.state != SITE_DONE) {
 			return;
@@ -2401,14 +2395,33 @@ struct Walker
 		}
 	}
 
-	// all lanes: load TEXT_CACHE bytes of contig text starting at `base`
+	// all lanes: load TEXT_CACHE bytes of contig text starting at `base` (bytes behind the contig's end read as 0)
 	NTB_FN void fill_cache(uint32_t base)
 	{
 		warp_sync();
+#if defined(__CUDA_ARCH__)
+		// aligned 32-bit loads (the contig starts at an arbitrary byte of the batch buffer; SCAN_HALO bytes in front of the
+		// buffer and its zero padding behind make the rounded-out words readable), shifted into place
+		const uint8_t* src = S.io.text + base;
+		const uint32_t shift = (uint32_t)(reinterpret_cast<uintptr_t>(src) & 3u);
+		const uint32_t* words = reinterpret_cast<const uint32_t*>(src - shift);
+		uint32_t* dst = reinterpret_cast<uint32_t*>(S.tc);
+		for (uint32_t j = lane_id(); j < TEXT_CACHE / 4; j += lane_count()) {
+			const uint32_t lo = words[j], hi = words[j + 1];
+			uint32_t v = __funnelshift_r(lo, hi, 8u * shift);
+			const uint64_t pos = (uint64_t)base + 4u * j;
+			if (pos + 4 > S.io.len) {
+				const uint32_t keep = pos < S.io.len ? (uint32_t)(S.io.len - pos) : 0u; // 0..3 bytes of this word lie inside the contig
+				v &= keep ? (0xFFFFFFFFu >> (8u * (4u - keep))) : 0u;
+			}
+			dst[j] = v;
+		}
+#else
 		for (uint32_t o = lane_id(); o < TEXT_CACHE; o += lane_count()) {
 			const uint64_t pos = (uint64_t)base + o;
 			S.tc[o] = pos < S.io.len ? S.io.text[pos] : (uint8_t)0;
 		}
+#endif
 		if (lane_id() == 0) {
 			S.tc_base = base;
 			S.tc_n = TEXT_CACHE;
@@ -2557,7 +2570,7 @@ struct Walker
 		}
 	}
 
-	// every lane: get ready for pre_run() / pre_finish() on the contig S.io describes
+	// every lane: get ready for pre_run() on the contig S.io describes
 	NTB_FN void pre_begin()
 	{
 		NTB_LEADER_BEGIN
@@ -2944,6 +2957,7 @@ struct Walker
 				atomicAdd(&S.io.ctr->n_rec_used, 1u);
 #elif !defined(__CUDA_ARCH__)
 				S.io.ctr->n_rec_used++;
+				S.io.ctr->n_rec_used2 += S.rec_second ? 1u : 0u;
 #endif
 				NTB_LEADER_END
 				ok = S.site_ok;

@@ -807,7 +807,7 @@ walk_smem_init(uint8_t* walk_smem, const KParams& kp)
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// Pre-evaluation (ntb_common.h: SiteRec; engine.h: pre_run / pre_finish).
+// Pre-evaluation (ntb_common.h: SiteRec; engine.h: pre_run).
 // heads_kernel: one warp per task lists the heads of its nominal range [start, end) -- the ranges partition every contig.
 __global__ void __launch_bounds__(256)
 heads_kernel(const uint32_t* visit, const Task* tasks, uint32_t n_tasks, uint32_t gap, uint2* items, uint32_t cap, Counters* ctr)
@@ -864,7 +864,7 @@ heads_kernel(const uint32_t* visit, const Task* tasks, uint32_t n_tasks, uint32_
 }
 
 // presite_kernel<.., SECOND = false>: first pass, one item (head + chain) per warp at a time, tryIndels left out of the code;
-// <.., SECOND = true>: second pass over the sites the first one left pending.  Same shared-memory layout and persistent-warp
+// <.., SECOND = true>: second pass over the sites the first one left pending (and the chains behind them).  Same shared-memory layout and persistent-warp
 // scheme as walk_kernel.
 template<int NCAP, bool COMMON, bool POW2, bool SECOND>
 __global__ void __launch_bounds__(WALK_THREADS, NTB_WALK_MIN_CTAS)
@@ -889,12 +889,11 @@ presite_kernel(const uint8_t* text, const uint32_t* visit, FilterView bloom, Fil
 		if (i >= n_units) {
 			break;
 		}
-		uint32_t ti, pos, slot = 0;
+		uint32_t ti, pos;
 		if (SECOND) {
 			const PendingSite ps = pending[i];
 			ti = ps.task;
 			pos = ps.pos;
-			slot = ps.slot;
 		} else {
 			const uint2 it = items[i];
 			ti = it.x;
@@ -920,11 +919,7 @@ presite_kernel(const uint8_t* text, const uint32_t* visit, FilterView bloom, Fil
 		}
 		warp_sync();
 		w.pre_begin();
-		if (SECOND) {
-			w.pre_finish(pos, slot);
-		} else {
-			w.pre_run(ti, pos);
-		}
+		w.pre_run(ti, pos, SECOND);
 	}
 }
 

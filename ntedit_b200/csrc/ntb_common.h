@@ -144,6 +144,7 @@ constexpr uint8_t SITE_DONE = 2;    // the decision is in the record
 constexpr uint8_t SITE_PENDING = 3; // stopped in front of tryIndels; completed by the second pre-evaluation pass (else ignored)
 constexpr uint8_t SITE_FL_TOUCHED = 1; // makeEdit's `touched && raw != draft` (EV_TOUCHED of the event)
 constexpr uint8_t SITE_FL_QUIET = 2;   // accepted substitution whose k-1 following windows are no sites: the walker jumps k
+constexpr uint8_t SITE_FL_SECOND = 4;  // completed by the second pass (diagnostics)
 constexpr uint32_t SITE_TABLE_PROBES = 64;  // linear probing gives up after this many slots (insert: the record is dropped)
 constexpr uint32_t SITE_CHAIN_MAX = 64;     // flagged positions one pre-evaluation item follows behind a failed site
 
@@ -169,7 +170,8 @@ struct Counters
 	uint32_t n_pending;  // ... sites waiting for the second pass (tryIndels)
 	uint32_t next_pending;
 	uint32_t n_dropped;  // ... records that found no slot / list entry (the walkers evaluate those sites themselves)
-	uint32_t n_rec_used; // walkers: sites committed from a record
+	uint32_t n_rec_used; // walkers: sites committed from a record (diagnostics)
+	uint32_t n_rec_used2; // ... from a record of the second pass
 	unsigned long long prof[16]; // -DNTB_PHASE_PROF: leader cycles per phase of the walker
 };
 

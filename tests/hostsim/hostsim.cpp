@@ -125,7 +125,7 @@ struct HostBackend
 				io.pending_cap = (uint32_t)pending.size();
 				w.pre_begin();
 				if (pass == 1) {
-					w.pre_finish(pending[u].pos, pending[u].slot);
+					w.pre_run(pending[u].task, pending[u].pos, true);
 					continue;
 				}
 				// heads among the flagged positions of [start, end)
@@ -134,7 +134,7 @@ struct HostBackend
 					const bool f = (visit[g >> 5] >> (g & 31)) & 1u;
 					if (f && W::is_head(visit.data(), t.text_off, (uint32_t)p, w.pre_gap())) {
 						pre_records++;
-						w.pre_run((uint32_t)ti, (uint32_t)p);
+						w.pre_run((uint32_t)ti, (uint32_t)p, false);
 					}
 				}
 			}
@@ -202,8 +202,8 @@ struct HostBackend
 			}
 			delete st;
 			if (std::getenv("HOSTSIM_DEBUG")) {
-				std::fprintf(stderr, "[hostsim] round %zu: %zu tasks, run heads %llu, pending %llu, dropped %llu, sites from records %u\n", rounds.size(),
-				             n_tasks, (unsigned long long)pre_records, (unsigned long long)pre_pending, (unsigned long long)pre_dropped, ctr.n_rec_used);
+				std::fprintf(stderr, "[hostsim] round %zu: %zu tasks, run heads %llu, pending %llu, dropped %llu, sites from records %u (%u of the second pass)\n", rounds.size(),
+				             n_tasks, (unsigned long long)pre_records, (unsigned long long)pre_pending, (unsigned long long)pre_dropped, ctr.n_rec_used, ctr.n_rec_used2);
 			}
 			if (!ctr.overflow) {
 				events.resize(ctr.n_events);
