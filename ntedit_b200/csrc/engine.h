@@ -2045,8 +2045,8 @@ struct Walker
 			if (S.next != NEXT_INDELS) {
 				break;
 			}
-			if (!allow_indels) {
-				return SITE_PENDING;
+			if (!allow_indels && P.max_ins_tries != 0) {
+				return SITE_PENDING; // (with nothing to try, tryIndels returns at once and the loop goes on)
 			}
 			NTB_PROF(11);
 #if defined(NTB_PHASE_PROF) && defined(__CUDA_ARCH__)
@@ -2167,8 +2167,10 @@ struct Walker
 		r.altbase[1] = s.altbase2;
 		r.altbase[2] = s.altbase3;
 		r.indel_len = s.indel_len;
-		for (int i = 0; i < 5; i++) {
-			r.indel[i] = s.indel[i];
+		if (s.best_type == 2) {
+			for (int i = 0; i < 5; i++) {
+				r.indel[i] = i < s.indel_len ? s.indel[i] : 0;
+			}
 		}
 	}
 

@@ -923,6 +923,39 @@ presite_kernel(const uint8_t* text, const uint32_t* visit, FilterView bloom, Fil
 	}
 }
 
+// presite_dense_kernel: the first pass with one THREAD per item (site_dense.h) -- 32 sites per warp in flight, every probe
+// of a stage issued before any is consumed.  Persistent grid, items dealt round-robin.
+constexpr int DENSE_THREADS = 128;
+
+template<int KCAP>
+__global__ void __launch_bounds__(DENSE_THREADS)
+presite_dense_kernel(const uint8_t* text, const uint32_t* visit, FilterView bloom, FilterView rep, const __grid_constant__ KParams kp,
+                     const Task* tasks, const uint2* items, uint32_t items_cap, SiteRec* table, uint32_t table_mask, PendingSite* pending,
+                     uint32_t pending_cap, Counters* ctr)
+{
+	__shared__ uint64_t rot[ROT_WORDS];
+	__shared__ uint8_t cls[256];
+	for (uint32_t q = threadIdx.x; q < ROT_WORDS; q += blockDim.x) {
+		rot[q] = rot_entry(q);
+	}
+	for (uint32_t q = threadIdx.x; q < 256; q += blockDim.x) {
+		cls[q] = class_of(q);
+	}
+	__syncthreads();
+	DenseCtx C;
+	C.kp = &kp;
+	C.bloom = bloom;
+	C.rep = rep;
+	C.rot = rot;
+	C.cls = cls;
+	const uint32_t n = min(ctr->n_items, items_cap);
+	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+		const uint2 it = items[i];
+		const Task task = tasks[it.x];
+		dense_run<KCAP>(C, text + task.text_off, task.len, task.text_off, visit, it.x, it.y, table, table_mask, pending, pending_cap, ctr);
+	}
+}
+
 template<int NCAP, bool COMMON, bool POW2>
 __global__ void __launch_bounds__(WALK_THREADS, NTB_WALK_MIN_CTAS)
 walk_kernel(const uint8_t* text, const uint32_t* visit, FilterView bloom, FilterView rep, const __grid_constant__ KParams kp,
@@ -1178,10 +1211,34 @@ launch_presite_second(const WalkArgs& a, cudaStream_t stream)
 #undef NTB_COMMA_TRUE
 }
 
+template<int KCAP>
+static cudaError_t
+launch_presite_dense_k(const WalkArgs& a, cudaStream_t stream)
+{
+	static OccCache cache;
+	int per_sm = 0;
+	cudaError_t e = walker_occupancy(presite_dense_kernel<KCAP>, cache, 0, DENSE_THREADS, &per_sm);
+	if (e != cudaSuccess) {
+		return e;
+	}
+	presite_dense_kernel<KCAP><<<(unsigned)(a.sm_count * per_sm), DENSE_THREADS, 0, stream>>>(a.text, a.visit, a.bloom, a.rep, a.kp, a.tasks, a.items,
+	                                                                                      a.items_cap, a.table, a.table_mask, a.pending,
+	                                                                                      a.pending_cap, a.ctr);
+	return cudaGetLastError();
+}
+
 cudaError_t
 launch_presite(const WalkArgs& a, bool second, cudaStream_t stream)
 {
-	return second ? launch_presite_second(a, stream) : launch_presite_first(a, stream);
+	if (second) {
+		return launch_presite_second(a, stream);
+	}
+	// NTB_PRESITE_DENSE=0 (testing aid): the warp-per-site form of the first pass
+	const char* dv = std::getenv("NTB_PRESITE_DENSE");
+	if (dv && dv[0] == '0') {
+		return launch_presite_first(a, stream);
+	}
+	return a.kp.k <= 48 ? launch_presite_dense_k<48>(a, stream) : launch_presite_dense_k<(int)KMAX>(a, stream);
 }
 #undef NTB_WALK_DISPATCH
 

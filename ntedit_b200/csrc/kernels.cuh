@@ -4,8 +4,10 @@
 //   K1b bin_kernel + probe_bin_kernel : the same bitmap for filters larger than L2 -- probes become records bucketed by filter
 //                           region, then are served bucket by bucket from the L2-resident region (a direct probe costs a 128-byte
 //                           DRAM line on B200)
-//   K2p heads_kernel + presite_kernel (two passes) : the evaluation of every site the walk can reach with a clean window,
-//                           ahead of the walk, into a table of site records (ntb_common.h: SiteRec)
+//   K2p heads_kernel + presite_dense_kernel + presite_kernel : the evaluation of every site the walk can reach with a clean
+//                           window, ahead of the walk, into a table of site records (ntb_common.h: SiteRec): first pass one
+//                           THREAD per site (site_dense.h: check-missing, gates, substitution trials), second pass one warp
+//                           per site that needs tryIndels
 //   K2  walk_kernel       : one warp per contig segment replays the edit state machine (engine.h) at the flagged positions:
 //                           commits pre-evaluated sites, evaluates the others (dirty windows) one candidate k-mer series per lane
 //                           replaces ntedit.cpp:1808-2116 (check-missing, substitutions, tryIndels, tryDeletion, makeEdit decisions)
@@ -14,6 +16,7 @@
 //   K5  insert_kernel     : filter construction (src/ntedit_make_genome_bf.cpp:151-156)
 #pragma once
 #include "engine.h"
+#include "site_dense.h"
 
 #include <cuda_runtime.h>
 

@@ -6,6 +6,7 @@
 // fuzzed against the reference in a container without a GPU; the GPU tests then only have to show that the CUDA
 // build of the same engine gives the same events.
 #include "../../ntedit_b200/csrc/engine.h"
+#include "../../ntedit_b200/csrc/site_dense.h"
 #include "../../ntedit_b200/csrc/polish_driver.hpp"
 #include "../../ntedit_b200/csrc/writer.hpp"
 
@@ -85,6 +86,7 @@ struct HostBackend
 	}
 
 	std::vector<SiteRec> table;
+	std::string dense_mismatch;
 	uint64_t pre_records = 0, pre_pending = 0, pre_dropped = 0;
 
 	template<class W>
@@ -100,10 +102,43 @@ struct HostBackend
 		table.assign(slots, SiteRec());
 		std::memset(table.data(), 0, slots * sizeof(SiteRec));
 		std::vector<PendingSite> pending(ts ? 8 : (size_t)(total / 32 + 64));
-		Counters ctr = {};
+		Counters ctr = {}, ctr2 = {};
 		WalkerState<352>* st = new WalkerState<352>();
 		W w(*st, kp);
+		const char* dv = std::getenv("HOSTSIM_DENSE");
+		const bool dense = !(dv && dv[0] == '0');
+		const bool check = dense && std::getenv("HOSTSIM_CHECK_DENSE") != nullptr;
+		std::vector<SiteRec> table2(check ? slots : 0);
+		std::vector<PendingSite> pending2(check ? pending.size() : 0);
+		if (check) {
+			std::memset(table2.data(), 0, slots * sizeof(SiteRec));
+		}
+		uint8_t cls_tab[256];
+		for (unsigned c = 0; c < 256; c++) {
+			cls_tab[c] = (uint8_t)(base_code((unsigned char)c) | (rev_code((unsigned char)c) << 3) | (is_accepted_any_case((unsigned char)c) ? 0x40u : 0u));
+		}
+		DenseCtx dctx;
+		dctx.kp = &kp;
+		dctx.bloom = bloom;
+		dctx.rep = rep;
+		dctx.rot = rot.data();
+		dctx.cls = cls_tab;
 		for (int pass = 0; pass < 2; pass++) {
+			if (pass == 1 && check) {
+				// the two forms of the first pass must have produced the same records and the same pending sites
+				if (ctr.n_pending != ctr2.n_pending || ctr.n_dropped != ctr2.n_dropped) {
+					dense_mismatch = "pending / dropped counts differ";
+				}
+				for (size_t q = 0; q < slots && dense_mismatch.empty(); q++) {
+					if (std::memcmp(&table[q], &table2[q], sizeof(SiteRec)) != 0) {
+						char buf[160];
+						std::snprintf(buf, sizeof buf, "record of text position %llu differs (dense state %u type %u, walker state %u type %u)",
+						              (unsigned long long)(table[q].key ? table[q].key : table2[q].key) - 1, table[q].state, table[q].best_type,
+						              table2[q].state, table2[q].best_type);
+						dense_mismatch = buf;
+					}
+				}
+			}
 			const size_t n_units = pass == 0 ? n_tasks : std::min<size_t>(ctr.n_pending, pending.size());
 			for (size_t u = 0; u < n_units; u++) {
 				const size_t ti = pass == 0 ? u : pending[u].task;
@@ -128,13 +163,25 @@ struct HostBackend
 					w.pre_run(pending[u].task, pending[u].pos, true);
 					continue;
 				}
-				// heads among the flagged positions of [start, end)
+				// heads among the flagged positions of [start, end): the dense (thread-per-site) form of the first pass, as the
+				// product runs it; HOSTSIM_DENSE=0 takes the walker form, HOSTSIM_CHECK_DENSE=1 runs both and compares every record
 				for (uint64_t p = t.start; p < t.end; p++) {
 					const uint64_t g = t.text_off + p;
 					const bool f = (visit[g >> 5] >> (g & 31)) & 1u;
 					if (f && W::is_head(visit.data(), t.text_off, (uint32_t)p, w.pre_gap())) {
 						pre_records++;
-						w.pre_run((uint32_t)ti, (uint32_t)p, false);
+						if (dense) {
+							dense_run<(int)KMAX>(dctx, io.text, io.len, io.goff, visit.data(), (uint32_t)ti, (uint32_t)p, table.data(),
+							                     (uint32_t)slots - 1, pending.data(), (uint32_t)pending.size(), &ctr);
+						}
+						if (!dense || check) {
+							if (check) {
+								io.table = table2.data();
+								io.pending = pending2.data();
+								io.ctr = &ctr2;
+							}
+							w.pre_run((uint32_t)ti, (uint32_t)p, false);
+						}
 					}
 				}
 			}
@@ -168,6 +215,10 @@ struct HostBackend
 		// flagged runs per task, first pass (no tryIndels), second pass (the pending ones); HOSTSIM_NO_PRESITE=1 turns it off
 		if (rounds.size() == 1 && !kp.snv && !std::getenv("HOSTSIM_NO_PRESITE")) {
 			presites(kp, n_tasks, rot);
+			if (!dense_mismatch.empty()) {
+				err = "dense first pass != walker first pass: " + dense_mismatch;
+				return NTB_EINTERNAL;
+			}
 		}
 		for (;;) {
 			Counters ctr = {};

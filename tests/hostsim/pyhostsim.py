@@ -38,7 +38,7 @@ def default_params(**kw):
 def build():
     srcs = [os.path.join(HERE, "hostsim.cpp")]
     deps = srcs + [os.path.join(ROOT, "ntedit_b200", "csrc", f) for f in
-                   ("engine.h", "nthash.h", "ntb_common.h", "replay.hpp", "polish_driver.hpp", "writer.hpp")]
+                   ("engine.h", "site_dense.h", "nthash.h", "ntb_common.h", "replay.hpp", "polish_driver.hpp", "writer.hpp")]
     if os.path.exists(SO) and all(os.path.getmtime(SO) >= os.path.getmtime(d) for d in deps):
         return
     os.makedirs(os.path.dirname(SO), exist_ok=True)

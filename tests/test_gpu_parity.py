@@ -173,3 +173,26 @@ def test_rerun_rounds_survive_a_moving_event_arena(nb, oracle, monkeypatch):
     ofa, otsv, ovcf = oracle.polish(inp["contigs"], ofilt, op, bloomrep=orep)
     assert fa == ofa and tsv == otsv and vcf == ovcf
     ofilt.free()
+
+
+@pytest.mark.parametrize("env", [{"NTB_NO_PRESITE": "1"}, {"NTB_PRESITE_DENSE": "0"}, {"NTB_SITE_TABLE_SLOTS": "64"}],
+                         ids=["no_presite", "warp_first_pass", "tiny_table"])
+def test_pre_evaluation_is_optional_on_the_device(nb, oracle, monkeypatch, env):
+    """The site records only run ahead of the walk: without them, with the warp-per-site form of the first pass, and with a
+    table that drops most records, the walkers evaluate the missing sites themselves -- same bytes out."""
+    for k_, v in env.items():
+        monkeypatch.setenv(k_, v)
+    for name in ("m1", "m2_i2_d3", "cbf_p2_q200", "secondary_filter", "k64_h4"):
+        case = [c for c in tc.CASES if c["name"] == name][0]
+        inp = tc.make_inputs(7000 + tc.CASES.index(case), **case.get("g", {}))
+        ofilt, orep = tc.oracle_filters(oracle, inp)
+        bloom, rep = device_filters(nb, inp)
+        fa, tsv, vcf, st = nb.polish(inp["contigs"], bloom, nb.default_params(segment_len=300, **case["p"]), bloomrep=rep)
+        op = oracle.default_params(inp["k"], inp["h"], **tc.oracle_param_overrides(case["p"]))
+        if orep:
+            op.secbf = 1
+        ofa, otsv, ovcf = oracle.polish(inp["contigs"], ofilt, op, bloomrep=orep)
+        assert fa == ofa and tsv == otsv and vcf == ovcf
+        ofilt.free()
+        if orep:
+            orep.free()

@@ -10,6 +10,13 @@ from tests import golden_util as gu
 from tests.hostsim import pyhostsim as hs
 
 
+@pytest.fixture(autouse=True)
+def _cross_check_the_dense_first_pass(monkeypatch):
+    """Every polishing call of this file also runs the walker form of the first pre-evaluation pass and fails when a record
+    differs from the dense (thread-per-site) form's, site_dense.h vs engine.h: evaluate_site_core."""
+    monkeypatch.setenv("HOSTSIM_CHECK_DENSE", "1")
+
+
 def run_hostsim(contigs, filt, params_kw, rep=None, segment_len=0):
     params = hs.default_params(segment_len=segment_len, **params_kw)
     repa = (rep.data().tobytes(), rep.h, rep.counting) if rep else None
@@ -126,3 +133,24 @@ def test_fragmented_draft_of_tiny_contigs(oracle, monkeypatch, piece_events):
     assert fa == ofa and tsv == otsv and vcf == ovcf
     assert st.edits > 500
     filt.free()
+
+
+@pytest.mark.parametrize("env", [{"HOSTSIM_NO_PRESITE": "1"}, {"HOSTSIM_DENSE": "0"}, {"HOSTSIM_TABLE_SLOTS": "64"}])
+def test_pre_evaluation_is_optional(oracle, monkeypatch, env):
+    """Records only run ahead of the walk: without the pre-evaluation pass, with its walker form, and with a table so small
+    that most records are dropped, the walkers evaluate what is missing themselves and the output does not change."""
+    for k_, v in env.items():
+        monkeypatch.setenv(k_, v)
+    for name in ("m1", "m2_i2_d3", "cbf_p2_q200", "secondary_filter", "high_fpr_m0"):
+        case = [c for c in tc.CASES if c["name"] == name][0]
+        inp = tc.make_inputs(7000 + tc.CASES.index(case), **case.get("g", {}))
+        filt, rep = tc.oracle_filters(oracle, inp)
+        fa, tsv, vcf, st = run_hostsim(inp["contigs"], filt, case["p"], rep=rep, segment_len=300)
+        op = oracle.default_params(inp["k"], inp["h"], **tc.oracle_param_overrides(case["p"]))
+        if rep:
+            op.secbf = 1
+        ofa, otsv, ovcf = oracle.polish(inp["contigs"], filt, op, bloomrep=rep, min_contig_len=case["p"].get("min_contig_len", 100))
+        assert fa == ofa and tsv == otsv and vcf == ovcf
+        filt.free()
+        if rep:
+            rep.free()
