@@ -252,8 +252,10 @@ struct Workspace
 	Task* h_tasks = nullptr;
 	TaskResult* h_results = nullptr;
 	size_t cap_h_tasks = 0;
-	Event* h_events = nullptr;
-	size_t cap_h_events = 0;
+	// pinned event arenas, one per walker round of a call: a round's events never move, so the host may replay one round
+	// while the device fills the next (polish_driver.hpp: contig groups)
+	std::vector<Event*> h_event_blocks;
+	std::vector<size_t> cap_event_blocks;
 	Counters* h_ctr = nullptr;
 
 	~Workspace()
@@ -284,7 +286,9 @@ struct Workspace
 		}
 		cudaFreeHost(h_tasks);
 		cudaFreeHost(h_results);
-		cudaFreeHost(h_events);
+		for (Event* b : h_event_blocks) {
+			cudaFreeHost(b);
+		}
 		cudaFreeHost(h_ctr);
 		if (ev0) {
 			cudaEventDestroy(ev0);
@@ -353,8 +357,7 @@ struct CudaBackend
 	ntb_filter* rep;
 	ntb_batch* batch;
 	Workspace* ws = nullptr;
-	size_t ev_used = 0; // events of earlier rounds kept in ws->h_events
-	std::vector<size_t> round_off; // first event of every round inside ws->h_events (offsets: the arena may move when it grows)
+	size_t n_rounds = 0; // walker rounds of this call so far; round r's events live in ws->h_event_blocks[r]
 	float ms_scan = 0, ms_walk = 0, ms_d2h = 0, ms_pre = 0;
 	bool pre_timed = false;       // ev_pre0 / ev_pre1 bracket this call's pre-evaluation passes
 	size_t table_slots = 0;       // slots of ws->d_table that hold this call's records (0: no pre-evaluation)
@@ -364,7 +367,29 @@ struct CudaBackend
 
 	const std::string& error() const { return err; }
 
-	const Event* round_events(size_t r) const { return ws->h_events + round_off[r]; }
+	const Event* round_events(size_t r) const { return ws->h_event_blocks[r]; }
+
+	// the pinned arena of the round about to run, with room for n events
+	int round_block(size_t n, Event** out)
+	{
+		if (n_rounds >= ws->h_event_blocks.size()) {
+			ws->h_event_blocks.push_back(nullptr);
+			ws->cap_event_blocks.push_back(0);
+		}
+		if (n > ws->cap_event_blocks[n_rounds]) {
+			cudaFreeHost(ws->h_event_blocks[n_rounds]);
+			ws->h_event_blocks[n_rounds] = nullptr;
+			ws->cap_event_blocks[n_rounds] = 0;
+			const size_t want = n + n / 4 + 4096;
+			cudaError_t e = cudaHostAlloc((void**)&ws->h_event_blocks[n_rounds], want * sizeof(Event), cudaHostAllocDefault);
+			if (e != cudaSuccess) {
+				return cuda_err(e, "cudaHostAlloc(events)");
+			}
+			ws->cap_event_blocks[n_rounds] = want;
+		}
+		*out = ws->h_event_blocks[n_rounds];
+		return NTB_OK;
+	}
 
 	int cuda_err(cudaError_t e, const char* what)
 	{
@@ -698,7 +723,10 @@ struct CudaBackend
 		a.pending = ws->d_pending;
 		a.pending_cap = (uint32_t)ws->cap_pending;
 		NTB_BE(cudaEventRecord(ws->ev_pre0, stream));
-		NTB_BE(cudaMemsetAsync(ws->d_table, 0, slots * sizeof(SiteRec), stream));
+		if (!table_slots) {
+			// (the contig groups of a call share the table)
+			NTB_BE(cudaMemsetAsync(ws->d_table, 0, slots * sizeof(SiteRec), stream));
+		}
 		NTB_BE(cudaMemsetAsync(ws->d_ctr, 0, sizeof(Counters), stream));
 		NTB_BE(launch_heads(a, stream));
 		NTB_BE(launch_presite(a, false, stream));
@@ -706,22 +734,26 @@ struct CudaBackend
 		NTB_BE(launch_presite(a, true, stream));
 		NTB_BE(cudaMemcpyAsync(ws->h_ctr_pre, ws->d_ctr, sizeof(Counters), cudaMemcpyDeviceToHost, stream));
 		NTB_BE(cudaEventRecord(ws->ev_pre1, stream));
-		launches += 3;
+		launches += presite_launch_count();
 		pre_timed = true;
 		table_slots = slots;
 		return NTB_OK;
 	}
 
-	int walk(const KParams& kp, size_t n, const TaskResult** res_out, const Event** ev_out, size_t* n_ev_out)
+	int walk(const KParams& kp, size_t n, bool first_round_of_group, const TaskResult** res_out, const Event** ev_out, size_t* n_ev_out)
 	{
 		if (rc != NTB_OK) {
 			return rc;
 		}
 		*res_out = ws->h_results;
-		*ev_out = ws->h_events + ev_used;
+		*ev_out = nullptr;
 		*n_ev_out = 0;
 		if (n == 0) {
-			round_off.push_back(ev_used);
+			Event* none = nullptr;
+			if (round_block(0, &none) != NTB_OK) {
+				return rc;
+			}
+			n_rounds++;
 			return NTB_OK;
 		}
 		if (n > 0xFFFFFFF0ULL) {
@@ -770,8 +802,8 @@ struct CudaBackend
 		wa.n_tasks = (uint32_t)n;
 		wa.ctr = ws->d_ctr;
 		wa.sm_count = sm_count(batch->device);
-		if (round_off.empty()) {
-			// first round: its tasks cover every contig
+		if (first_round_of_group) {
+			// a group's first round: its tasks cover every contig of the group
 			if (presites(wa, stream) != NTB_OK) {
 				return rc;
 			}
@@ -820,27 +852,16 @@ struct CudaBackend
 				ws->cap_events = want;
 				continue;
 			}
-			// the events of this round go behind those of the earlier rounds in the pinned arena
-			if (ev_used + ctr.n_events > ws->cap_h_events) {
-				// NTB_TEST_TIGHT_EVENT_ARENA (testing aid): no slack, so every later round with events moves the arena
-				const size_t want = std::getenv("NTB_TEST_TIGHT_EVENT_ARENA")
-				                        ? ev_used + ctr.n_events
-				                        : std::max<size_t>((ev_used + ctr.n_events) * 5 / 4 + 4096, ws->cap_events / 2);
-				Event* grown = nullptr;
-				NTB_BE(cudaHostAlloc((void**)&grown, want * sizeof(Event), cudaHostAllocDefault));
-				if (ev_used) {
-					std::memcpy(grown, ws->h_events, ev_used * sizeof(Event));
-				}
-				cudaFreeHost(ws->h_events);
-				ws->h_events = grown;
-				ws->cap_h_events = want;
+			Event* h_round = nullptr;
+			if (round_block(ctr.n_events, &h_round) != NTB_OK) {
+				return rc;
 			}
 			NTB_BE(cudaEventRecord(ws->ev0, stream));
 			if (ctr.n_events) {
 				// group the events by walker on the device, then bring them over
 				NTB_BE(launch_compact_events(ws->d_events, ws->d_events_sorted, ws->d_results, (uint32_t)n, ws->d_ctr, stream));
 				launches++;
-				NTB_BE(cudaMemcpyAsync(ws->h_events + ev_used, ws->d_events_sorted, (size_t)ctr.n_events * sizeof(Event),
+				NTB_BE(cudaMemcpyAsync(h_round, ws->d_events_sorted, (size_t)ctr.n_events * sizeof(Event),
 				                       cudaMemcpyDeviceToHost, stream));
 			}
 			NTB_BE(cudaMemcpyAsync(ws->h_results, ws->d_results, n * sizeof(TaskResult), cudaMemcpyDeviceToHost, stream));
@@ -849,10 +870,9 @@ struct CudaBackend
 			NTB_BE(cudaEventElapsedTime(&ms, ws->ev0, ws->ev1));
 			ms_d2h += ms;
 			*res_out = ws->h_results;
-			*ev_out = ws->h_events + ev_used;
+			*ev_out = h_round;
 			*n_ev_out = ctr.n_events;
-			round_off.push_back(ev_used);
-			ev_used += ctr.n_events;
+			n_rounds++;
 			if (std::getenv("NTB_DEBUG_TASKS")) {
 				debug_tasks(n, ctr);
 			}

@@ -923,16 +923,34 @@ presite_kernel(const uint8_t* text, const uint32_t* visit, FilterView bloom, Fil
 	}
 }
 
-// presite_dense_kernel: the first pass with one THREAD per item (site_dense.h) -- 32 sites per warp in flight, every probe
-// of a stage issued before any is consumed.  Persistent grid, items dealt round-robin.
+// presite_dense_kernel: the first pass with one THREAD per site (site_dense.h) -- 32 sites per warp in flight, every probe
+// of a stage issued before any is consumed.  It runs in rounds.  Round 0 takes the heads, one per thread.  A site that made
+// no edit hands its chain to the next round (a thread that followed its chain itself would hold its whole warp for the
+// ~3 % of heads that fail): there DENSE_GROUP consecutive lanes take one chain and evaluate its next DENSE_GROUP sites
+// side by side -- sites are functions of the text alone -- then keep the records up to the first one at which the main
+// loop would stop going on (an edit, or tryIndels pending), exactly the records the strictly sequential chain files; only
+// when all of them let it go on does the chain move to the round after.  SITE_CHAIN_MAX / DENSE_GROUP rounds.
 constexpr int DENSE_THREADS = 128;
+constexpr int DENSE_GROUP = 8;
+constexpr uint32_t DENSE_ROUNDS = 1 + SITE_CHAIN_MAX / DENSE_GROUP;
 
-template<int KCAP>
+__global__ void
+presite_round_kernel(Counters* ctr, uint32_t items_cap)
+{
+	ctr->item_lo = ctr->item_hi;
+	ctr->item_hi = min(ctr->n_items, items_cap);
+}
+
+template<int KCAP, bool CHAIN>
 __global__ void __launch_bounds__(DENSE_THREADS)
 presite_dense_kernel(const uint8_t* text, const uint32_t* visit, FilterView bloom, FilterView rep, const __grid_constant__ KParams kp,
-                     const Task* tasks, const uint2* items, uint32_t items_cap, SiteRec* table, uint32_t table_mask, PendingSite* pending,
+                     const Task* tasks, uint2* items, uint32_t items_cap, SiteRec* table, uint32_t table_mask, PendingSite* pending,
                      uint32_t pending_cap, Counters* ctr)
 {
+	const uint32_t lo = ctr->item_lo, hi = ctr->item_hi;
+	if (lo >= hi) {
+		return;
+	}
 	__shared__ uint64_t rot[ROT_WORDS];
 	__shared__ uint8_t cls[256];
 	for (uint32_t q = threadIdx.x; q < ROT_WORDS; q += blockDim.x) {
@@ -948,11 +966,63 @@ presite_dense_kernel(const uint8_t* text, const uint32_t* visit, FilterView bloo
 	C.rep = rep;
 	C.rot = rot;
 	C.cls = cls;
-	const uint32_t n = min(ctr->n_items, items_cap);
-	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-		const uint2 it = items[i];
-		const Task task = tasks[it.x];
-		dense_run<KCAP>(C, text + task.text_off, task.len, task.text_off, visit, it.x, it.y, table, table_mask, pending, pending_cap, ctr);
+	const uint32_t gap = kp.k - 1;
+	const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x, gthreads = gridDim.x * blockDim.x;
+	if (!CHAIN) {
+		for (uint32_t i = lo + gtid; i < hi; i += gthreads) {
+			const uint2 it = items[i];
+			const Task task = tasks[it.x];
+			SiteRec r;
+			const uint32_t st = dense_site<KCAP>(C, text + task.text_off, task.len, it.y, r);
+			if (dense_commit(r, st, task.text_off, it.x, it.y, table, table_mask, pending, pending_cap, ctr) && dense_continues(st, r) &&
+			    dense_chain_next(visit, task.text_off, task.len, it.y, gap) != NONE32) {
+				const uint32_t j = atomicAdd(&ctr->n_items, 1u);
+				if (j < items_cap) {
+					items[j] = it; // the chain behind this site
+				}
+			}
+		}
+		return;
+	}
+	// chain rounds: item = (task, position the chain goes on BEHIND); the whole warp iterates together
+	const uint32_t lane = threadIdx.x & 31u, sub = lane % DENSE_GROUP, gbase = lane - sub;
+	const uint32_t n_groups = gthreads / DENSE_GROUP;
+	const uint32_t n_iter = (hi - lo + n_groups - 1) / n_groups;
+	for (uint32_t iter = 0; iter < n_iter; iter++) {
+		const uint32_t i = lo + iter * n_groups + gtid / DENSE_GROUP;
+		bool active = i < hi;
+		uint2 it = make_uint2(0, 0);
+		Task task;
+		uint32_t pos = NONE32;
+		if (active) {
+			it = items[i];
+			task = tasks[it.x];
+			// this lane's site: the (sub + 1)-th of the chain behind it.y
+			pos = it.y;
+			for (uint32_t q = 0; q <= sub && pos != NONE32; q++) {
+				pos = dense_chain_next(visit, task.text_off, task.len, pos, gap);
+			}
+			active = pos != NONE32;
+		}
+		SiteRec r;
+		uint32_t st = SITE_NONE;
+		if (active) {
+			st = dense_site<KCAP>(C, text + task.text_off, task.len, pos, r);
+		}
+		// the first lane of the group at which the chain stops: its end, an edit, or a pending site
+		const bool stops = !active || !dense_continues(st, r);
+		const uint32_t stop_mask = (__ballot_sync(0xFFFFFFFFu, stops) >> gbase) & ((1u << DENSE_GROUP) - 1u);
+		const uint32_t first_stop = stop_mask ? (uint32_t)__ffs((int)stop_mask) - 1u : (uint32_t)DENSE_GROUP;
+		bool ok = true;
+		if (active && sub <= first_stop) {
+			ok = dense_commit(r, st, task.text_off, it.x, pos, table, table_mask, pending, pending_cap, ctr);
+		}
+		if (first_stop == (uint32_t)DENSE_GROUP && sub == DENSE_GROUP - 1 && ok) {
+			const uint32_t j = atomicAdd(&ctr->n_items, 1u);
+			if (j < items_cap) {
+				items[j] = make_uint2(it.x, pos);
+			}
+		}
 	}
 }
 
@@ -1215,15 +1285,26 @@ template<int KCAP>
 static cudaError_t
 launch_presite_dense_k(const WalkArgs& a, cudaStream_t stream)
 {
-	static OccCache cache;
-	int per_sm = 0;
-	cudaError_t e = walker_occupancy(presite_dense_kernel<KCAP>, cache, 0, DENSE_THREADS, &per_sm);
+	static OccCache cache[2];
+	int per_sm = 0, per_sm_chain = 0;
+	cudaError_t e = walker_occupancy(presite_dense_kernel<KCAP, false>, cache[0], 0, DENSE_THREADS, &per_sm);
+	if (e == cudaSuccess) {
+		e = walker_occupancy(presite_dense_kernel<KCAP, true>, cache[1], 0, DENSE_THREADS, &per_sm_chain);
+	}
 	if (e != cudaSuccess) {
 		return e;
 	}
-	presite_dense_kernel<KCAP><<<(unsigned)(a.sm_count * per_sm), DENSE_THREADS, 0, stream>>>(a.text, a.visit, a.bloom, a.rep, a.kp, a.tasks, a.items,
-	                                                                                      a.items_cap, a.table, a.table_mask, a.pending,
-	                                                                                      a.pending_cap, a.ctr);
+	for (uint32_t round = 0; round < DENSE_ROUNDS; round++) {
+		presite_round_kernel<<<1, 1, 0, stream>>>(a.ctr, a.items_cap);
+		// (later rounds hold a few percent of the heads, then nothing: an empty round returns at once)
+		if (round == 0) {
+			presite_dense_kernel<KCAP, false><<<(unsigned)(a.sm_count * per_sm), DENSE_THREADS, 0, stream>>>(
+			    a.text, a.visit, a.bloom, a.rep, a.kp, a.tasks, a.items, a.items_cap, a.table, a.table_mask, a.pending, a.pending_cap, a.ctr);
+		} else {
+			presite_dense_kernel<KCAP, true><<<(unsigned)(a.sm_count * per_sm_chain), DENSE_THREADS, 0, stream>>>(
+			    a.text, a.visit, a.bloom, a.rep, a.kp, a.tasks, a.items, a.items_cap, a.table, a.table_mask, a.pending, a.pending_cap, a.ctr);
+		}
+	}
 	return cudaGetLastError();
 }
 
@@ -1239,6 +1320,12 @@ launch_presite(const WalkArgs& a, bool second, cudaStream_t stream)
 		return launch_presite_first(a, stream);
 	}
 	return a.kp.k <= 48 ? launch_presite_dense_k<48>(a, stream) : launch_presite_dense_k<(int)KMAX>(a, stream);
+}
+
+uint32_t
+presite_launch_count()
+{
+	return 2 + 2 * DENSE_ROUNDS; // heads, the rounds of the first pass (bookkeeping + sites), second pass
 }
 #undef NTB_WALK_DISPATCH
 

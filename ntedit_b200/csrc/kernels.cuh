@@ -147,6 +147,7 @@ cudaError_t launch_walk(const WalkArgs& a, cudaStream_t stream);
 // must be zero before launch_heads.
 cudaError_t launch_heads(const WalkArgs& a, cudaStream_t stream);
 cudaError_t launch_presite(const WalkArgs& a, bool second, cudaStream_t stream);
+uint32_t presite_launch_count(); // kernels launch_heads + both passes launch
 
 // lays every walker's events out contiguously in `out`, in emission order; results[i].last_event becomes the index of the first
 cudaError_t launch_compact_events(const Event* in, Event* out, TaskResult* results, uint32_t n_tasks, Counters* ctr, cudaStream_t stream);

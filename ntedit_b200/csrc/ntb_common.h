@@ -165,8 +165,9 @@ struct Counters
 	uint32_t n_front;    // order_tasks_kernel: dense tasks placed so far (from the front of the queue)
 	uint32_t n_back;     // ... the others (from the back)
 	uint32_t n_compact;  // compact_events_kernel: events placed so far
-	uint32_t n_items;    // pre-evaluation: run heads listed so far
-	uint32_t next_item;  // ... work queue of the first pass
+	uint32_t n_items;    // pre-evaluation: items listed so far (heads, then the chain items each round of the first pass adds)
+	uint32_t item_lo, item_hi; // ... the items of the current round of the first pass
+	uint32_t next_item;  // ... work queue of the first pass (warp form)
 	uint32_t n_pending;  // ... sites waiting for the second pass (tryIndels)
 	uint32_t next_pending;
 	uint32_t n_dropped;  // ... records that found no slot / list entry (the walkers evaluate those sites themselves)

@@ -156,9 +156,27 @@ dense_site(const DenseCtx& C, const uint8_t* text, uint32_t len, uint32_t pos, S
 	const uint32_t n_sub = n_rolls < k ? n_rolls : k;
 	uint8_t cw[2 * KCAP]; // cw[i] = class of text[pos + 1 - k + i], i < k + n_sub
 	const uint32_t head = pos + 1 - k;
+#if defined(__CUDA_ARCH__)
+	{
+		// aligned 32-bit loads (SCAN_HALO bytes in front of the batch buffer and its zero padding behind make the rounded-out
+		// words readable)
+		const uintptr_t a0 = reinterpret_cast<uintptr_t>(text + head);
+		const uint32_t sh = (uint32_t)(a0 & 3u);
+		const uint32_t* wp = reinterpret_cast<const uint32_t*>(a0 - sh);
+		uint32_t word = 0;
+		for (uint32_t i = 0; i < k + n_sub; i++) {
+			const uint32_t q = sh + i;
+			if (i == 0 || (q & 3u) == 0) {
+				word = __ldg(wp + (q >> 2));
+			}
+			cw[i] = cls[(word >> (8u * (q & 3u))) & 0xFFu];
+		}
+	}
+#else
 	for (uint32_t i = 0; i < k + n_sub; i++) {
 		cw[i] = cls[text[head + i]];
 	}
+#endif
 	uint32_t n_check = k; // iterations of the check loop that complete (ntedit.cpp:1826-1858)
 	for (uint32_t m = 0; m < k; m++) {
 		if (m >= n_rolls || !((cw[k + m] >> 6) & 1u)) {
@@ -293,9 +311,14 @@ dense_site(const DenseCtx& C, const uint8_t* text, uint32_t len, uint32_t pos, S
 	}
 	uint32_t sup[4] = { 0, 0, 0, 0 };
 	uint32_t loud = 0; // bit c: one of the k-1 windows that contain candidate c's base is a site
-	for (uint32_t c = 0; c < ncand; c++) {
-		if (!(P.mode == 2 || ((gate >> c) & 1u))) {
-			continue;
+	// the candidates that are tried, packed: the a-th pass of the loop below serves every thread's a-th tried candidate (which
+	// of the three bases passes its gate differs from site to site; looping over c would run the trial once per c with a
+	// third of the warp)
+	const uint32_t tried = P.mode == 2 ? ((1u << ncand) - 1u) : gate;
+	for (uint32_t rest = tried; rest; rest &= rest - 1) {
+		uint32_t c = 0;
+		while (!((rest >> c) & 1u)) {
+			c++;
 		}
 		const uint32_t xcl = cls[(cands >> (8 * c)) & 0xFF];
 		const uint32_t xf = xcl & 7u, xr = (xcl >> 3) & 7u;
@@ -468,52 +491,69 @@ dense_next_visit(const uint32_t* visit, uint64_t goff, uint32_t from, uint32_t l
 	return NONE32;
 }
 
-// One item of the first pass, one thread: the head at `pos` and the chain behind it (engine.h: Walker::pre_run with
-// allow_indels == false).
-template<int KCAP>
-NTB_FN inline void
-dense_run(const DenseCtx& C, const uint8_t* text, uint32_t len, uint64_t goff, const uint32_t* visit, uint32_t task_idx, uint32_t pos,
-          SiteRec* table, uint32_t table_mask, PendingSite* pending, uint32_t pending_cap, Counters* ctr)
+// files the record of an evaluated site (key = text position + 1) and, for SITE_PENDING, lists it for the second pass;
+// false when the table has no room (the record is dropped)
+NTB_FN inline bool
+dense_commit(SiteRec& r, uint32_t st, uint64_t goff, uint32_t task_idx, uint32_t pos, SiteRec* table, uint32_t table_mask, PendingSite* pending,
+             uint32_t pending_cap, Counters* ctr)
 {
-	const uint32_t gap = C.kp->k - 1;
-	for (uint32_t n = 0; n < SITE_CHAIN_MAX; n++) {
-		SiteRec r;
-		const uint32_t st = dense_site<KCAP>(C, text, len, pos, r);
-		r.key = goff + pos + 1;
-		const uint32_t slot = site_table_insert(table, table_mask, r.key);
-		if (slot == NONE32) {
+	r.key = goff + pos + 1;
+	const uint32_t slot = site_table_insert(table, table_mask, r.key);
+	if (slot == NONE32) {
 #if defined(__CUDA_ARCH__)
-			atomicAdd(&ctr->n_dropped, 1u);
+		atomicAdd(&ctr->n_dropped, 1u);
 #else
-			ctr->n_dropped++;
+		ctr->n_dropped++;
 #endif
-			return;
-		}
-		if (st == SITE_PENDING) {
-			uint32_t idx;
+		return false;
+	}
+	if (st == SITE_PENDING) {
+		uint32_t idx;
 #if defined(__CUDA_ARCH__)
-			idx = atomicAdd(&ctr->n_pending, 1u);
+		idx = atomicAdd(&ctr->n_pending, 1u);
 #else
-			idx = ctr->n_pending++;
+		idx = ctr->n_pending++;
 #endif
-			if (idx < pending_cap) {
-				PendingSite ps;
-				ps.task = task_idx;
-				ps.pos = pos;
-				ps.slot = slot;
-				pending[idx] = ps;
-			}
-		}
-		table[slot] = r;
-		if (!(st == SITE_NONE || (st == SITE_DONE && r.best_type == 0))) {
-			return;
-		}
-		const uint32_t lim = len - pos - 1 < gap ? len : pos + 1 + gap;
-		pos = dense_next_visit(visit, goff, pos + 1, lim);
-		if (pos == NONE32) {
-			return;
+		if (idx < pending_cap) {
+			PendingSite ps;
+			ps.task = task_idx;
+			ps.pos = pos;
+			ps.slot = slot;
+			pending[idx] = ps;
 		}
 	}
+	table[slot] = r;
+	return true;
+}
+
+// does the main loop go on to the next flagged position behind this site with a clean window (no edit was made)?
+NTB_FN inline bool
+dense_continues(uint32_t st, const SiteRec& r)
+{
+	return st == SITE_NONE || (st == SITE_DONE && r.best_type == 0);
+}
+
+// the chain's next site behind `pos`: the next flagged position within pre_gap() = k-1 (a farther one is a head), or NONE32
+NTB_FN inline uint32_t
+dense_chain_next(const uint32_t* visit, uint64_t goff, uint32_t len, uint32_t pos, uint32_t gap)
+{
+	const uint32_t lim = len - pos - 1 < gap ? len : pos + 1 + gap;
+	return dense_next_visit(visit, goff, pos + 1, lim);
+}
+
+// One site of the first pass, one thread: evaluates the site at `pos`, files its record, and returns the position the chain
+// goes on with or NONE32 when the chain ends here (engine.h: one iteration of Walker::pre_run with allow_indels == false).
+template<int KCAP>
+NTB_FN inline uint32_t
+dense_step(const DenseCtx& C, const uint8_t* text, uint32_t len, uint64_t goff, const uint32_t* visit, uint32_t task_idx, uint32_t pos,
+           SiteRec* table, uint32_t table_mask, PendingSite* pending, uint32_t pending_cap, Counters* ctr)
+{
+	SiteRec r;
+	const uint32_t st = dense_site<KCAP>(C, text, len, pos, r);
+	if (!dense_commit(r, st, goff, task_idx, pos, table, table_mask, pending, pending_cap, ctr) || !dense_continues(st, r)) {
+		return NONE32;
+	}
+	return dense_chain_next(visit, goff, len, pos, C.kp->k - 1);
 }
 
 } // namespace ntb

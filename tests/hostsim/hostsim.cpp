@@ -85,7 +85,7 @@ struct HostBackend
 		return tasks.data();
 	}
 
-	std::vector<SiteRec> table;
+	std::vector<SiteRec> table, table2;
 	std::string dense_mismatch;
 	uint64_t pre_records = 0, pre_pending = 0, pre_dropped = 0;
 
@@ -99,19 +99,28 @@ struct HostBackend
 		while (slots < want) {
 			slots <<= 1;
 		}
-		table.assign(slots, SiteRec());
-		std::memset(table.data(), 0, slots * sizeof(SiteRec));
+		if (table.size() != slots) {
+			// (the contig groups of a call share the table)
+			table.assign(slots, SiteRec());
+			std::memset(table.data(), 0, slots * sizeof(SiteRec));
+		}
 		std::vector<PendingSite> pending(ts ? 8 : (size_t)(total / 32 + 64));
 		Counters ctr = {}, ctr2 = {};
 		WalkerState<352>* st = new WalkerState<352>();
 		W w(*st, kp);
 		const char* dv = std::getenv("HOSTSIM_DENSE");
 		const bool dense = !(dv && dv[0] == '0');
-		const bool check = dense && std::getenv("HOSTSIM_CHECK_DENSE") != nullptr;
-		std::vector<SiteRec> table2(check ? slots : 0);
+		const bool check = dense && !ts && std::getenv("HOSTSIM_CHECK_DENSE") != nullptr; // (a tiny table drops different records)
 		std::vector<PendingSite> pending2(check ? pending.size() : 0);
-		if (check) {
+		if (check && table2.size() != slots) {
+			table2.assign(slots, SiteRec());
 			std::memset(table2.data(), 0, slots * sizeof(SiteRec));
+		}
+		// text range of this group's tasks: the records its first pass files have their keys in there
+		uint64_t key_lo = ~0ULL, key_hi = 0;
+		for (size_t u = 0; u < n_tasks; u++) {
+			key_lo = std::min<uint64_t>(key_lo, tasks[u].text_off + tasks[u].start + 1);
+			key_hi = std::max<uint64_t>(key_hi, tasks[u].text_off + tasks[u].len + 1);
 		}
 		uint8_t cls_tab[256];
 		for (unsigned c = 0; c < 256; c++) {
@@ -129,13 +138,35 @@ struct HostBackend
 				if (ctr.n_pending != ctr2.n_pending || ctr.n_dropped != ctr2.n_dropped) {
 					dense_mismatch = "pending / dropped counts differ";
 				}
-				for (size_t q = 0; q < slots && dense_mismatch.empty(); q++) {
-					if (std::memcmp(&table[q], &table2[q], sizeof(SiteRec)) != 0) {
-						char buf[160];
-						std::snprintf(buf, sizeof buf, "record of text position %llu differs (dense state %u type %u, walker state %u type %u)",
-						              (unsigned long long)(table[q].key ? table[q].key : table2[q].key) - 1, table[q].state, table[q].best_type,
-						              table2[q].state, table2[q].best_type);
-						dense_mismatch = buf;
+				auto find = [&](const std::vector<SiteRec>& tab, uint64_t key) -> const SiteRec* {
+					uint32_t slot = site_hash(key) & ((uint32_t)slots - 1);
+					for (uint32_t i = 0; i < SITE_TABLE_PROBES; i++, slot = (slot + 1) & ((uint32_t)slots - 1)) {
+						if (tab[slot].key == key) {
+							return &tab[slot];
+						}
+						if (tab[slot].key == 0) {
+							break;
+						}
+					}
+					return nullptr;
+				};
+				// (slot positions may differ: the second passes of earlier groups only filled `table`)
+				for (int dir = 0; dir < 2 && dense_mismatch.empty(); dir++) {
+					const std::vector<SiteRec>& from = dir ? table2 : table;
+					const std::vector<SiteRec>& to = dir ? table : table2;
+					for (size_t q = 0; q < slots && dense_mismatch.empty(); q++) {
+						const uint64_t key = from[q].key;
+						if (key == 0 || key < key_lo || key > key_hi) {
+							continue; // empty, or an earlier group's record (its second pass has completed it since)
+						}
+						const SiteRec* other = find(to, key);
+						if (!other || std::memcmp(&from[q], other, sizeof(SiteRec)) != 0) {
+							char buf[200];
+							std::snprintf(buf, sizeof buf, "record of text position %llu differs (%s state %u type %u, other form %s)",
+							              (unsigned long long)key - 1, dir ? "walker" : "dense", from[q].state, from[q].best_type,
+							              other ? "has another record" : "has none");
+							dense_mismatch = buf;
+						}
 					}
 				}
 			}
@@ -171,8 +202,12 @@ struct HostBackend
 					if (f && W::is_head(visit.data(), t.text_off, (uint32_t)p, w.pre_gap())) {
 						pre_records++;
 						if (dense) {
-							dense_run<(int)KMAX>(dctx, io.text, io.len, io.goff, visit.data(), (uint32_t)ti, (uint32_t)p, table.data(),
-							                     (uint32_t)slots - 1, pending.data(), (uint32_t)pending.size(), &ctr);
+							// (the device runs the chain as rounds of items: a site's successor is an item of the next round)
+							uint32_t q = (uint32_t)p;
+							for (uint32_t n = 0; n < SITE_CHAIN_MAX && q != NONE32; n++) {
+								q = dense_step<(int)KMAX>(dctx, io.text, io.len, io.goff, visit.data(), (uint32_t)ti, q, table.data(),
+								                          (uint32_t)slots - 1, pending.data(), (uint32_t)pending.size(), &ctr);
+							}
 						}
 						if (!dense || check) {
 							if (check) {
@@ -202,7 +237,7 @@ struct HostBackend
 		}
 	}
 
-	int walk(const KParams& kp, size_t n_tasks, const TaskResult** res_out, const Event** ev_out, size_t* n_ev_out)
+	int walk(const KParams& kp, size_t n_tasks, bool first_round_of_group, const TaskResult** res_out, const Event** ev_out, size_t* n_ev_out)
 	{
 		results.resize(n_tasks);
 		rounds.emplace_back(new std::vector<Event>(1u << 16));
@@ -213,7 +248,7 @@ struct HostBackend
 		}
 		// the pre-evaluation pass of the first round, as the CUDA backend runs it (capi.cu: CudaBackend::presites): heads of
 		// flagged runs per task, first pass (no tryIndels), second pass (the pending ones); HOSTSIM_NO_PRESITE=1 turns it off
-		if (rounds.size() == 1 && !kp.snv && !std::getenv("HOSTSIM_NO_PRESITE")) {
+		if (first_round_of_group && !kp.snv && !std::getenv("HOSTSIM_NO_PRESITE")) {
 			presites(kp, n_tasks, rot);
 			if (!dense_mismatch.empty()) {
 				err = "dense first pass != walker first pass: " + dense_mismatch;

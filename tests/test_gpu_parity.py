@@ -196,3 +196,19 @@ def test_pre_evaluation_is_optional_on_the_device(nb, oracle, monkeypatch, env):
         ofilt.free()
         if orep:
             orep.free()
+
+
+def test_contig_groups_pipeline_on_the_device(nb, oracle, monkeypatch):
+    """Contig groups (device phase of one beside the host replay of the one before, one site table for all) on the GPU."""
+    case = [c for c in tc.CASES if c["name"] == "m1"][0]
+    inp = tc.make_inputs(31337, ncontigs=7, n=9000)
+    ofilt, orep = tc.oracle_filters(oracle, inp)
+    bloom, rep = device_filters(nb, inp)
+    op = oracle.default_params(inp["k"], inp["h"], **tc.oracle_param_overrides(case["p"]))
+    ofa, otsv, ovcf = oracle.polish(inp["contigs"], ofilt, op)
+    monkeypatch.setenv("NTB_CONTIG_GROUP_MIN", "1000")
+    for groups in ("1", "2", "7"):
+        monkeypatch.setenv("NTB_CONTIG_GROUPS", groups)
+        fa, tsv, vcf, st = nb.polish(inp["contigs"], bloom, nb.default_params(segment_len=400, **case["p"]))
+        assert fa == ofa and tsv == otsv and vcf == ovcf
+    ofilt.free()

@@ -154,3 +154,19 @@ def test_pre_evaluation_is_optional(oracle, monkeypatch, env):
         filt.free()
         if rep:
             rep.free()
+
+
+def test_contig_groups_pipeline(oracle, monkeypatch):
+    """The contigs of a call are polished as groups -- device phase of one beside the replay of the one before -- that share
+    the site table; any cut into groups gives the same bytes (NTB_CONTIG_GROUP_MIN lets tiny inputs form groups)."""
+    case = [c for c in tc.CASES if c["name"] == "m1"][0]
+    inp = tc.make_inputs(31337, ncontigs=7, n=9000)
+    filt, rep = tc.oracle_filters(oracle, inp)
+    op = oracle.default_params(inp["k"], inp["h"], **tc.oracle_param_overrides(case["p"]))
+    ofa, otsv, ovcf = oracle.polish(inp["contigs"], filt, op)
+    monkeypatch.setenv("NTB_CONTIG_GROUP_MIN", "1000")
+    for groups in ("1", "2", "3", "7", "50"):
+        monkeypatch.setenv("NTB_CONTIG_GROUPS", groups)
+        fa, tsv, vcf, st = run_hostsim(inp["contigs"], filt, case["p"], segment_len=400)
+        assert fa == ofa and tsv == otsv and vcf == ovcf
+    filt.free()
