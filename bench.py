@@ -369,6 +369,80 @@ def split_rows(data, skip_header):
     return out
 
 
+def file_digests(prefix):
+    import hashlib
+    fa = {}
+    with open(prefix + "_edited.fa", "rb") as fh:
+        while True:
+            hdr = fh.readline()
+            if not hdr:
+                break
+            fa[hdr] = hashlib.blake2b(fh.readline(), digest_size=16).digest()
+    rows = {}
+    for sfx, skip in (("_changes.tsv", 1), ("_variants.vcf", 0)):
+        with open(prefix + sfx, "rb") as fh:
+            for i, ln in enumerate(fh):
+                if i < skip or ln.startswith(b"#"):
+                    continue
+                key = (sfx, ln.split(b"\t", 1)[0])
+                h = rows.get(key)
+                if h is None:
+                    h = rows[key] = hashlib.blake2b(digest_size=16)
+                h.update(ln)
+    return fa, {k: v.digest() for k, v in rows.items()}
+
+
+def e2e_files_leg(nb, bloom, host_np, offs, w, cores, bases):
+    """File -> file, whole processes: the draft as a plain FASTA (80 columns) and the filter file on local disk; ours and the
+    reference's wall clocks, outputs compared per contig."""
+    from oracle import pyoracle as po
+    tmp = tempfile.mkdtemp(prefix="ntb_files_")
+    out = {"draft": "plain FASTA, 80 columns", "bases": bases}
+    try:
+        fpath = os.path.join(tmp, "reads.bf")
+        bloom.save(fpath)
+        dpath = os.path.join(tmp, "draft.fa")
+        nl = np.frombuffer(b"\n", dtype=np.uint8)
+        with open(dpath, "wb") as fh:
+            for c in range(len(offs) - 1):
+                s, e = int(offs[c]), int(offs[c + 1]) - 1
+                fh.write(b">contig%d len=%d\n" % (c, e - s))
+                seq = host_np[s:e]
+                full = (e - s) // 80 * 80
+                if full:
+                    block = np.empty((full // 80, 81), dtype=np.uint8)
+                    block[:, :80] = seq[:full].reshape(-1, 80)
+                    block[:, 80] = nl[0]
+                    fh.write(block.tobytes())
+                if e - s > full:
+                    fh.write(seq[full:].tobytes() + b"\n")
+        out["draft_bytes"] = os.path.getsize(dpath)
+        flags = reference_flags(w)
+
+        def run(cmd):
+            t0 = time.perf_counter()
+            subprocess.run(cmd, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+            return time.perf_counter() - t0
+        ours = os.path.join(tmp, "ours")
+        run([nb.lib.CLI, "-f", dpath, "-r", fpath, "-b", ours, "-t", str(cores)] + flags)   # page cache and pinned pool warm-up
+        t_ours = min(run([nb.lib.CLI, "-f", dpath, "-r", fpath, "-b", ours, "-t", str(cores)] + flags) for _ in range(2))
+        out["ours_wall_s"] = t_ours
+        out["ours_bases_per_s"] = bases / t_ours
+        if po.have_ref():
+            ref = os.path.join(tmp, "ref")
+            t_ref = run([po.REF_BIN, "-f", dpath, "-r", fpath, "-b", ref, "-t", str(cores)] + flags)
+            out["reference_wall_s"] = t_ref
+            out["reference_bases_per_s"] = bases / t_ref
+            out["reference_threads"] = cores
+            out["identical_outputs"] = file_digests(ours) == file_digests(ref)
+        return out
+    except Exception as ex:
+        out["failed"] = repr(ex)
+        return out
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -378,6 +452,9 @@ def main():
     ap.add_argument("--workload", default=os.environ.get("NTB_BENCH_WORKLOAD", "3Gbp_k25_4GiB_m1"), choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--sample-mbp", type=float, default=0.0, help="CPU reference sample size (0 = from core count)")
+    ap.add_argument("--e2e-files", action="store_true",
+                    help="also time file -> file: `ntedit-b200 -f draft.fa -r filter.bf` as a whole process (filter load, FASTA parse, "
+                         "polishing, the three output files) and the reference binary on the same files (SURVEY.md 8d ii); minutes")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -564,6 +641,10 @@ def main():
         except Exception as ex:  # the baseline must never take the bench line down
             cpu = {"value": None, "unit": "bases/s", "cores": cores, "kind": "reference", "sample": "failed: %r" % (ex,)}
 
+    files = None
+    if rank == 0 and args.e2e_files:
+        files = e2e_files_leg(nb, bloom, host_np, offs, w, cores, bases)
+
     if rank == 0:
         peaks = {}
         try:
@@ -627,6 +708,7 @@ def main():
                                                 "ceiling, profiles/r01_gather_*); K1b serves probes from L2-resident filter regions"},
             "cpu_baseline": cpu,
             "verified": verified,
+            "e2e_files": files,
             "breakdown_ms": {"scan_kernel": ms_scan, "presite_kernels": ms_pre, "walk_kernel": ms_walk,
                              "host_stitch_replay": ms_host, "d2h_events": ms_d2h, "rounds": stats[-1]["rounds"],
                              "segments": stats[-1]["segments"], "reruns": stats[-1]["reruns"], "sites": stats[-1]["sites"],

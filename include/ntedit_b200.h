@@ -51,6 +51,12 @@ typedef struct ntb_filter_info {
 	double fpr;        /* btllib get_fpr(): (occupancy)^hash_num, the value print_details shows, ntedit.cpp:387-395 */
 } ntb_filter_info;
 
+/* Page-locked host memory for batch buffers.  ntb_polish_batch streams its upload straight out of such a buffer while the
+ * scan of the earlier pieces already runs; from pageable memory the driver stages every piece through its own pinned
+ * buffer first.  NULL when no device / no memory. */
+void* ntb_host_alloc(size_t bytes);
+void ntb_host_free(void* p);
+
 /* Replaces `BFWrapper bloom(path)` (ntedit.cpp:355-364, 2438): parses the btllib header
  * ([BTLKmerBloomFilter_v*] / [BTLKmerCountingBloomFilter_v*], TOML keys in any order, [HeaderEnd]),
  * uploads `bytes` raw bytes to `device` and computes the occupancy on the device. */

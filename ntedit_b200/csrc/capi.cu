@@ -1034,6 +1034,25 @@ ntb_device_count(void)
 	return n;
 }
 
+void*
+ntb_host_alloc(size_t bytes)
+{
+	void* p = nullptr;
+	if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable) != cudaSuccess) {
+		cudaGetLastError();
+		return nullptr;
+	}
+	return p;
+}
+
+void
+ntb_host_free(void* p)
+{
+	if (p) {
+		cudaFreeHost(p);
+	}
+}
+
 void
 ntb_params_init(ntb_params* p)
 {

@@ -16,6 +16,9 @@
 #include <algorithm>
 #include <atomic>
 #include <chrono>
+#include <condition_variable>
+#include <deque>
+#include <mutex>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -192,11 +195,157 @@ load_clinvar(const std::string& path, ntb::ClinvarMap& m)
 	gzclose(fp);
 }
 
+// Growable byte buffer in page-locked host memory (ntb_host_alloc): the batch text the reader appends to and the polishing
+// call uploads from.  Buffers are recycled through a small pool: pinning a gigabyte costs hundreds of milliseconds.
+class PinnedBuf
+{
+  public:
+	PinnedBuf() = default;
+	PinnedBuf(const PinnedBuf&) = delete;
+	PinnedBuf& operator=(const PinnedBuf&) = delete;
+	~PinnedBuf() { release(); }
+
+	size_t size() const { return size_; }
+	bool empty() const { return size_ == 0; }
+	char& operator[](size_t i) { return data_[i]; }
+	char* data() { return data_; }
+	char& back() { return data_[size_ - 1]; }
+	void pop_back() { size_--; }
+	void clear() { size_ = 0; }
+	void push_back(char c)
+	{
+		if (size_ == cap_) {
+			grow(size_ + 1);
+		}
+		data_[size_++] = c;
+	}
+	void append(const char* p, size_t n)
+	{
+		if (size_ + n > cap_) {
+			grow(size_ + n);
+		}
+		std::memcpy(data_ + size_, p, n);
+		size_ += n;
+	}
+	void reserve(size_t n)
+	{
+		if (n > cap_) {
+			grow(n);
+		}
+	}
+
+  private:
+	void grow(size_t need)
+	{
+		size_t cap = cap_ ? cap_ : (size_t)1 << 20;
+		while (cap < need) {
+			cap += cap / 2;
+		}
+		char* p = take(cap);
+		if (size_) {
+			std::memcpy(p, data_, size_);
+		}
+		release();
+		data_ = p;
+		cap_ = cap;
+	}
+	struct Pool
+	{
+		std::mutex lock;
+		std::vector<std::pair<char*, size_t>> free_list;
+	};
+	static Pool& pool()
+	{
+		static Pool p;
+		return p;
+	}
+	// a pooled buffer of at least `cap` bytes (cap_ is set by the caller to what was asked for: pooled ones may be larger)
+	static char* take(size_t& cap)
+	{
+		{
+			std::lock_guard<std::mutex> g(pool().lock);
+			for (size_t i = 0; i < pool().free_list.size(); i++) {
+				if (pool().free_list[i].second >= cap) {
+					char* p = pool().free_list[i].first;
+					cap = pool().free_list[i].second;
+					pool().free_list.erase(pool().free_list.begin() + (long)i);
+					return p;
+				}
+			}
+		}
+		char* p = (char*)ntb_host_alloc(cap);
+		if (!p) {
+			std::cerr << PROGRAM ": error: out of page-locked host memory (" << cap << " bytes)\n";
+			std::exit(EXIT_FAILURE);
+		}
+		return p;
+	}
+	void release()
+	{
+		if (data_) {
+			std::lock_guard<std::mutex> g(pool().lock);
+			if (pool().free_list.size() < 6) {
+				pool().free_list.emplace_back(data_, cap_);
+			} else {
+				ntb_host_free(data_);
+			}
+		}
+		data_ = nullptr;
+		size_ = cap_ = 0;
+	}
+	char* data_ = nullptr;
+	size_t size_ = 0, cap_ = 0;
+};
+
 struct Batch
 {
 	std::vector<std::string> names;
-	std::string bases; // contigs end to end, each followed by its NUL
+	PinnedBuf bases; // contigs end to end, each followed by its NUL
 	std::vector<uint64_t> offsets{ 0 };
+};
+
+// bounded hand-over between the pipeline's threads (reader -> dispatcher -> writer)
+template<class T>
+class Channel
+{
+  public:
+	explicit Channel(size_t cap) : cap_(cap) {}
+	void push(T v)
+	{
+		std::unique_lock<std::mutex> lk(m_);
+		space_.wait(lk, [this]() { return q_.size() < cap_; });
+		q_.push_back(std::move(v));
+		lk.unlock();
+		data_.notify_one();
+	}
+	void close()
+	{
+		{
+			std::lock_guard<std::mutex> g(m_);
+			closed_ = true;
+		}
+		data_.notify_all();
+	}
+	bool pop(T& v) // false: closed and drained
+	{
+		std::unique_lock<std::mutex> lk(m_);
+		data_.wait(lk, [this]() { return !q_.empty() || closed_; });
+		if (q_.empty()) {
+			return false;
+		}
+		v = std::move(q_.front());
+		q_.pop_front();
+		lk.unlock();
+		space_.notify_one();
+		return true;
+	}
+
+  private:
+	size_t cap_;
+	std::mutex m_;
+	std::condition_variable data_, space_;
+	std::deque<T> q_;
+	bool closed_ = false;
 };
 
 struct BatchOut
@@ -206,8 +355,30 @@ struct BatchOut
 };
 
 // polish one batch on `device` and format it (contigs formatted in parallel, concatenated in input order)
+// counts the batches whose polishing call is running: one per device at a time
+struct DeviceSlots
+{
+	std::mutex m;
+	std::condition_variable cv;
+	size_t busy = 0;
+	void acquire(size_t limit)
+	{
+		std::unique_lock<std::mutex> lk(m);
+		cv.wait(lk, [&]() { return busy < limit; });
+		busy++;
+	}
+	void release()
+	{
+		{
+			std::lock_guard<std::mutex> g(m);
+			busy--;
+		}
+		cv.notify_one();
+	}
+};
+
 BatchOut
-process_batch(std::unique_ptr<Batch> b, ntb_filter* bloom, ntb_filter* rep, const Opt& opt, const ntb::ClinvarMap* cv)
+process_batch(std::unique_ptr<Batch> b, ntb_filter* bloom, ntb_filter* rep, const Opt& opt, const ntb::ClinvarMap* cv, DeviceSlots* slots)
 {
 	BatchOut out;
 	ntb_result* res = nullptr;
@@ -216,6 +387,7 @@ process_batch(std::unique_ptr<Batch> b, ntb_filter* bloom, ntb_filter* rep, cons
 		          << b->names.back() << "'; the output files are incomplete\n";
 		die_ntb("ntb_polish_batch");
 	}
+	slots->release(); // the device is free for the next batch while this one is formatted
 	const size_t n = b->names.size();
 	std::vector<std::string> fa(n), tsv(n), vcf(n);
 	std::atomic<size_t> next(0);
@@ -482,51 +654,65 @@ main(int argc, char** argv)
 	vfout << ntb::vcf_header("ntEdit v2.1.1", opt.draft); // the reference's PROGRAM string (ntedit.cpp:1), kept for byte-compatible headers
 
 	const ntb::ClinvarMap* cv = &clinvar;
-	std::vector<std::future<BatchOut>> inflight; // in input order
+	// Three stages run beside each other: a reader thread parses the draft into batches (its bytes are read / inflated ahead
+	// of it by the ByteSource's own threads), this thread hands every batch to a device, and a writer thread writes the
+	// finished batches in input order.  At most one batch per device is being polished, one more is being read.
 	uint64_t tot_contigs = 0, tot_bases = 0, tot_edits = 0, n_read = 0;
-	size_t next_dev = 0;
-	auto drain_one = [&]() {
-		BatchOut o = inflight.front().get();
-		inflight.erase(inflight.begin());
-		dfout.write(o.fa.data(), (std::streamsize)o.fa.size());
-		rfout.write(o.tsv.data(), (std::streamsize)o.tsv.size());
-		vfout.write(o.vcf.data(), (std::streamsize)o.vcf.size());
-		tot_contigs += o.contigs;
-		tot_bases += o.bases;
-		tot_edits += o.edits;
-	};
 	const auto t_begin = std::chrono::steady_clock::now();
-	bool more = true;
-	std::string name, comment;
-	while (more) {
-		std::unique_ptr<Batch> b(new Batch());
-		b->bases.reserve((size_t)std::min<uint64_t>(opt.batch_bases + (64u << 20), 1ull << 32));
-		while (b->bases.size() < opt.batch_bases) {
-			more = reader.next(name, comment, b->bases);
-			if (!more) {
+	Channel<std::unique_ptr<Batch>> batches((size_t)1);
+	Channel<std::future<BatchOut>> finished((size_t)opt.gpus + 1);
+	DeviceSlots slots;
+	std::thread reader_thread([&]() {
+		bool more = true;
+		std::string name, comment;
+		while (more) {
+			std::unique_ptr<Batch> b(new Batch());
+			b->bases.reserve((size_t)std::min<uint64_t>(opt.batch_bases + (64u << 20), 1ull << 32));
+			while (b->bases.size() < opt.batch_bases) {
+				more = reader.next(name, comment, b->bases);
+				if (!more) {
+					break;
+				}
+				b->bases.push_back('\0');
+				b->offsets.push_back(b->bases.size());
+				b->names.push_back(comment.empty() ? name : name + " " + comment); // ntedit.cpp:2224-2229
+				n_read++;
+			}
+			if (b->names.empty()) {
 				break;
 			}
-			b->bases.push_back('\0');
-			b->offsets.push_back(b->bases.size());
-			b->names.push_back(comment.empty() ? name : name + " " + comment); // ntedit.cpp:2224-2229
-			n_read++;
+			batches.push(std::move(b));
 		}
-		if (b->names.empty()) {
-			break;
+		batches.close();
+	});
+	std::thread writer_thread([&]() {
+		std::future<BatchOut> f;
+		while (finished.pop(f)) {
+			BatchOut o = f.get();
+			dfout.write(o.fa.data(), (std::streamsize)o.fa.size());
+			rfout.write(o.tsv.data(), (std::streamsize)o.tsv.size());
+			vfout.write(o.vcf.data(), (std::streamsize)o.vcf.size());
+			tot_contigs += o.contigs;
+			tot_bases += o.bases;
+			tot_edits += o.edits;
 		}
-		const size_t d = next_dev;
-		next_dev = (next_dev + 1) % (size_t)opt.gpus;
-		while (inflight.size() >= (size_t)opt.gpus) { // at most one batch per device in flight (+ the one being read)
-			drain_one();
+	});
+	{
+		size_t next_dev = 0;
+		std::unique_ptr<Batch> b;
+		while (batches.pop(b)) {
+			const size_t d = next_dev;
+			next_dev = (next_dev + 1) % (size_t)opt.gpus;
+			Batch* raw = b.release();
+			slots.acquire((size_t)opt.gpus); // batches go round-robin and take about equally long: device d is the one that is free
+			finished.push(std::async(std::launch::async, [raw, &bloom, &rep, &opt, cv, d, &slots]() {
+				return process_batch(std::unique_ptr<Batch>(raw), bloom[d], rep[d], opt, cv, &slots);
+			}));
 		}
-		Batch* raw = b.release();
-		inflight.push_back(std::async(std::launch::async, [raw, &bloom, &rep, &opt, cv, d]() {
-			return process_batch(std::unique_ptr<Batch>(raw), bloom[d], rep[d], opt, cv);
-		}));
+		finished.close();
 	}
-	while (!inflight.empty()) {
-		drain_one();
-	}
+	reader_thread.join();
+	writer_thread.join();
 	dfout.close();
 	rfout.close();
 	vfout.close();

@@ -1,6 +1,7 @@
-// kseq-compatible FASTA/FASTQ reader over zlib, shared by the ntedit-b200 command line tools.
+// kseq-compatible FASTA/FASTQ reader, shared by the ntedit-b200 command line tools.  The bytes come from a ByteSource
+// (bytesource.hpp): read and inflated ahead of the parser by its own thread(s).
 #pragma once
-#include <zlib.h>
+#include "bytesource.hpp"
 
 #include <cstring>
 #include <string>
@@ -14,23 +15,14 @@ namespace ntb {
 class FastxReader
 {
   public:
-	explicit FastxReader(const std::string& path) : buf_(1 << 20)
-	{
-		fp_ = gzopen(path.c_str(), "r");
-		if (fp_) {
-			gzbuffer(fp_, 1 << 20);
-		}
-	}
-	~FastxReader()
-	{
-		if (fp_) {
-			gzclose(fp_);
-		}
-	}
-	bool ok() const { return fp_ != nullptr; }
+	explicit FastxReader(const std::string& path, unsigned inflate_threads = 4) : src_(path, inflate_threads) {}
+	bool ok() const { return src_.ok(); }
+	const char* kind() const { return src_.kind(); }
 
-	// reads the next record; sequence is appended to `seq`.  Returns false at end of file.
-	bool next(std::string& name, std::string& comment, std::string& seq)
+	// reads the next record; sequence is appended to `seq` (anything with size / push_back / append(ptr, n) / back / pop_back).
+	// Returns false at end of file.
+	template<class Seq>
+	bool next(std::string& name, std::string& comment, Seq& seq)
 	{
 		int c;
 		if (last_char_ == 0) { // jump to the next header line
@@ -105,19 +97,20 @@ class FastxReader
 			if (eof_) {
 				return -1;
 			}
-			const int n = gzread(fp_, buf_.data(), (unsigned)buf_.size());
-			if (n <= 0) {
+			if (!src_.next(buf_) || buf_.empty()) {
 				eof_ = true;
+				len_ = pos_ = 0;
 				return -1;
 			}
-			len_ = (size_t)n;
+			len_ = buf_.size();
 			pos_ = 0;
 		}
 		return (unsigned char)buf_[pos_++];
 	}
 
 	// appends the rest of the current line (without its terminator) to s
-	void append_line_(std::string& s)
+	template<class Seq>
+	void append_line_(Seq& s)
 	{
 		for (;;) {
 			if (pos_ >= len_) {
@@ -142,7 +135,7 @@ class FastxReader
 		}
 	}
 
-	gzFile fp_ = nullptr;
+	ByteSource src_;
 	std::vector<char> buf_;
 	size_t pos_ = 0, len_ = 0;
 	bool eof_ = false;

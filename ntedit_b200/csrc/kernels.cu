@@ -809,6 +809,23 @@ walk_smem_init(uint8_t* walk_smem, const KParams& kp)
 // ------------------------------------------------------------------------------------------------------------------
 // Pre-evaluation (ntb_common.h: SiteRec; engine.h: pre_run).
 // heads_kernel: one warp per task lists the heads of its nominal range [start, end) -- the ranges partition every contig.
+// A head is a flagged position with no flagged position among the `gap` (< 128) positions in front of it: every lane takes
+// one bitmap word, gets the three words in front of it from its neighbours and smears that 128-bit window instead of
+// testing bit by bit.
+struct Bits128
+{
+	uint64_t lo, hi;
+};
+
+__device__ __forceinline__ Bits128
+shl128(Bits128 x, uint32_t n) // n < 64
+{
+	Bits128 r;
+	r.hi = n ? (x.hi << n) | (x.lo >> (64 - n)) : x.hi;
+	r.lo = x.lo << n;
+	return r;
+}
+
 __global__ void __launch_bounds__(256)
 heads_kernel(const uint32_t* visit, const Task* tasks, uint32_t n_tasks, uint32_t gap, uint2* items, uint32_t cap, Counters* ctr)
 {
@@ -817,23 +834,50 @@ heads_kernel(const uint32_t* visit, const Task* tasks, uint32_t n_tasks, uint32_
 	for (uint32_t ti = warp; ti < n_tasks; ti += n_warps) {
 		const Task t = tasks[ti];
 		const uint64_t g0 = t.text_off + t.start, g1 = t.text_off + t.end;
+		const uint64_t gc = t.text_off; // flagged positions in front of the contig's first base do not count
 		for (uint64_t w0 = g0 >> 5; (w0 << 5) < g1; w0 += 32) {
 			const uint64_t w = w0 + lane;
-			uint32_t bits = (w << 5) < g1 ? visit[w] : 0u;
-			if (w == (g0 >> 5)) {
-				bits &= 0xFFFFFFFFu << (g0 & 31);
-			}
-			if (((w + 1) << 5) > g1 && (w << 5) < g1) {
-				bits &= 0xFFFFFFFFu >> (32 - (g1 & 31));
-			}
-			// keep the flagged positions that are heads
-			uint32_t heads = 0;
-			for (uint32_t rest = bits; rest; rest &= rest - 1) {
-				const uint32_t b = (uint32_t)__ffs((int)rest) - 1u;
-				const uint32_t pos = (uint32_t)((w << 5) + b - t.text_off);
-				if (Walker<160>::is_head(visit, t.text_off, pos, gap)) {
-					heads |= 1u << b;
+			// this lane's word and the three in front of it (bits in front of the contig masked away)
+			auto word = [&](uint64_t wi) -> uint32_t {
+				if ((int64_t)wi < (int64_t)(gc >> 5) || (wi << 5) >= g1 + 32) {
+					return 0u;
 				}
+				uint32_t b = visit[wi];
+				if (wi == (gc >> 5)) {
+					b &= 0xFFFFFFFFu << (gc & 31);
+				}
+				return b;
+			};
+			const uint32_t cur = (w << 5) < g1 ? word(w) : 0u;
+			uint32_t p1 = __shfl_up_sync(0xFFFFFFFFu, cur, 1), p2 = __shfl_up_sync(0xFFFFFFFFu, cur, 2), p3 = __shfl_up_sync(0xFFFFFFFFu, cur, 3);
+			if (lane < 1) {
+				p1 = word(w - 1);
+			}
+			if (lane < 2) {
+				p2 = word(w - 2);
+			}
+			if (lane < 3) {
+				p3 = word(w - 3);
+			}
+			Bits128 x;
+			x.lo = ((uint64_t)p2 << 32) | p3;
+			x.hi = ((uint64_t)cur << 32) | p1;
+			// near = positions with a flagged position 1 .. gap in front of them: x smeared upwards by gap, less x itself
+			Bits128 s = shl128(x, 1);
+			for (uint32_t covered = 1; covered < gap;) { // s covers distances 1 .. covered; gap <= KMAX - 1 keeps every step below 64
+				const uint32_t step = covered < gap - covered ? covered : gap - covered;
+				const Bits128 sh = shl128(s, step);
+				s.lo |= sh.lo;
+				s.hi |= sh.hi;
+				covered += step;
+			}
+			uint32_t heads = cur & ~(uint32_t)(s.hi >> 32);
+			// only positions of [g0, g1) are this task's
+			if (w == (g0 >> 5)) {
+				heads &= 0xFFFFFFFFu << (g0 & 31);
+			}
+			if (((w + 1) << 5) > g1) {
+				heads &= (w << 5) < g1 ? (0xFFFFFFFFu >> (32 - (g1 & 31))) : 0u;
 			}
 			// warp-aggregated append
 			const uint32_t n = (uint32_t)__popc(heads);

@@ -98,6 +98,8 @@ SYMBOLS = {
     "ntb_last_error": (C.c_char_p, []),
     "ntb_version": (C.c_char_p, []),
     "ntb_device_count": (C.c_int, []),
+    "ntb_host_alloc": (_VP, [C.c_size_t]),
+    "ntb_host_free": (None, [_VP]),
     "ntb_filter_load": (C.c_int, [C.c_char_p, C.c_int, C.POINTER(_VP)]),
     "ntb_filter_create": (C.c_int, [C.c_uint64, C.c_uint32, C.c_uint32, C.c_int, C.c_int, C.POINTER(_VP)]),
     "ntb_filter_wrap_device": (C.c_int, [_VP, C.c_uint64, C.c_uint32, C.c_uint32, C.c_int, C.c_int, C.POINTER(_VP)]),
