@@ -181,15 +181,18 @@ def test_make_bf_cli_builds_the_filter_the_oracle_builds(nb, oracle, tmp_path):
     want.free()
 
 
-def test_cli_shards_batches_over_two_gpus(nb, oracle, tmp_path):
-    """--gpus 2: batches of contigs go round-robin to two devices, each with its own replica of the filter; the output
-    is still in input order and bit-exact.  Skipped on a one-GPU box."""
+@pytest.mark.parametrize("gen", [dict(), dict(k=64, h=4, fbytes=1 << 17)], ids=["k25", "k64_large_rope_kernels"])
+def test_cli_shards_batches_over_two_gpus(nb, oracle, tmp_path, gen):
+    """--gpus 2: batches of contigs go round-robin to two devices (host threads of one process), each with its own replica
+    of the filter -- one file read, one device-to-device copy; the output is still in input order and bit-exact.  The k = 64
+    case runs the large-rope kernel instantiations (more dynamic shared memory than the default limit: the attribute
+    must be set on BOTH devices).  Skipped on a one-GPU box."""
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs two GPUs")
     if not oracle.have_ref():
         pytest.skip("oracle/_ref/ntedit_ref not present")
-    inp = tc.make_inputs(606, ncontigs=7, n=12000)
+    inp = tc.make_inputs(606, ncontigs=7, n=12000, **gen)
     dpath, fpath, _ = write_inputs(nb, tmp_path, inp)
     got = run_cli(dpath, fpath, str(tmp_path / "ours"), extra=("-m", 1, "--gpus", 2, "--batch_bases", 20000))
     rfa, rtsv, rvcf = oracle.run_ref(dpath, fpath, workdir=str(tmp_path), extra=("-m", 1))

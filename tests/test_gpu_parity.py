@@ -212,3 +212,39 @@ def test_contig_groups_pipeline_on_the_device(nb, oracle, monkeypatch):
         fa, tsv, vcf, st = nb.polish(inp["contigs"], bloom, nb.default_params(segment_len=400, **case["p"]))
         assert fa == ofa and tsv == otsv and vcf == ovcf
     ofilt.free()
+
+
+def test_concurrent_calls_from_two_host_threads(nb, oracle):
+    """The boundary's threading contract (the reference calls kmerizeAndCorrect from every OpenMP thread,
+    ntedit.cpp:2242-2245): two host threads polish different batches against the same filter handles at the same time, on
+    one device; each checks its own workspace out, and both get the bytes the oracle gives."""
+    import threading
+    cases = [[c for c in tc.CASES if c["name"] == n][0] for n in ("m1", "k64_h4")]
+    jobs = []
+    for case in cases:
+        for seed in (1, 2):
+            inp = tc.make_inputs(500 + seed + 10 * tc.CASES.index(case), ncontigs=3, **case.get("g", {}))
+            ofilt, _ = tc.oracle_filters(oracle, inp)
+            bloom, _ = device_filters(nb, inp)
+            op = oracle.default_params(inp["k"], inp["h"], **tc.oracle_param_overrides(case["p"]))
+            want = oracle.polish(inp["contigs"], ofilt, op)
+            ofilt.free()
+            jobs.append((inp, bloom, nb.default_params(segment_len=500, **case["p"]), want))
+    results = [None] * len(jobs)
+    errors = []
+
+    def worker(i):
+        try:
+            inp, bloom, params, _ = jobs[i]
+            for _ in range(6):  # keep the calls overlapping
+                results[i] = nb.polish(inp["contigs"], bloom, params)[:3]
+        except Exception as ex:  # noqa: BLE001
+            errors.append(repr(ex))
+    threads = [threading.Thread(target=worker, args=(i,)) for i in range(len(jobs))]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
+    for (inp, bloom, params, want), got in zip(jobs, results):
+        assert got[0] == want[0] and got[1] == want[1] and got[2] == want[2]
