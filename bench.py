@@ -206,9 +206,100 @@ def insert_truth(nb, bloom, truth, dev):
     b.free()
 
 
+def insert_any(nb, bloom, truth, dev):
+    if nb is None:
+        bloom.insert(truth)
+    else:
+        insert_truth(nb, bloom, truth, dev)
+
+
+class TorchFilterBuilder:
+    """The filter of the benchmark built with torch tensor operations only -- ntHash (both strands from
+    rotation tables, canonical = f + r, extend_hashes) and btllib's bit / counter addressing (App. B) -- so that the reference
+    arm (`--impl reference`) fabricates its inputs without loading the product library; tests/test_gpu_parity.py checks
+    that it builds, byte for byte, the filter the product's insert kernel builds."""
+    SEEDS = (0x3c8bfbb395c60474, 0x3193c18562a02b4c, 0x20323ed082572324, 0x295549f54be24456)  # A C G T
+    MULTISEED, MULTISHIFT = 0x90b45d39fb6da1fa, 27
+
+    @staticmethod
+    def srol(x, d):
+        lo, hi = x & 0x1FFFFFFFF, x >> 33
+        dl, dh = d % 33, d % 31
+        lo = ((lo << dl) | (lo >> (33 - dl))) & 0x1FFFFFFFF if dl else lo
+        hi = ((hi << dh) | (hi >> (31 - dh))) & 0x7FFFFFFF if dh else hi
+        return (hi << 33) | lo
+
+    @staticmethod
+    def i64(x):
+        return x - (1 << 64) if x >= (1 << 63) else x
+
+    def __init__(self, filt, nbytes, k, h, counting, dev):
+        self.filt, self.nbytes, self.k, self.h, self.counting, self.dev = filt, nbytes, k, h, counting, dev
+        mod = nbytes if counting else nbytes * 8
+        assert mod & (mod - 1) == 0, "the torch builder serves power-of-two filter sizes (mask instead of an unsigned %)"
+        self.mask = mod - 1
+        # rot_f[d][c] = srol^d(seed[c]) (forward strand), rot_r[d][c] = srol^d(seed[3 - c]) (reverse-complement strand)
+        self.rot_f = [torch.tensor([self.i64(self.srol(sd, d)) for sd in self.SEEDS], dtype=torch.int64, device=dev) for d in range(k)]
+        self.rot_r = [torch.tensor([self.i64(self.srol(self.SEEDS[3 - c], d)) for c in range(4)], dtype=torch.int64, device=dev)
+                      for d in range(k)]
+        self.code = torch.full((256,), 0, dtype=torch.int64, device=dev)
+        for c, ch in enumerate(b"ACGT"):
+            self.code[ch] = c
+            self.code[ch | 0x20] = c
+
+    def insert(self, truth, chunk=1 << 25):
+        """every k-mer of the ACGT-only sequence `truth` (uint8 ASCII tensor)"""
+        k = self.k
+        n = len(truth) - k + 1
+        for o in range(0, max(0, n), chunk):
+            m = min(chunk, n - o)
+            codes = self.code[truth[o:o + m + k - 1].long()]
+            f = torch.zeros(m, dtype=torch.int64, device=self.dev)
+            r = torch.zeros(m, dtype=torch.int64, device=self.dev)
+            for i in range(k):
+                c = codes[i:i + m]
+                f ^= self.rot_f[k - 1 - i][c]
+                r ^= self.rot_r[i][c]
+            base = f + r  # canonical(): wrapping add
+            del f, r, codes
+            for i in range(self.h):
+                hv = base
+                if i > 0:
+                    hv = base * self.i64(i ^ ((k * self.MULTISEED) & ((1 << 64) - 1)))
+                    hv = hv ^ ((hv >> self.MULTISHIFT) & ((1 << (64 - self.MULTISHIFT)) - 1))  # logical shift
+                slot = hv & self.mask
+                if self.counting:
+                    # saturating 8-bit counters: add this chunk's occurrences per counter, clamp at 255
+                    uniq, occ = torch.unique(slot, return_counts=True)
+                    cur = self.filt[uniq].to(torch.int64) + occ
+                    self.filt[uniq] = cur.clamp_(max=255).to(torch.uint8)
+                    del uniq, occ, cur
+                else:
+                    byte, bit = slot >> 3, slot & 7
+                    for b in range(8):
+                        sel = byte[bit == b]
+                        self.filt[sel] = self.filt[sel] | (1 << b)
+                del slot
+            del base
+
+
+def save_filter_file(path, filt, nbytes, k, h, counting):
+    """btllib's file format, as ntedit_b200/csrc/filter_io.hpp writes it."""
+    if counting:
+        hdr = "[BTLKmerCountingBloomFilter_v5]\nbytes = %d\ncounter_bits = 8\nhash_fn = \"ntHash_v2\"\nhash_num = %d\nk = %d\n[HeaderEnd]\n" % (nbytes, h, k)
+    else:
+        hdr = "[BTLKmerBloomFilter_v7]\nbytes = %d\nhash_fn = \"ntHash_v2\"\nhash_num = %d\nk = %d\n[HeaderEnd]\n" % (nbytes, h, k)
+    with open(path, "wb") as fh:
+        fh.write(hdr.encode())
+        step = 1 << 28
+        for o in range(0, nbytes, step):
+            fh.write(filt[o:min(nbytes, o + step)].cpu().numpy().tobytes())
+
+
 def build_workload(w, dev, rank, bloom, nb):
     """Returns (draft buffer uint8 tensor on device with NUL separators, offsets np.uint64).  When `bloom` is given,
-    every k-mer of the error-free genome is inserted into it (filter construction kernel)."""
+    every k-mer of the error-free genome is inserted into it: a product BloomFilter (filter construction kernel) or, with
+    nb None, a TorchFilterBuilder."""
     lens = contig_lengths(w)
     if w["shape"] == "conifer":
         # the genome is generated in 100 Mbp pieces, each cut into contigs of the drawn lengths
@@ -230,7 +321,7 @@ def build_workload(w, dev, rank, bloom, nb):
             if bloom is not None:
                 # contig borders of the truth: k-mers across them do not exist in the genome, but a few hundred thousand extra
                 # k-mers in a 16 GiB filter change nothing measurable
-                insert_truth(nb, bloom, truth, dev)
+                insert_any(nb, bloom, truth, dev)
             del truth
             # cut the draft (its length differs from n by the indels) proportionally
             m = len(draft)
@@ -256,7 +347,7 @@ def build_workload(w, dev, rank, bloom, nb):
         g.manual_seed(SEED + ci)          # genome: same on every rank
         truth, draft = gen_sequence(n, g, dev, rank, ci)
         if bloom is not None:
-            insert_truth(nb, bloom, truth, dev)
+            insert_any(nb, bloom, truth, dev)
         drafts.append(draft)
         del truth
     total = sum(len(d) + 1 for d in drafts)
@@ -443,6 +534,95 @@ def e2e_files_leg(nb, bloom, host_np, offs, w, cores, bases):
         shutil.rmtree(tmp, ignore_errors=True)
 
 
+def run_reference_sample(args, w, cores, host_np, offs, bases, fpath, tmp, steps, warmup, polish):
+    """Times oracle/_ref/ntedit_ref on a bounded sample of the draft (the filter file is at fpath); with `polish` (the
+    product's polishing call) the product's output for the same sample is compared with the files the reference wrote."""
+    from oracle import pyoracle as po
+    if not po.have_ref():
+        return None
+    per_core = 1.0e6 * (12 if not w.get("snv") else 1.5)
+    target = int(args.sample_mbp * 1e6) if args.sample_mbp > 0 else int(min(bases, cores * per_core))
+    dpath = os.path.join(tmp, "sample.fa")
+    sample_bases, sample = write_sample_fasta(dpath, host_np, offs, target)
+    tiny = os.path.join(tmp, "tiny.fa")
+    with open(tiny, "wb") as fh:
+        fh.write(b">tiny\n" + host_np[:200].tobytes() + b"\n")
+    times = []
+    for i in range(warmup + steps):
+        dt, t_load, t_all = time_reference(po.REF_BIN, dpath, tiny, fpath, cores, w, tmp)
+        if i >= warmup:
+            times.append(dt)
+    out = dict(value=sample_bases * len(times) / sum(times), sample_bases=sample_bases, times=times, t_load=t_load, verified=None)
+    if polish:
+        # the product on the very same pseudo-contigs, through the host-buffer call, against the files the reference just
+        # wrote (per contig: with -t > 1 the reference's output order is its completion order)
+        contigs = [(h, host_np[p:q].tobytes()) for h, p, q in sample]
+        fa, tsv, vcf, _ = polish(contigs)
+        rfa = open(os.path.join(tmp, "sample_edited.fa"), "rb").read()
+        rtsv = open(os.path.join(tmp, "sample_changes.tsv"), "rb").read()
+        rvcf = open(os.path.join(tmp, "sample_variants.vcf"), "rb").read()
+        ok_fa = split_fasta(fa) == split_fasta(rfa)
+        ok_tsv = split_rows(tsv, True) == split_rows(rtsv, True) and tsv.split(b"\n")[0] == rtsv.split(b"\n")[0]
+        ok_vcf = split_rows(vcf, False) == split_rows(rvcf, False)
+        out["verified"] = {"ok": bool(ok_fa and ok_tsv and ok_vcf), "edited_fa": bool(ok_fa), "changes_tsv": bool(ok_tsv),
+                           "variants_vcf": bool(ok_vcf), "contigs": len(contigs), "bases": sample_bases, "tsv_rows": tsv.count(b"\n") - 1,
+                           "against": "oracle/_ref/ntedit_ref -t %d on the same pseudo-contigs and filter file, byte-compared per contig" % cores}
+    return out
+
+
+def torch_fpr(filt, nbytes, h, counting):
+    """btllib get_fpr(): (occupancy)^hash_num"""
+    lut = torch.tensor([bin(i).count("1") for i in range(256)], dtype=torch.int64, device=filt.device)
+    total = 0
+    step = 1 << 28
+    for o in range(0, nbytes, step):
+        v = filt[o:min(nbytes, o + step)]
+        total += int((v != 0).sum()) if counting else int(lut[v.long()].sum())
+    return (total / (nbytes if counting else nbytes * 8.0)) ** h
+
+
+def reference_arm(args, w, cores):
+    """`--impl reference`: the unmodified reference binary on a bounded sample of the same draft and the same filter, inputs
+    fabricated with torch only (same generators and seeds as our arm: the same bytes)."""
+    from oracle import pyoracle as po
+    if not po.have_ref():
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/ntedit_ref not present on this box"}))
+        return 0
+    dev = torch.device("cuda", 0) if torch.cuda.is_available() else torch.device("cpu")
+    K, H, counting = w["k"], w["h"], bool(w.get("counting"))
+    filt = torch.zeros(w["fbytes"] + 64, dtype=torch.uint8, device=dev)
+    builder = TorchFilterBuilder(filt, w["fbytes"], K, H, counting, dev)
+    buf, offs = build_workload(w, dev, 0, builder, None)
+    notes = finish_filter(w, filt, dev)
+    n_contigs = len(offs) - 1
+    bases = int(offs[-1]) - n_contigs
+    host_np = buf.cpu().numpy()
+    del buf
+    tmp = tempfile.mkdtemp(prefix="ntb_ref_")
+    try:
+        fpath = os.path.join(tmp, "filter.bf")
+        save_filter_file(fpath, filt, w["fbytes"], K, H, counting)
+        fpr = torch_fpr(filt, w["fbytes"], H, counting)
+        del filt
+        r = run_reference_sample(args, w, cores, host_np, offs, bases, fpath, tmp, args.steps, max(0, min(args.warmup, 1)), None)
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+    config = {"workload": args.workload, "baseline_config": w["baseline_config"], "k": K, "hash_num": H, "filter_bytes": w["fbytes"],
+              "filter_kind": "counting (8-bit)" if counting else "bit", "filter_fpr": fpr, "mode": w["mode"], "snv": int(w.get("snv", 0)),
+              "bases_per_gpu": bases, "contigs_per_gpu": n_contigs,
+              "errors": "substitution 1e-3, indel 1e-4 (len 1-5), 0.2% lower case, N runs",
+              "inputs": "fabricated with torch only (bench.py: gen_sequence, TorchFilterBuilder); the product library is not loaded"}
+    config.update(notes)
+    sample = "%d bases of the same draft as <=1 Mbp pseudo-contigs, same filter file; time = wall - wall(200 bp draft)" % r["sample_bases"]
+    line = {"metric": "bases polished/sec", "value": r["value"], "unit": "bases/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1000.0 * sum(r["times"]) / len(r["times"]), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u64", "data": "synthetic", "impl": "reference", "config": config,
+            "cpu_baseline": {"value": r["value"], "unit": "bases/s", "cores": cores, "kind": "reference", "sample": sample},
+            "e2e": {"value": r["value"], "unit": "bases/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -465,8 +645,9 @@ def main():
     counting = bool(w.get("counting"))
     cores = os.cpu_count() or 1
 
-    if args.impl == "reference" and rank != 0:
-        return 0
+    if args.impl == "reference":
+        # the reference arm never loads the product library: draft and filter are fabricated with torch alone
+        return reference_arm(args, w, cores) if rank == 0 else 0
 
     import ntedit_b200 as nb
     nb.lib.load()  # fails loudly if the CUDA library is not built
@@ -503,46 +684,13 @@ def main():
     torch.cuda.synchronize()
     host_np = host.numpy()
 
-    # ------------------------------------------------------------------ reference arm / cpu baseline helper
     def reference_run(steps, warmup, verify):
-        from oracle import pyoracle as po
-        if not po.have_ref():
-            return None
         tmp = tempfile.mkdtemp(prefix="ntb_ref_")
         try:
             fpath = os.path.join(tmp, "filter.bf")
             bloom.save(fpath)
-            per_core = 1.0e6 * (12 if not w.get("snv") else 1.5)
-            target = int(args.sample_mbp * 1e6) if args.sample_mbp > 0 else int(min(bases, cores * per_core))
-            dpath = os.path.join(tmp, "sample.fa")
-            sample_bases, sample = write_sample_fasta(dpath, host_np, offs, target)
-            tiny = os.path.join(tmp, "tiny.fa")
-            with open(tiny, "wb") as fh:
-                fh.write(b">tiny\n" + host_np[:200].tobytes() + b"\n")
-            times = []
-            for i in range(warmup + steps):
-                dt, t_load, t_all = time_reference(po.REF_BIN, dpath, tiny, fpath, cores, w, tmp)
-                if i >= warmup:
-                    times.append(dt)
-            out = dict(value=sample_bases * len(times) / sum(times), sample_bases=sample_bases, times=times, t_load=t_load,
-                       verified=None)
-            if verify:
-                # the product on the very same pseudo-contigs, through the host-buffer call, against the files the
-                # reference just wrote (per contig: with -t > 1 the reference's output order is its completion order)
-                contigs = [(h, host_np[p:q].tobytes()) for h, p, q in sample]
-                fa, tsv, vcf, _ = nb.polish(contigs, bloom, params)
-                rfa = open(os.path.join(tmp, "sample_edited.fa"), "rb").read()
-                rtsv = open(os.path.join(tmp, "sample_changes.tsv"), "rb").read()
-                rvcf = open(os.path.join(tmp, "sample_variants.vcf"), "rb").read()
-                ok_fa = split_fasta(fa) == split_fasta(rfa)
-                ok_tsv = split_rows(tsv, True) == split_rows(rtsv, True) and tsv.split(b"\n")[0] == rtsv.split(b"\n")[0]
-                ok_vcf = split_rows(vcf, False) == split_rows(rvcf, False)
-                out["verified"] = {"ok": bool(ok_fa and ok_tsv and ok_vcf), "edited_fa": bool(ok_fa), "changes_tsv": bool(ok_tsv),
-                                   "variants_vcf": bool(ok_vcf), "contigs": len(contigs), "bases": sample_bases,
-                                   "tsv_rows": tsv.count(b"\n") - 1,
-                                   "against": "oracle/_ref/ntedit_ref -t %d on the same pseudo-contigs and filter file, "
-                                              "byte-compared per contig" % cores}
-            return out
+            polish = (lambda contigs: nb.polish(contigs, bloom, params)) if verify else None
+            return run_reference_sample(args, w, cores, host_np, offs, bases, fpath, tmp, steps, warmup, polish)
         finally:
             shutil.rmtree(tmp, ignore_errors=True)
 
@@ -554,21 +702,6 @@ def main():
               "l2_note": "inputs (draft + filter, GBs) are far larger than the 126 MB L2",
               "parallelism": "contigs sharded per GPU, filter replicated (1 NCCL broadcast at load)" if world > 1 else "1 GPU"}
     config.update(filter_notes)
-
-    if args.impl == "reference":
-        r = reference_run(args.steps, max(0, min(args.warmup, 1)), False)
-        if r is None:
-            print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/ntedit_ref not present on this box"}))
-            return 0
-        sample = "%d bases of the same draft as <=1 Mbp pseudo-contigs, same filter file; time = wall - wall(200 bp draft)" % r["sample_bases"]
-        line = {"metric": "bases polished/sec", "value": r["value"], "unit": "bases/s", "n_gpus": args.gpus,
-                "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * sum(r["times"]) / len(r["times"]),
-                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-                "impl": "reference", "config": config,
-                "cpu_baseline": {"value": r["value"], "unit": "bases/s", "cores": cores, "kind": "reference", "sample": sample},
-                "e2e": {"value": r["value"], "unit": "bases/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(line))
-        return 0
 
     # ------------------------------------------------------------------ our arm
     batch = nb.Batch.wrap_device(buf.data_ptr(), offs, device=dev.index)

@@ -248,3 +248,24 @@ def test_concurrent_calls_from_two_host_threads(nb, oracle):
     assert not errors, errors
     for (inp, bloom, params, want), got in zip(jobs, results):
         assert got[0] == want[0] and got[1] == want[1] and got[2] == want[2]
+
+
+@pytest.mark.parametrize("counting", [False, True])
+def test_torch_builder_matches_the_insert_kernel(nb, counting):
+    """bench.py's reference arm fabricates its filter with torch tensor operations only (TorchFilterBuilder: ntHash from
+    rotation tables + btllib addressing, written independently of the CUDA code); it must build the very bytes the product's
+    filter construction kernel (K5) builds."""
+    import sys
+    import torch
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    rng = np.random.default_rng(17)
+    truth = synth.random_genome(400_000, rng, dup_frac=0.05)
+    k, h, nbytes = (32, 3, 1 << 19) if counting else (25, 3, 1 << 18)
+    bloom = nb.BloomFilter.create(nbytes, k, h, counting=counting, device=0)
+    bloom.insert([(b"t", truth.tobytes())])
+    dev = torch.device("cuda", 0)
+    filt = torch.zeros(nbytes, dtype=torch.uint8, device=dev)
+    tb = bench.TorchFilterBuilder(filt, nbytes, k, h, counting, dev)
+    tb.insert(torch.from_numpy(truth.copy()).to(dev), chunk=100_003)
+    assert np.array_equal(bloom.download(), filt.cpu().numpy())
