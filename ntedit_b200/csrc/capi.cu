@@ -227,6 +227,8 @@ struct Workspace
 	cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 	uint32_t* d_visit = nullptr;
 	size_t cap_visit = 0; // words
+	uint32_t* d_visit2 = nullptr; // -s 1: the positions whose site does something (K3)
+	size_t cap_visit2 = 0;
 	Task* d_tasks = nullptr;
 	uint32_t* d_order = nullptr;
 	TaskResult* d_results = nullptr;
@@ -262,6 +264,7 @@ struct Workspace
 	{
 		cudaSetDevice(device);
 		cudaFree(d_visit);
+		cudaFree(d_visit2);
 		cudaFree(d_tasks);
 		cudaFree(d_order);
 		cudaFree(d_results);
@@ -361,6 +364,7 @@ struct CudaBackend
 	float ms_scan = 0, ms_walk = 0, ms_d2h = 0, ms_pre = 0;
 	bool pre_timed = false;       // ev_pre0 / ev_pre1 bracket this call's pre-evaluation passes
 	size_t table_slots = 0;       // slots of ws->d_table that hold this call's records (0: no pre-evaluation)
+	bool use_visit2 = false;      // -s 1 with K3: the walkers jump through ws->d_visit2
 	uint32_t launches = 0;
 	std::string err;
 	int rc = NTB_OK;
@@ -678,8 +682,8 @@ struct CudaBackend
 	// (the walkers evaluate what has no record).
 	int presites(WalkArgs& a, cudaStream_t stream)
 	{
-		if (a.kp.snv || env_u64("NTB_NO_PRESITE", 0)) {
-			return NTB_OK; // -s 1: every position is a site, nothing to run ahead of
+		if (env_u64("NTB_NO_PRESITE", 0)) {
+			return NTB_OK;
 		}
 		const uint64_t total = batch->total;
 		const size_t want_items = (size_t)std::min<uint64_t>(0x7FFFFFF0ull, std::max<uint64_t>(1u << 14, total / 96));
@@ -728,13 +732,31 @@ struct CudaBackend
 			NTB_BE(cudaMemsetAsync(ws->d_table, 0, slots * sizeof(SiteRec), stream));
 		}
 		NTB_BE(cudaMemsetAsync(ws->d_ctr, 0, sizeof(Counters), stream));
-		NTB_BE(launch_heads(a, stream));
-		NTB_BE(launch_presite(a, false, stream));
-		NTB_BE(cudaEventRecord(ws->ev_pre_mid, stream));
-		NTB_BE(launch_presite(a, true, stream));
+		if (a.kp.snv) {
+			// K3: every valid position is a site; the walkers get a bitmap of the ones that do something
+			const size_t words = batch->n_tiles * SCAN_BITWORDS + 16;
+			if (!use_visit2) {
+				if (words > ws->cap_visit2) {
+					cudaFree(ws->d_visit2);
+					ws->d_visit2 = nullptr;
+					ws->cap_visit2 = 0;
+					NTB_BE(cudaMalloc((void**)&ws->d_visit2, words * 4));
+					ws->cap_visit2 = words;
+				}
+				NTB_BE(cudaMemsetAsync(ws->d_visit2, 0, words * 4, stream)); // (the contig groups of a call share it)
+				use_visit2 = true;
+			}
+			NTB_BE(launch_snv_dense(a, ws->d_visit2, stream));
+			NTB_BE(cudaEventRecord(ws->ev_pre_mid, stream));
+		} else {
+			NTB_BE(launch_heads(a, stream));
+			NTB_BE(launch_presite(a, false, stream));
+			NTB_BE(cudaEventRecord(ws->ev_pre_mid, stream));
+			NTB_BE(launch_presite(a, true, stream));
+		}
 		NTB_BE(cudaMemcpyAsync(ws->h_ctr_pre, ws->d_ctr, sizeof(Counters), cudaMemcpyDeviceToHost, stream));
 		NTB_BE(cudaEventRecord(ws->ev_pre1, stream));
-		launches += presite_launch_count();
+		launches += a.kp.snv ? 1u : presite_launch_count();
 		pre_timed = true;
 		table_slots = slots;
 		return NTB_OK;
@@ -812,6 +834,9 @@ struct CudaBackend
 			// (later rounds look the same records up)
 			wa.table = ws->d_table;
 			wa.table_mask = (uint32_t)(table_slots - 1);
+		}
+		if (use_visit2) {
+			wa.visit = ws->d_visit2;
 		}
 		for (;;) {
 			wa.events = ws->d_events;

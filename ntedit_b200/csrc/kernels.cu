@@ -1070,6 +1070,52 @@ presite_dense_kernel(const uint8_t* text, const uint32_t* visit, FilterView bloo
 	}
 }
 
+// K3 snv_dense_kernel (-s 1, ntedit.cpp:1806 "opt::snv ||": every valid window is a site): one thread per position
+// evaluates the site from the text (site_dense.h: dense_site -- draft baseline from the check subset, gates, sampled
+// trial windows, best / alternates), files a record for the positions whose commit does something (an accepted
+// substitution, a variant record, a case change) and marks them in a second bitmap.  The walkers then jump through THAT
+// bitmap: between two such positions the main loop's iterations have no observable effect.  One warp per task, lanes on
+// consecutive positions (their text and their filter probes are independent; neighbouring windows share cache lines of text).
+template<int KCAP>
+__global__ void __launch_bounds__(DENSE_THREADS)
+snv_dense_kernel(const uint8_t* text, const uint32_t* visit, uint32_t* visit2, FilterView bloom, FilterView rep, const __grid_constant__ KParams kp,
+                 const Task* tasks, uint32_t n_tasks, SiteRec* table, uint32_t table_mask, Counters* ctr)
+{
+	__shared__ uint64_t rot[ROT_WORDS];
+	__shared__ uint8_t cls[256];
+	for (uint32_t q = threadIdx.x; q < ROT_WORDS; q += blockDim.x) {
+		rot[q] = rot_entry(q);
+	}
+	for (uint32_t q = threadIdx.x; q < 256; q += blockDim.x) {
+		cls[q] = class_of(q);
+	}
+	__syncthreads();
+	DenseCtx C;
+	C.kp = &kp;
+	C.bloom = bloom;
+	C.rep = rep;
+	C.rot = rot;
+	C.cls = cls;
+	const uint32_t lane = threadIdx.x & 31u;
+	const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+	for (uint32_t ti = warp; ti < n_tasks; ti += n_warps) {
+		const Task t = tasks[ti];
+		for (uint32_t p0 = t.start; p0 < t.end; p0 += 32) {
+			const uint32_t pos = p0 + lane;
+			const uint64_t g = t.text_off + pos;
+			if (pos >= t.end || !((visit[g >> 5] >> (g & 31)) & 1u)) {
+				continue;
+			}
+			SiteRec r;
+			const uint32_t st = dense_site<KCAP>(C, text + t.text_off, t.len, pos, r);
+			if (dense_has_effect(st, r, kp.mask != 0)) {
+				atomicOr(&visit2[g >> 5], 1u << (g & 31));
+				dense_commit(r, st, t.text_off, ti, pos, table, table_mask, nullptr, 0, ctr);
+			}
+		}
+	}
+}
+
 template<int NCAP, bool COMMON, bool POW2>
 __global__ void __launch_bounds__(WALK_THREADS, NTB_WALK_MIN_CTAS)
 walk_kernel(const uint8_t* text, const uint32_t* visit, FilterView bloom, FilterView rep, const __grid_constant__ KParams kp,
@@ -1364,6 +1410,32 @@ launch_presite(const WalkArgs& a, bool second, cudaStream_t stream)
 		return launch_presite_first(a, stream);
 	}
 	return a.kp.k <= 48 ? launch_presite_dense_k<48>(a, stream) : launch_presite_dense_k<(int)KMAX>(a, stream);
+}
+
+template<int KCAP>
+static cudaError_t
+launch_snv_dense_k(const WalkArgs& a, uint32_t* visit2, cudaStream_t stream)
+{
+	static OccCache cache;
+	int per_sm = 0;
+	cudaError_t e = walker_occupancy(snv_dense_kernel<KCAP>, cache, 0, DENSE_THREADS, &per_sm);
+	if (e != cudaSuccess) {
+		return e;
+	}
+	const uint64_t warps_per_cta = DENSE_THREADS / 32;
+	const uint64_t want = ((uint64_t)a.n_tasks + warps_per_cta - 1) / warps_per_cta, cap = (uint64_t)a.sm_count * (uint64_t)per_sm;
+	snv_dense_kernel<KCAP><<<(unsigned)(want < cap ? want : cap), DENSE_THREADS, 0, stream>>>(a.text, a.visit, visit2, a.bloom, a.rep, a.kp, a.tasks,
+	                                                                                      a.n_tasks, a.table, a.table_mask, a.ctr);
+	return cudaGetLastError();
+}
+
+cudaError_t
+launch_snv_dense(const WalkArgs& a, uint32_t* visit2, cudaStream_t stream)
+{
+	if (a.n_tasks == 0) {
+		return cudaSuccess;
+	}
+	return a.kp.k <= 48 ? launch_snv_dense_k<48>(a, visit2, stream) : launch_snv_dense_k<(int)KMAX>(a, visit2, stream);
 }
 
 uint32_t

@@ -8,6 +8,8 @@
 //                           window, ahead of the walk, into a table of site records (ntb_common.h: SiteRec): first pass one
 //                           THREAD per site (site_dense.h: check-missing, gates, substitution trials), second pass one warp
 //                           per site that needs tryIndels
+//   K3  snv_dense_kernel  : -s 1 -- every valid position is a site: one thread per position evaluates it from the text and
+//                           marks the few that do something; the walk jumps through those
 //   K2  walk_kernel       : one warp per contig segment replays the edit state machine (engine.h) at the flagged positions:
 //                           commits pre-evaluated sites, evaluates the others (dirty windows) one candidate k-mer series per lane
 //                           replaces ntedit.cpp:1808-2116 (check-missing, substitutions, tryIndels, tryDeletion, makeEdit decisions)
@@ -148,6 +150,9 @@ cudaError_t launch_walk(const WalkArgs& a, cudaStream_t stream);
 cudaError_t launch_heads(const WalkArgs& a, cudaStream_t stream);
 cudaError_t launch_presite(const WalkArgs& a, bool second, cudaStream_t stream);
 uint32_t presite_launch_count(); // kernels launch_heads + both passes launch
+// K3 (-s 1): evaluates every valid position of the tasks' nominal ranges, files the records of the sites that do something
+// and marks those in `visit2` (zeroed by the caller, same geometry as a.visit); the walkers then take visit2 as their bitmap
+cudaError_t launch_snv_dense(const WalkArgs& a, uint32_t* visit2, cudaStream_t stream);
 
 // lays every walker's events out contiguously in `out`, in emission order; results[i].last_event becomes the index of the first
 cudaError_t launch_compact_events(const Event* in, Event* out, TaskResult* results, uint32_t n_tasks, Counters* ctr, cudaStream_t stream);

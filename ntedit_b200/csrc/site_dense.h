@@ -322,13 +322,18 @@ dense_site(const DenseCtx& C, const uint8_t* text, uint32_t len, uint32_t pos, S
 		}
 		const uint32_t xcl = cls[(cands >> (8 * c)) & 0xFF];
 		const uint32_t xf = xcl & 7u, xr = (xcl >> 3) & 7u;
-		for (uint32_t R0 = 1; R0 <= n_sub; R0 += B) {
+		// -s 1 never jumps behind a substitution (every position is a site), so only the sampled windows are read there:
+		// window index w stands for R = 1 + w * stride rolls
+		const uint32_t stride = snv ? jump : 1u;
+		const uint32_t n_win = n_sub ? (n_sub - 1) / stride + 1 : 0;
+		for (uint32_t w0 = 0; w0 < n_win; w0 += B) {
 			uint64_t hb[B];
 			uint32_t val[B];
-			const uint32_t n = n_sub + 1 - R0 < (uint32_t)B ? n_sub + 1 - R0 : (uint32_t)B;
+			const uint32_t n = n_win - w0 < (uint32_t)B ? n_win - w0 : (uint32_t)B;
+			const uint32_t R0 = 1 + w0 * stride;
 #pragma unroll
 			for (int i = 0; i < B; i++) {
-				const uint32_t R = (uint32_t)i < n ? R0 + i : R0;
+				const uint32_t R = (uint32_t)i < n ? R0 + i * stride : R0;
 				uint64_t f = pf[R], rv = pr[R];
 				if (R < k) {
 					f ^= rot[df * ROT_STRIDE + R] ^ rot[xf * ROT_STRIDE + R];
@@ -344,7 +349,7 @@ dense_site(const DenseCtx& C, const uint8_t* text, uint32_t len, uint32_t pos, S
 					if (solid_value(val[i])) {
 						solid |= 1u << i;
 					}
-					if (is_site_value(val[i]) && R0 + i + 1 <= k) {
+					if (is_site_value(val[i]) && R0 + i * stride + 1 <= k) {
 						loud |= 1u << c;
 					}
 				}
@@ -361,7 +366,7 @@ dense_site(const DenseCtx& C, const uint8_t* text, uint32_t len, uint32_t pos, S
 			}
 #pragma unroll
 			for (int i = 0; i < B; i++) {
-				if ((uint32_t)i < n && ((solid >> i) & 1u) && (R0 + i - 1) % jump == 0) {
+				if ((uint32_t)i < n && ((solid >> i) & 1u) && (R0 + i * stride - 1) % jump == 0) {
 					sup[c]++;
 				}
 			}
@@ -524,6 +529,14 @@ dense_commit(SiteRec& r, uint32_t st, uint64_t goff, uint32_t task_idx, uint32_t
 	}
 	table[slot] = r;
 	return true;
+}
+
+// -s 1: does committing this site do anything observable -- an edit, or an event (a variant record, a case change of the
+// tail char, -a masking)?  Sites that do not are skipped by the walk altogether (Walker::site_commit, default case).
+NTB_FN inline bool
+dense_has_effect(uint32_t st, const SiteRec& r, bool mask)
+{
+	return st == SITE_DONE && (r.best_type != 0 || (r.flags & SITE_FL_TOUCHED) || mask || r.altsupp[0] != 0);
 }
 
 // does the main loop go on to the next flagged position behind this site with a clean window (no edit was made)?

@@ -226,6 +226,90 @@ struct HostBackend
 		delete st;
 	}
 
+	// K3 (-s 1), as the CUDA backend runs it (kernels.cu: snv_dense_kernel): every valid position is a site; the dense form
+	// evaluates them all from the text, files a record for those that do something and marks them in a second bitmap -- the
+	// one the walkers then jump through.  HOSTSIM_CHECK_DENSE=1 compares every position's record with the walker's own
+	// evaluation.
+	std::vector<uint32_t> visit2;
+
+	void snv_presites(const KParams& kp, size_t n_tasks, const std::vector<uint64_t>& rot)
+	{
+		const char* ts = std::getenv("HOSTSIM_TABLE_SLOTS");
+		size_t slots = 1;
+		const size_t want = ts ? (size_t)std::strtoull(ts, nullptr, 10) : std::max<size_t>(1024, (size_t)(total / 16));
+		while (slots < want) {
+			slots <<= 1;
+		}
+		if (table.size() != slots) {
+			table.assign(slots, SiteRec());
+			std::memset(table.data(), 0, slots * sizeof(SiteRec));
+		}
+		if (visit2.size() != visit.size()) {
+			visit2.assign(visit.size(), 0u);
+		}
+		const bool check = std::getenv("HOSTSIM_CHECK_DENSE") != nullptr;
+		uint8_t cls_tab[256];
+		for (unsigned c = 0; c < 256; c++) {
+			cls_tab[c] = (uint8_t)(base_code((unsigned char)c) | (rev_code((unsigned char)c) << 3) | (is_accepted_any_case((unsigned char)c) ? 0x40u : 0u));
+		}
+		DenseCtx dctx;
+		dctx.kp = &kp;
+		dctx.bloom = bloom;
+		dctx.rep = rep;
+		dctx.rot = rot.data();
+		dctx.cls = cls_tab;
+		Counters ctr = {};
+		WalkerState<352>* st = check ? new WalkerState<352>() : nullptr;
+		for (size_t ti = 0; ti < n_tasks; ti++) {
+			const Task& t = tasks[ti];
+			for (uint64_t p = t.start; p < t.end; p++) {
+				const uint64_t g = t.text_off + p;
+				if (!((visit[g >> 5] >> (g & 31)) & 1u)) {
+					continue;
+				}
+				SiteRec r;
+				const uint32_t state = dense_site<(int)KMAX>(dctx, bases + t.text_off, t.len, (uint32_t)p, r);
+				if (dense_has_effect(state, r, kp.mask != 0)) {
+					visit2[g >> 5] |= 1u << (g & 31);
+					dense_commit(r, state, t.text_off, (uint32_t)ti, (uint32_t)p, table.data(), (uint32_t)slots - 1, nullptr, 0, &ctr);
+				}
+				if (check && dense_mismatch.empty()) {
+					WalkerIO& io = st->io;
+					io.text = bases + t.text_off;
+					io.len = t.len;
+					io.visit = visit.data();
+					io.goff = t.text_off;
+					io.bloom = bloom;
+					io.rep = rep;
+					io.events = nullptr;
+					io.ev_cap = 0;
+					io.ctr = &ctr;
+					io.rot = rot.data();
+					io.table = nullptr;
+					io.table_mask = 0;
+					io.pending = nullptr;
+					io.pending_cap = 0;
+					Walker<352, false, false> w(*st, kp);
+					w.pre_begin();
+					w.pre_seed((uint32_t)p);
+					const uint32_t wstate = w.evaluate_site_core(true);
+					SiteRec wr;
+					w.pre_fill(wr, wstate);
+					wr.key = r.key = 0;
+					if (wstate != state || std::memcmp(&wr, &r, sizeof(SiteRec)) != 0) {
+						char buf[200];
+						std::snprintf(buf, sizeof buf, "text position %llu: dense state %u type %u sub %u supp %u alt %u, walker state %u type %u sub %u supp %u alt %u",
+						              (unsigned long long)g, state, r.best_type, r.best_sub, r.support, r.altsupp[0], wstate, wr.best_type, wr.best_sub,
+						              wr.support, wr.altsupp[0]);
+						dense_mismatch = buf;
+					}
+				}
+			}
+		}
+		delete st;
+		pre_dropped += ctr.n_dropped;
+	}
+
 	void presites(const KParams& kp, size_t n_tasks, const std::vector<uint64_t>& rot)
 	{
 		if (!kp.counting && !kp.h_rep && !kp.snv && !kp.mask && bloom.mask != 0) {
@@ -248,6 +332,13 @@ struct HostBackend
 		}
 		// the pre-evaluation pass of the first round, as the CUDA backend runs it (capi.cu: CudaBackend::presites): heads of
 		// flagged runs per task, first pass (no tryIndels), second pass (the pending ones); HOSTSIM_NO_PRESITE=1 turns it off
+		if (first_round_of_group && kp.snv && !std::getenv("HOSTSIM_NO_PRESITE")) {
+			snv_presites(kp, n_tasks, rot);
+			if (!dense_mismatch.empty()) {
+				err = "dense -s 1 pass != walker: " + dense_mismatch;
+				return NTB_EINTERNAL;
+			}
+		}
 		if (first_round_of_group && !kp.snv && !std::getenv("HOSTSIM_NO_PRESITE")) {
 			presites(kp, n_tasks, rot);
 			if (!dense_mismatch.empty()) {
@@ -266,7 +357,7 @@ struct HostBackend
 				io.pending_cap = 0;
 				io.text = bases + tasks[i].text_off;
 				io.len = tasks[i].len;
-				io.visit = visit.data();
+				io.visit = visit2.empty() ? visit.data() : visit2.data(); // -s 1: only the sites that do something (snv_presites)
 				io.goff = tasks[i].text_off;
 				io.bloom = bloom;
 				io.rep = rep;
