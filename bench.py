@@ -67,9 +67,13 @@ WORKLOADS = {
 # (profiles/); None = not captured for the current kernels
 NCU_TRAFFIC = {
     "3Gbp_k25_4GiB_m1": {
-        "scan": (int((0.688038e9 + 16.137119e9 + 22.335070e9 + 0.884871e9) * 88796 / 19982),
-                 "profiles/r01y_ncu_full_bin_probe_summary.csv: (bin_kernel 16.83 GB + probe_bin_kernel 23.22 GB) per "
+        "scan": (int((16.8e9 + 23.2e9) * 88796 / 19982),
+                 "profiles/r02_ncu_full_kernels_summary.csv: (bin_kernel 16.8 GB + probe_bin_kernel 23.2 GB) per "
                  "19982-tile chunk x 88796/19982 chunks"),
+        "presite": (int(39.4e9 + 0.7e9 + 116.1e9),
+                    "profiles/r02_ncu_full_kernels_summary.csv: presite_dense_kernel round 0 39.4 GB + chain rounds 0.7 GB + "
+                    "presite_kernel (second pass) 116.1 GB; a direct 1-bit probe moves a 128-byte DRAM line"),
+        "walk": (int(22.5e9), "profiles/r02_ncu_full_kernels_summary.csv: walk_kernel 22.5 GB (276 GB in round 1)"),
     },
 }
 
@@ -801,7 +805,8 @@ def main():
                     "traffic": t[0] if t else None, "traffic_source": t[1] if t else None}
         stages = [
             stage("scan", "K1b bin_kernel + probe_bin_kernel per text chunk (filters > L2), else K1 scan_kernel", ms_scan, "scan"),
-            stage("presite", "K2p heads_kernel + presite_kernel (2 passes)", ms_pre, "presite"),
+            stage("presite", "K2p heads_kernel + presite_dense_kernel (first pass, rounds) + presite_kernel (second pass); -s 1: K3 snv_dense_kernel",
+                  ms_pre, "presite"),
             stage("walk", "K2 order_tasks_kernel + walk_kernel + compact_events_kernel, all rounds", ms_walk, "walk"),
         ]
         dev_ms = ms_scan + ms_pre + ms_walk
