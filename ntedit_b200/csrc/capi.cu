@@ -689,7 +689,23 @@ struct CudaBackend
 		const size_t want_items = (size_t)std::min<uint64_t>(0x7FFFFFF0ull, std::max<uint64_t>(1u << 14, total / 96));
 		const size_t want_pending = (size_t)std::min<uint64_t>(0x7FFFFFF0ull, std::max<uint64_t>(1u << 12, total / 384));
 		size_t slots = 1u << 12;
-		const uint64_t want_slots = std::min<uint64_t>(1ull << 31, env_u64("NTB_SITE_TABLE_SLOTS", total / 64));
+		// -s 1 files a record wherever a variant has support: with a well-filled counting filter that is a large share of all
+		// positions, so the table gets a slot per two positions as far as a third of the free memory allows
+		uint64_t dflt_slots = total / 64;
+		if (a.kp.snv) {
+			size_t free_b = 0, total_b = 0;
+			uint64_t room = 1ull << 24;
+			if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
+				room = ((uint64_t)free_b + (uint64_t)ws->cap_table * sizeof(SiteRec)) / 3 / sizeof(SiteRec);
+			}
+			dflt_slots = std::min<uint64_t>(total / 2, room);
+			uint64_t p2 = 1;
+			while (p2 * 2 <= dflt_slots) {
+				p2 *= 2; // (the loop below rounds up: stay below the memory bound)
+			}
+			dflt_slots = p2;
+		}
+		const uint64_t want_slots = std::min<uint64_t>(1ull << 31, env_u64("NTB_SITE_TABLE_SLOTS", dflt_slots));
 		while (slots < want_slots) {
 			slots <<= 1;
 		}
