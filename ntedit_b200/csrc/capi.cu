@@ -566,13 +566,24 @@ struct CudaBackend
 		A.n_buckets = nb;
 		A.region_log2 = rl;
 		const int sms = sm_count(batch->device);
+		const uint64_t bin_ctas = std::max<uint64_t>(1, env_u64("NTB_BIN_CTAS_PER_SM", BIN_CTAS_PER_SM));
 		const int probe_ctas = (int)env_u64("NTB_BIN_PROBE_CTAS_PER_SM", 3); // measured: 2 -> 81 ms, 3 -> 77, 4 -> 85, 5 -> 93
 		cudaStream_t s_probe = overlap ? ws->stream2 : ws->stream;
 		NTB_BE(cudaEventRecord(ws->ev0, ws->stream));
 		NTB_BE(cudaMemsetAsync(ws->d_visit, 0, batch->n_tiles * SCAN_BITWORDS * 4, ws->stream));
+		// A batch whose text is still arriving from the host (ntb_polish_batch) starts with a small chunk and grows from there:
+		// the first kernel then waits for 128 MB instead of a whole chunk's upload, and as long as a chunk is at most 1.25 x its
+		// predecessor a PCIe 5 upload (1.3 x the scan rate) stays ahead of the scan (NTB_BIN_FIRST_CHUNK_MB: 0 = whole chunks)
+		uint64_t cur_tiles = chunk_tiles;
+		if (batch->up_src) {
+			const uint64_t first_mb = env_u64("NTB_BIN_FIRST_CHUNK_MB", 128);
+			if (first_mb) {
+				cur_tiles = std::max<uint64_t>(1, std::min<uint64_t>(chunk_tiles, (first_mb << 20) / SCAN_TILE));
+			}
+		}
 		uint64_t c = 0;
-		for (uint64_t t0 = 0; t0 < batch->n_tiles; t0 += chunk_tiles, c++) {
-			const uint64_t nt = std::min<uint64_t>(chunk_tiles, batch->n_tiles - t0);
+		for (uint64_t t0 = 0, nt = 0; t0 < batch->n_tiles; t0 += nt, c++, cur_tiles = std::min<uint64_t>(chunk_tiles, cur_tiles + cur_tiles / 4 + 1)) {
+			nt = std::min<uint64_t>(cur_tiles, batch->n_tiles - t0);
 			const int buf = overlap ? (int)(c & 1) : 0;
 			A.scan.text = batch->d_text + t0 * SCAN_TILE;
 			A.scan.n_tiles = nt;
@@ -587,7 +598,7 @@ struct CudaBackend
 				NTB_BE(cudaStreamWaitEvent(ws->stream, ws->ev_probe[buf], 0)); // the buffer's previous chunk has been probed
 			}
 			NTB_BE(cudaMemsetAsync(A.cursor, 0, (BIN_MAX_BUCKETS + 1) * sizeof(uint32_t), ws->stream));
-			NTB_BE(launch_bin(A, bloom->counting != 0, (int)std::min<uint64_t>(nt, (uint64_t)sms * BIN_CTAS_PER_SM), ws->stream));
+			NTB_BE(launch_bin(A, bloom->counting != 0, (int)std::min<uint64_t>(nt, (uint64_t)sms * bin_ctas), ws->stream));
 			NTB_BE(cudaEventRecord(ws->ev_bin[buf], ws->stream));
 			NTB_BE(cudaStreamWaitEvent(s_probe, ws->ev_bin[buf], 0));
 			NTB_BE(launch_probe_bin(A, bloom->counting != 0, probe_ctas, s_probe));

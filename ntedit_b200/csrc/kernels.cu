@@ -396,7 +396,7 @@ st_record(uint64_t* p, uint64_t v, uint64_t policy)
 #elif NTB_BIN_STORE_HINT == 2
 	asm volatile("st.global.L2::cache_hint.u64 [%0], %1, %2;" ::"l"(p), "l"(v), "l"(policy) : "memory");
 #else
-	*p = v;
+	asm volatile("st.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory"); // (the row pointers come out of shared memory: say "global")
 #endif
 }
 
@@ -411,20 +411,21 @@ probe_misses(const uint8_t* data, uint64_t slot, uint32_t thr)
 	return ((ld_filter_u8(data + (slot >> 3)) >> ((uint32_t)slot & 7u)) & 1u) == 0;
 }
 
-template<int H, bool COUNTING>
+template<int H, bool COUNTING, bool POW2>
 __global__ void __launch_bounds__(SCAN_THREADS, BIN_CTAS_PER_SM)
 bin_kernel(const __grid_constant__ BinArgs A)
 {
 	const ScanArgs& a = A.scan;
 	constexpr int RR = SCAN_THREADS * BIN_POS_PER_ROUND * H; // records a round can produce
+	constexpr uint32_t NONE = BIN_MAX_BUCKETS;               // "bucket" of a window that is not valid: 32 spare counters, one per lane
 	extern __shared__ __align__(128) uint8_t smem[];
 	uint8_t* stage_buf = smem;                                                // BIN_STAGES * SCAN_STAGE_BYTES
-	uint64_t* sorted = (uint64_t*)(smem + BIN_STAGES * SCAN_STAGE_BYTES);    // the round's records, grouped by bucket
-	uint16_t* sorted_b = (uint16_t*)(sorted + RR);                            // their buckets
-	uint32_t* cnt = (uint32_t*)(sorted_b + RR);                               // per bucket: records of this round
-	uint32_t* off = cnt + BIN_MAX_BUCKETS;                                    // per bucket: start inside sorted[]
-	uint32_t* gbase = off + BIN_MAX_BUCKETS;                                  // per bucket: start inside the bucket's global rows
-	uint32_t* wsum = gbase + BIN_MAX_BUCKETS;                                 // [0..8) warp totals, [8] round total
+	// the round's records, grouped by bucket: slot in region : 32 | bucket : 16 | position in tile : 16 (SCAN_TILE < 2^16)
+	uint64_t* sorted = (uint64_t*)(smem + BIN_STAGES * SCAN_STAGE_BYTES);
+	uint64_t** rowp = (uint64_t**)(sorted + RR);                              // per bucket: where sorted[j] goes, minus j
+	uint32_t* cnt = (uint32_t*)(rowp + BIN_MAX_BUCKETS);                      // per bucket: records of this round (+ 32 spare)
+	uint32_t* off = cnt + BIN_MAX_BUCKETS + 32;                               // per bucket: start inside sorted[] (+ 32 spare)
+	uint32_t* wsum = off + BIN_MAX_BUCKETS + 32;                              // [0..8) warp totals, [8] round total
 	uint8_t* cls = (uint8_t*)(wsum + 16);                                     // 256
 	uint64_t* tab = (uint64_t*)(cls + 256);                                   // seed[8], rotk[8]
 	uint64_t* bars = tab + 16;                                                // BIN_STAGES mbarriers
@@ -434,8 +435,9 @@ bin_kernel(const __grid_constant__ BinArgs A)
 	for (int i = tid; i < 256; i += SCAN_THREADS) {
 		cls[i] = class_of((unsigned)i);
 	}
-	for (int i = tid; i < BIN_MAX_BUCKETS; i += SCAN_THREADS) {
+	for (int i = tid; i < BIN_MAX_BUCKETS + 32; i += SCAN_THREADS) {
 		cnt[i] = 0;
+		off[i] = 0;
 	}
 	if (tid < 8) {
 		tab[tid] = tid < 5 ? a.seed[tid] : 0;
@@ -460,6 +462,7 @@ bin_kernel(const __grid_constant__ BinArgs A)
 	const uint32_t cap = A.bucket_cap;
 	const uint32_t thr = a.min_threshold > 1u ? a.min_threshold : 1u;
 	const uint64_t pol_stream = NTB_BIN_STORE_HINT == 2 ? policy_evict_first() : 0;
+	const uint32_t none = NONE + (uint32_t)lane;
 
 	uint64_t tile = blockIdx.x;
 	uint32_t phase[BIN_STAGES];
@@ -509,15 +512,17 @@ bin_kernel(const __grid_constant__ BinArgs A)
 
 		const int o0 = strip0 - (int)k;
 		uint32_t wlo = *(const uint32_t*)(st + (o0 & ~3));
-		const uint32_t pos0 = (uint32_t)(tile * SCAN_TILE) + (uint32_t)tid * SCAN_STRIP; // position inside the chunk
+		const uint32_t tile_pos = (uint32_t)(tile * SCAN_TILE); // position of the tile inside the chunk
+		const uint32_t pit0 = (uint32_t)tid * SCAN_STRIP;       // position of the strip inside the tile
 		for (int wi = 0; wi < SCAN_STRIP / 4; wi++) {
 			const uint32_t win = *(const uint32_t*)(st + strip0 + 4 * wi);
 			const uint32_t whi = *(const uint32_t*)(st + (o0 & ~3) + 4 * wi + 4);
 			const uint32_t wout = __funnelshift_r(wlo, whi, oshift);
 			wlo = whi;
-			// ---- (a) the round's records: slot inside its region, bucket, rank inside the bucket (shared atomics)
+			// ---- (a) the round's records: slot inside its region, bucket, rank inside the bucket (shared atomics).  A window that
+			// is not valid counts on the lane's spare counter and is dropped in (c): no branch around the atomics
 			uint32_t rsir[4 * H];
-			uint32_t rbr[4 * H]; // bucket << 16 | rank ; 0xFFFFFFFF = no record
+			uint32_t rbr[4 * H]; // bucket << 16 | rank ; bucket >= NONE = no record
 #pragma unroll
 			for (int b = 0; b < 4; b++) {
 				const uint32_t ci = cls[(win >> (8 * b)) & 0xFF];
@@ -534,10 +539,10 @@ bin_kernel(const __grid_constant__ BinArgs A)
 						hv *= a.mult[i];
 						hv ^= hv >> MULTISHIFT;
 					}
-					const uint64_t slot = filter_slot(F, hv);
-					const uint32_t bucket = (uint32_t)(slot >> rl);
+					const uint64_t slot = POW2 ? (hv & F.mask) : filter_slot(F, hv);
+					const uint32_t bucket = valid ? (uint32_t)(slot >> rl) : none;
 					rsir[b * H + i] = (uint32_t)(slot & rmask);
-					rbr[b * H + i] = valid ? ((bucket << 16) | atomicAdd(&cnt[bucket], 1u)) : 0xFFFFFFFFu;
+					rbr[b * H + i] = (bucket << 16) | (atomicAdd(&cnt[bucket], 1u) & 0xFFFFu);
 				}
 			}
 			__syncthreads();
@@ -562,15 +567,18 @@ bin_kernel(const __grid_constant__ BinArgs A)
 			if (c) {
 				g = atomicAdd(&A.cursor[tid], c);
 			}
-			__syncthreads();
+			// a row that runs full in this round (heavily repeated k-mers): the round takes the checked copy-out
+			const int over = __syncthreads_or((uint64_t)g + c > (uint64_t)cap);
 			uint32_t woff = 0;
 #pragma unroll
 			for (int w = 0; w < SCAN_THREADS / 32; w++) {
 				woff += w < warp ? wsum[w] : 0u;
 			}
 			if ((uint32_t)tid < nb) {
-				off[tid] = woff + incl - c;
-				gbase[tid] = g;
+				const uint32_t o = woff + incl - c;
+				off[tid] = o;
+				// (with "over" the pointer is not used: it carries the row index of sorted[o] instead)
+				rowp[tid] = over ? (uint64_t*)(uintptr_t)(uint64_t)g : A.records + ((uint64_t)tid * cap + g) - o;
 			}
 			if (tid == SCAN_THREADS - 1) {
 				wsum[8] = woff + incl;
@@ -579,32 +587,39 @@ bin_kernel(const __grid_constant__ BinArgs A)
 			// ---- (c) group the records by bucket
 #pragma unroll
 			for (int q = 0; q < 4 * H; q++) {
-				if (rbr[q] != 0xFFFFFFFFu) {
-					const uint32_t bucket = rbr[q] >> 16;
-					const uint32_t j = off[bucket] + (rbr[q] & 0xFFFFu);
-					sorted[j] = ((uint64_t)rsir[q] << 32) | (uint64_t)(pos0 + 4 * wi + q / H);
-					sorted_b[j] = (uint16_t)bucket;
+				const uint32_t bucket = rbr[q] >> 16;
+				const uint32_t j = off[bucket] + (rbr[q] & 0xFFFFu);
+				if (bucket < NONE) {
+					sorted[j] = ((uint64_t)rsir[q] << 32) | (uint64_t)((rbr[q] & 0xFFFF0000u) | (pit0 + 4 * wi + q / H));
 				}
 			}
 			__syncthreads();
 			// ---- (d) contiguous runs out to the buckets' rows
 			const uint32_t total = wsum[8];
-			for (uint32_t j = tid; j < total; j += SCAN_THREADS) {
-				const uint32_t bucket = sorted_b[j];
-				const uint64_t rec = sorted[j];
-				const uint32_t idx = gbase[bucket] + (j - off[bucket]);
-				if (idx < cap) {
-					st_record(&A.records[(uint64_t)bucket * cap + idx], rec, pol_stream);
-				} else {
-					// the bucket's rows are full (heavily repeated k-mers): probe directly
-					const uint64_t slot = ((uint64_t)bucket << rl) | (rec >> 32);
-					if (probe_misses<COUNTING>(F.data, slot, thr)) {
-						const uint32_t pos = (uint32_t)rec;
-						atomicOr(&a.visit[pos >> 5], 1u << (pos & 31));
+			if (!over) {
+#pragma unroll 4
+				for (uint32_t j = tid; j < total; j += SCAN_THREADS) {
+					const uint2 sr = *(const uint2*)&sorted[j];
+					st_record(rowp[sr.x >> 16] + j, ((uint64_t)sr.y << 32) | (tile_pos + (sr.x & 0xFFFFu)), pol_stream);
+				}
+			} else {
+				for (uint32_t j = tid; j < total; j += SCAN_THREADS) {
+					const uint2 sr = *(const uint2*)&sorted[j];
+					const uint32_t bucket = sr.x >> 16;
+					const uint32_t pos = tile_pos + (sr.x & 0xFFFFu);
+					const uint64_t idx = (uint64_t)(uintptr_t)rowp[bucket] + (j - off[bucket]);
+					if (idx < cap) {
+						st_record(&A.records[(uint64_t)bucket * cap + idx], ((uint64_t)sr.y << 32) | pos, pol_stream);
+					} else {
+						// the bucket's rows are full: probe directly
+						const uint64_t slot = ((uint64_t)bucket << rl) | sr.y;
+						if (probe_misses<COUNTING>(F.data, slot, thr)) {
+							atomicOr(&a.visit[pos >> 5], 1u << (pos & 31));
+						}
 					}
 				}
 			}
-			// the next round's shared atomics may start: cnt[] was cleared in (b); sorted[] / off[] / gbase[] are only written
+			// the next round's shared atomics may start: cnt[] was cleared in (b); sorted[] / off[] / rowp[] are only written
 			// again after the next round's first barrier, which every thread reaches after finishing (d)
 		}
 		__syncthreads(); // tile consumed: its stage may be refilled
@@ -721,26 +736,31 @@ probe_bin_kernel(const __grid_constant__ BinArgs A)
 	}
 }
 
+template<int H, bool COUNTING, bool POW2>
+static cudaError_t
+launch_bin_hcp(const BinArgs& a, int grid, cudaStream_t stream)
+{
+	size_t smem = bin_smem_bytes(H);
+	if (const char* v = std::getenv("NTB_BIN_SMEM_PAD_KB")) {
+		smem += (size_t)std::strtoul(v, nullptr, 10) << 10; // experiment: fewer bin CTAs per SM, room for another kernel beside them
+	}
+	const cudaError_t e = cudaFuncSetAttribute(bin_kernel<H, COUNTING, POW2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+	if (e != cudaSuccess) {
+		return e;
+	}
+	bin_kernel<H, COUNTING, POW2><<<grid, SCAN_THREADS, smem, stream>>>(a);
+	return cudaGetLastError();
+}
+
 template<int H>
 static cudaError_t
 launch_bin_h(const BinArgs& a, bool counting, int grid, cudaStream_t stream)
 {
-	const size_t smem = bin_smem_bytes(H);
-	cudaError_t e;
+	const bool pow2 = a.scan.filter.mask != 0;
 	if (counting) {
-		e = cudaFuncSetAttribute(bin_kernel<H, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-		if (e != cudaSuccess) {
-			return e;
-		}
-		bin_kernel<H, true><<<grid, SCAN_THREADS, smem, stream>>>(a);
-	} else {
-		e = cudaFuncSetAttribute(bin_kernel<H, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-		if (e != cudaSuccess) {
-			return e;
-		}
-		bin_kernel<H, false><<<grid, SCAN_THREADS, smem, stream>>>(a);
+		return pow2 ? launch_bin_hcp<H, true, true>(a, grid, stream) : launch_bin_hcp<H, true, false>(a, grid, stream);
 	}
-	return cudaGetLastError();
+	return pow2 ? launch_bin_hcp<H, false, true>(a, grid, stream) : launch_bin_hcp<H, false, false>(a, grid, stream);
 }
 
 cudaError_t

@@ -83,7 +83,7 @@ inline size_t
 bin_smem_bytes(int hash_num)
 {
 	const size_t round_records = (size_t)SCAN_THREADS * BIN_POS_PER_ROUND * (size_t)hash_num;
-	return (size_t)BIN_STAGES * SCAN_STAGE_BYTES + round_records * 8 + round_records * 2 + 3 * BIN_MAX_BUCKETS * 4 + 16 * 4 + 256 + 16 * 8 +
+	return (size_t)BIN_STAGES * SCAN_STAGE_BYTES + round_records * 8 + BIN_MAX_BUCKETS * 8 + 2 * (BIN_MAX_BUCKETS + 32) * 4 + 16 * 4 + 256 + 16 * 8 +
 	       SCAN_STAGES * 8 + 64;
 }
 

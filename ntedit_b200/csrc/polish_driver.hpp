@@ -267,7 +267,13 @@ polish_run(Backend& be, const KParams& kp_in, const ntb_params& up, char* host_b
 	// host thread stitches nothing any more -- that happened in the device phase -- but replays group g's events into
 	// ropes.  The host work of a call (a quarter of the device time with every core of the box, as much as the device
 	// time when eight ranks share the cores) then hides behind the kernels except for the last group's.
-	uint64_t n_groups = 4;
+	// How many, and how unequal: every further group costs device time (launch tails, 3 ms per group at 3 Gbp), and the replay
+	// of group g has to fit beside the device phase of group g+1.  With a dozen host threads or more per GPU the replay is
+	// a fifth of the device time: two groups, the second a quarter of the first (measured at 3 Gbp, 16 threads: 177 ms per
+	// call with 4 equal groups, 174 with 4 at ratio 0.6, 170 with 3 at 0.4, 169 with 2 at 0.3).  With a few threads per GPU
+	// (eight ranks sharing one host) the replay is as long as the device phase: four groups that shrink slowly.
+	const bool many_threads = nthreads >= 12;
+	uint64_t n_groups = many_threads ? 2 : 4;
 	if (const char* v = std::getenv("NTB_CONTIG_GROUPS")) {
 		n_groups = std::max<uint64_t>(1, std::strtoull(v, nullptr, 10));
 	}
@@ -281,9 +287,23 @@ polish_run(Backend& be, const KParams& kp_in, const ntb_params& up, char* host_b
 	}
 	std::vector<uint64_t> group_first(1, 0); // first contig of every group, then n_contigs
 	{
+		// group g+1 holds `ratio` times the bases of group g: the device launches of the large early groups run at their best,
+		// and the replay nothing hides any more -- the last group's -- is small (NTB_CONTIG_GROUP_RATIO; 1 = equal groups)
 		const uint64_t total = n_contigs ? offsets[n_contigs] : 0;
+		double ratio = many_threads ? 0.25 : 0.7;
+		if (const char* v = std::getenv("NTB_CONTIG_GROUP_RATIO")) {
+			ratio = std::min(1.0, std::max(0.05, std::strtod(v, nullptr)));
+		}
+		double wsum = 0, w = 1;
+		for (uint64_t g = 0; g < n_groups; g++, w *= ratio) {
+			wsum += w;
+		}
+		double acc = 0;
+		w = 1;
 		for (uint64_t g = 1; g < n_groups; g++) {
-			const uint64_t want = total / n_groups * g;
+			acc += w;
+			w *= ratio;
+			const uint64_t want = (uint64_t)((double)total * (acc / wsum));
 			uint64_t c = std::upper_bound(offsets, offsets + n_contigs + 1, want) - offsets; // first contig that starts behind `want`
 			c = std::min<uint64_t>(c, n_contigs);
 			if (c > group_first.back()) {
