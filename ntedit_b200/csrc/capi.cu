@@ -225,6 +225,7 @@ struct Workspace
 	cudaEvent_t ev_bin[2] = { nullptr, nullptr };        // K1b: records of buffer i are complete
 	cudaEvent_t ev_probe[2] = { nullptr, nullptr };      // K1b: buffer i has been consumed
 	cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+	std::vector<cudaEvent_t> ev_scan;                    // K1 / K1b: begin / end of every scanned range of a call
 	uint32_t* d_visit = nullptr;
 	size_t cap_visit = 0; // words
 	uint32_t* d_visit2 = nullptr; // -s 1: the positions whose site does something (K3)
@@ -298,6 +299,9 @@ struct Workspace
 		}
 		if (ev1) {
 			cudaEventDestroy(ev1);
+		}
+		for (cudaEvent_t ev : ev_scan) {
+			cudaEventDestroy(ev);
 		}
 		for (int i = 0; i < 2; i++) {
 			if (ev_bin[i]) {
@@ -509,13 +513,43 @@ struct CudaBackend
 		return true;
 	}
 
-	int scan_binned(const KParams& kp, uint32_t rl, uint32_t nb)
+	// ---- K1 / K1b, enqueued range by range: the contig groups of a call are consecutive pieces of the text, and the scan
+	// of group g+1 is put on the work stream right behind the kernels of group g (walk(): after the round's copies are
+	// enqueued), so a text that is still arriving from the host is uploaded beside ALL device work, not just beside the scan.
+	KParams scan_kp;
+	bool scan_prepared = false, scan_is_binned = false;
+	BinArgs binA;
+	uint64_t bin_chunk_tiles = 0, bin_cur_tiles = 0, bin_per_buffer = 0, bin_ctas = BIN_CTAS_PER_SM, bin_chunks = 0;
+	int bin_probe_ctas = 3;
+	bool bin_overlap = false;
+	uint64_t scan_hi = 0;       // tiles [0, scan_hi) have been enqueued
+	uint64_t scan_prefetch_p = 0; // scan up to this text position behind the next round's copies (0: nothing)
+	size_t scan_ev_used = 0;    // event pairs of this call (ws->ev_scan)
+
+	int scan_prepare(const KParams& kp)
 	{
+		scan_kp = kp;
+		scan_prepared = true;
+		scan_hi = 0;
+		if (batch->n_tiles == 0) {
+			return NTB_OK;
+		}
+		// every piece of a streamed text is put on the copy stream now, in order; the ranges wait for the pieces they read
+		{
+			cudaEvent_t ev = nullptr;
+			NTB_BE(batch->upload_until(batch->total, &ev));
+		}
+		uint32_t rl = 0, nb = 0;
+		scan_is_binned = binned_geometry(kp, rl, nb);
+		if (!scan_is_binned) {
+			return NTB_OK;
+		}
 		// NTB_BIN_OVERLAP=1 (experiment, off): two record buffers, the probe kernel of chunk c on a second stream beside the bin
-		// kernel of chunk c+1.  Measured 2x SLOWER (profiles/r01b_scan_stage_tuning_overlap.jsonl): the bin kernel's 8 GB/chunk write
+		// kernel of chunk c+1.  Measured 1.6-2.5x SLOWER, also with the two kernels sized to be co-resident
+		// (profiles/r01b_scan_stage_tuning_overlap.jsonl, r02_tuning_bin_probe_overlap*.jsonl): the bin kernel's 8 GB/chunk write
 		// stream evicts the filter region the probe kernel needs in L2, so the two kernels of a chunk run back to back.
 		const uint64_t H = bloom->h;
-		const bool overlap = env_u64("NTB_BIN_OVERLAP", 0) != 0;
+		bin_overlap = env_u64("NTB_BIN_OVERLAP", 0) != 0;
 		// record scratch: fewer, larger chunks amortise the per-bucket pacing of the probe kernel (16 GB: 75 ms, 8 GB: 77 ms,
 		// 4 GB: 94 ms per 3 G positions); never more than a quarter of the memory that is free right now
 		uint64_t scratch_mb = env_u64("NTB_BIN_SCRATCH_MB", 0);
@@ -527,7 +561,7 @@ struct CudaBackend
 				scratch_mb = std::max<uint64_t>(64, std::min<uint64_t>(scratch_mb, have / 4));
 			}
 		}
-		const uint64_t budget_records = (scratch_mb << 20) / 8 / (overlap ? 2 : 1);
+		const uint64_t budget_records = (scratch_mb << 20) / 8 / (bin_overlap ? 2 : 1);
 		uint64_t chunk_tiles = budget_records / (uint64_t)((double)SCAN_TILE * (double)H * 1.06);
 		chunk_tiles = std::max<uint64_t>(1, std::min<uint64_t>(chunk_tiles, batch->n_tiles));
 		chunk_tiles = std::min<uint64_t>(chunk_tiles, (0xFFFFFFFFull / SCAN_TILE) - 1); // record positions are 32-bit
@@ -537,14 +571,14 @@ struct CudaBackend
 		if (cap > 0xFFFFFFE0ull) {
 			cap = 0xFFFFFFE0ull;
 		}
-		const size_t per_buffer = (size_t)nb * cap;
-		const size_t n_buffers = overlap ? 2 : 1;
-		if (n_buffers * per_buffer > ws->cap_records) {
+		bin_per_buffer = (uint64_t)nb * cap;
+		const size_t n_buffers = bin_overlap ? 2 : 1;
+		if (n_buffers * bin_per_buffer > ws->cap_records) {
 			cudaFree(ws->d_records);
 			ws->d_records = nullptr;
 			ws->cap_records = 0;
-			NTB_BE(cudaMalloc((void**)&ws->d_records, n_buffers * per_buffer * 8));
-			ws->cap_records = n_buffers * per_buffer;
+			NTB_BE(cudaMalloc((void**)&ws->d_records, n_buffers * bin_per_buffer * 8));
+			ws->cap_records = n_buffers * bin_per_buffer;
 		}
 		if (!ws->d_cursor) {
 			NTB_BE(cudaMalloc((void**)&ws->d_cursor, 2 * (BIN_MAX_BUCKETS + 1) * sizeof(uint32_t)));
@@ -556,113 +590,156 @@ struct CudaBackend
 				NTB_BE(cudaEventCreateWithFlags(&ws->ev_probe[i], cudaEventDisableTiming));
 			}
 		}
-		BinArgs A;
-		std::memset(&A, 0, sizeof A);
-		A.scan.filter = bloom->view();
-		A.scan.k = kp.k;
-		A.scan.min_threshold = kp.min_threshold;
-		fill_scan_tables(A.scan, kp.k);
-		A.bucket_cap = (uint32_t)cap;
-		A.n_buckets = nb;
-		A.region_log2 = rl;
-		const int sms = sm_count(batch->device);
-		const uint64_t bin_ctas = std::max<uint64_t>(1, env_u64("NTB_BIN_CTAS_PER_SM", BIN_CTAS_PER_SM));
-		const int probe_ctas = (int)env_u64("NTB_BIN_PROBE_CTAS_PER_SM", 3); // measured: 2 -> 81 ms, 3 -> 77, 4 -> 85, 5 -> 93
-		cudaStream_t s_probe = overlap ? ws->stream2 : ws->stream;
-		NTB_BE(cudaEventRecord(ws->ev0, ws->stream));
-		NTB_BE(cudaMemsetAsync(ws->d_visit, 0, batch->n_tiles * SCAN_BITWORDS * 4, ws->stream));
+		std::memset(&binA, 0, sizeof binA);
+		binA.scan.filter = bloom->view();
+		binA.scan.k = kp.k;
+		binA.scan.min_threshold = kp.min_threshold;
+		fill_scan_tables(binA.scan, kp.k);
+		binA.bucket_cap = (uint32_t)cap;
+		binA.n_buckets = nb;
+		binA.region_log2 = rl;
+		bin_ctas = std::max<uint64_t>(1, env_u64("NTB_BIN_CTAS_PER_SM", BIN_CTAS_PER_SM));
+		bin_probe_ctas = (int)env_u64("NTB_BIN_PROBE_CTAS_PER_SM", 3); // measured: 2 -> 81 ms, 3 -> 77, 4 -> 85, 5 -> 93
+		bin_chunk_tiles = chunk_tiles;
 		// A batch whose text is still arriving from the host (ntb_polish_batch) starts with a small chunk and grows from there:
 		// the first kernel then waits for 128 MB instead of a whole chunk's upload, and as long as a chunk is at most 1.25 x its
 		// predecessor a PCIe 5 upload (1.3 x the scan rate) stays ahead of the scan (NTB_BIN_FIRST_CHUNK_MB: 0 = whole chunks)
-		uint64_t cur_tiles = chunk_tiles;
+		bin_cur_tiles = chunk_tiles;
 		if (batch->up_src) {
 			const uint64_t first_mb = env_u64("NTB_BIN_FIRST_CHUNK_MB", 128);
 			if (first_mb) {
-				cur_tiles = std::max<uint64_t>(1, std::min<uint64_t>(chunk_tiles, (first_mb << 20) / SCAN_TILE));
+				bin_cur_tiles = std::max<uint64_t>(1, std::min<uint64_t>(chunk_tiles, (first_mb << 20) / SCAN_TILE));
 			}
 		}
-		uint64_t c = 0;
-		for (uint64_t t0 = 0, nt = 0; t0 < batch->n_tiles; t0 += nt, c++, cur_tiles = std::min<uint64_t>(chunk_tiles, cur_tiles + cur_tiles / 4 + 1)) {
-			nt = std::min<uint64_t>(cur_tiles, batch->n_tiles - t0);
-			const int buf = overlap ? (int)(c & 1) : 0;
+		bin_chunks = 0;
+		// the bitmap is OR-ed into: cleared once, for the whole batch
+		NTB_BE(cudaMemsetAsync(ws->d_visit, 0, batch->n_tiles * SCAN_BITWORDS * 4, ws->stream));
+		return NTB_OK;
+	}
+
+	// tiles [t0, t1) through K1b
+	int scan_binned_tiles(uint64_t t0, uint64_t t1)
+	{
+		const int sms = sm_count(batch->device);
+		cudaStream_t s_probe = bin_overlap ? ws->stream2 : ws->stream;
+		BinArgs& A = binA;
+		for (uint64_t nt = 0; t0 < t1; t0 += nt, bin_chunks++, bin_cur_tiles = std::min<uint64_t>(bin_chunk_tiles, bin_cur_tiles + bin_cur_tiles / 4 + 1)) {
+			nt = std::min<uint64_t>(bin_cur_tiles, t1 - t0);
+			const int buf = bin_overlap ? (int)(bin_chunks & 1) : 0;
 			A.scan.text = batch->d_text + t0 * SCAN_TILE;
 			A.scan.n_tiles = nt;
 			A.scan.visit = ws->d_visit + t0 * SCAN_BITWORDS;
 			A.chunk_base = t0 * SCAN_TILE;
-			A.records = ws->d_records + (size_t)buf * per_buffer;
+			A.records = ws->d_records + (size_t)buf * bin_per_buffer;
 			A.cursor = ws->d_cursor + (size_t)buf * (BIN_MAX_BUCKETS + 1);
 			if (need_text((t0 + nt) * SCAN_TILE) != NTB_OK) {
 				return rc;
 			}
-			if (overlap && c >= 2) {
+			if (bin_overlap && bin_chunks >= 2) {
 				NTB_BE(cudaStreamWaitEvent(ws->stream, ws->ev_probe[buf], 0)); // the buffer's previous chunk has been probed
 			}
 			NTB_BE(cudaMemsetAsync(A.cursor, 0, (BIN_MAX_BUCKETS + 1) * sizeof(uint32_t), ws->stream));
 			NTB_BE(launch_bin(A, bloom->counting != 0, (int)std::min<uint64_t>(nt, (uint64_t)sms * bin_ctas), ws->stream));
 			NTB_BE(cudaEventRecord(ws->ev_bin[buf], ws->stream));
 			NTB_BE(cudaStreamWaitEvent(s_probe, ws->ev_bin[buf], 0));
-			NTB_BE(launch_probe_bin(A, bloom->counting != 0, probe_ctas, s_probe));
+			NTB_BE(launch_probe_bin(A, bloom->counting != 0, bin_probe_ctas, s_probe));
 			NTB_BE(cudaEventRecord(ws->ev_probe[buf], s_probe));
 			launches += 2;
 		}
-		// the walkers (work stream) need every probe done
-		for (int i = 0; overlap && i < 2 && (uint64_t)i < c; i++) {
+		// what follows on the work stream needs every probe done
+		for (int i = 0; bin_overlap && i < 2 && (uint64_t)i < bin_chunks; i++) {
 			NTB_BE(cudaStreamWaitEvent(ws->stream, ws->ev_probe[i], 0));
 		}
-		NTB_BE(cudaEventRecord(ws->ev1, ws->stream));
 		return NTB_OK;
 	}
 
-	int scan_impl(const KParams& kp)
+	// tiles [t0, t1) through K1 (filters that fit L2, -s 1)
+	int scan_direct_tiles(uint64_t t0, uint64_t t1)
 	{
-		uint32_t rl = 0, nb = 0;
-		if (batch->n_tiles > 0 && binned_geometry(kp, rl, nb)) {
-			return scan_binned(kp, rl, nb);
-		}
 		ScanArgs a;
 		std::memset(&a, 0, sizeof a);
-		a.text = batch->d_text;
-		a.n_tiles = batch->n_tiles;
+		a.text = batch->d_text + t0 * SCAN_TILE;
+		a.n_tiles = t1 - t0;
 		a.filter = bloom->view();
-		a.k = kp.k;
-		a.min_threshold = kp.min_threshold;
-		a.snv = (uint32_t)kp.snv;
-		a.visit = ws->d_visit;
-		fill_scan_tables(a, kp.k);
-		const int grid = (int)std::min<uint64_t>(batch->n_tiles, (uint64_t)sm_count(batch->device) * 3);
-		if (need_text(batch->total) != NTB_OK) {
+		a.k = scan_kp.k;
+		a.min_threshold = scan_kp.min_threshold;
+		a.snv = (uint32_t)scan_kp.snv;
+		a.visit = ws->d_visit + t0 * SCAN_BITWORDS;
+		fill_scan_tables(a, scan_kp.k);
+		const int grid = (int)std::min<uint64_t>(a.n_tiles, (uint64_t)sm_count(batch->device) * 3);
+		if (need_text(t1 * SCAN_TILE) != NTB_OK) {
 			return rc;
 		}
-		NTB_BE(cudaEventRecord(ws->ev0, ws->stream));
 		if (grid > 0) {
 			NTB_BE(launch_scan(a, bloom->counting != 0, false, grid, ws->stream));
 			launches++;
 		}
-		NTB_BE(cudaEventRecord(ws->ev1, ws->stream));
 		return NTB_OK;
 	}
 
-	int scan_wait()
+	// enqueue the scan of every tile below text position p_end that has not been enqueued yet
+	int scan_until_impl(uint64_t p_end)
 	{
-		NTB_BE(cudaEventSynchronize(ws->ev1));
-		float ms = 0;
-		NTB_BE(cudaEventElapsedTime(&ms, ws->ev0, ws->ev1));
-		ms_scan += ms;
+		const uint64_t t1 = std::min<uint64_t>(batch->n_tiles, (std::min<uint64_t>(p_end, batch->total) + SCAN_TILE - 1) / SCAN_TILE);
+		if (t1 <= scan_hi) {
+			return NTB_OK;
+		}
+		while (ws->ev_scan.size() < 2 * (scan_ev_used + 1)) {
+			cudaEvent_t ev = nullptr;
+			NTB_BE(cudaEventCreate(&ev));
+			ws->ev_scan.push_back(ev);
+		}
+		NTB_BE(cudaEventRecord(ws->ev_scan[2 * scan_ev_used], ws->stream));
+		if ((scan_is_binned ? scan_binned_tiles(scan_hi, t1) : scan_direct_tiles(scan_hi, t1)) != NTB_OK) {
+			return rc;
+		}
+		NTB_BE(cudaEventRecord(ws->ev_scan[2 * scan_ev_used + 1], ws->stream));
+		scan_ev_used++;
+		scan_hi = t1;
 		return NTB_OK;
 	}
 
 	void scan_begin(const KParams& kp)
 	{
 		if (rc == NTB_OK) {
-			scan_impl(kp);
+			scan_prepare(kp);
 		}
 	}
 
+	void scan_until(uint64_t p_end)
+	{
+		if (rc == NTB_OK && scan_prepared) {
+			scan_until_impl(p_end);
+		}
+	}
+
+	void scan_prefetch(uint64_t p_end)
+	{
+		scan_prefetch_p = p_end;
+	}
+
+	// the work stream is idle: add up what the ranges took (waits for the text included)
 	void scan_end()
 	{
-		if (rc == NTB_OK) {
-			scan_wait();
+		if (rc != NTB_OK || !ws) {
+			return;
 		}
+		if (scan_ev_used && cudaEventSynchronize(ws->ev_scan[2 * scan_ev_used - 1]) != cudaSuccess) {
+			cuda_err(cudaGetLastError(), "cudaEventSynchronize(scan)");
+			return;
+		}
+		for (size_t i = 0; i < scan_ev_used; i++) {
+			float ms = 0;
+			if (cudaEventElapsedTime(&ms, ws->ev_scan[2 * i], ws->ev_scan[2 * i + 1]) == cudaSuccess) {
+				ms_scan += ms;
+			}
+			if (std::getenv("NTB_DEBUG_TASKS")) {
+				float a = 0;
+				cudaEventElapsedTime(&a, ws->ev_scan[0], ws->ev_scan[2 * i]);
+				std::fprintf(stderr, "[ntb] device: scan range %zu %.1f - %.1f ms\n", i, a, a + ms);
+			}
+		}
+		scan_ev_used = 0;
 	}
 
 	Task* task_buffer(size_t n)
@@ -831,7 +908,9 @@ struct CudaBackend
 			NTB_BE(cudaMalloc((void**)&ws->d_events_sorted, want * sizeof(Event)));
 			ws->cap_events = want;
 		}
-		NTB_BE(cudaMemcpyAsync(ws->d_tasks, ws->h_tasks, n * sizeof(Task), cudaMemcpyHostToDevice, stream));
+		static_assert(sizeof(Task) % 16 == 0, "tasks are fetched in 16-byte units");
+		NTB_BE(launch_fetch_host(ws->d_tasks, ws->h_tasks, n * sizeof(Task), stream));
+		launches++;
 		const FilterView fb = bloom->view();
 		FilterView fr;
 		std::memset(&fr, 0, sizeof fr);
@@ -879,6 +958,17 @@ struct CudaBackend
 			float ms = 0;
 			NTB_BE(cudaEventElapsedTime(&ms, ws->ev0, ws->ev1));
 			ms_walk += ms;
+			if (std::getenv("NTB_DEBUG_TASKS") && !ws->ev_scan.empty()) {
+				// device timeline of the call, relative to the first scanned range
+				float a = 0, b = 0, c = 0, d = 0;
+				cudaEventElapsedTime(&c, ws->ev_scan[0], ws->ev0);
+				cudaEventElapsedTime(&d, ws->ev_scan[0], ws->ev1);
+				if (pre_timed) {
+					cudaEventElapsedTime(&a, ws->ev_scan[0], ws->ev_pre0);
+					cudaEventElapsedTime(&b, ws->ev_scan[0], ws->ev_pre1);
+				}
+				std::fprintf(stderr, "[ntb] device: pre-evaluation %.1f - %.1f ms, walk %.1f - %.1f ms\n", a, b, c, d);
+			}
 			if (pre_timed) {
 				pre_timed = false;
 				NTB_BE(cudaEventElapsedTime(&ms, ws->ev_pre0, ws->ev_pre1));
@@ -918,7 +1008,16 @@ struct CudaBackend
 			}
 			NTB_BE(cudaMemcpyAsync(ws->h_results, ws->d_results, n * sizeof(TaskResult), cudaMemcpyDeviceToHost, stream));
 			NTB_BE(cudaEventRecord(ws->ev1, stream));
-			NTB_BE(cudaStreamSynchronize(stream));
+			if (scan_prefetch_p) {
+				// the next contig group's scan goes right behind this round's copies: the device works on it while the host
+				// stitches, and a text that is still being uploaded had the whole group's device phase to arrive
+				const uint64_t p = scan_prefetch_p;
+				scan_prefetch_p = 0;
+				if (scan_until_impl(p) != NTB_OK) {
+					return rc;
+				}
+			}
+			NTB_BE(cudaEventSynchronize(ws->ev1));
 			NTB_BE(cudaEventElapsedTime(&ms, ws->ev0, ws->ev1));
 			ms_d2h += ms;
 			*res_out = ws->h_results;
@@ -935,6 +1034,9 @@ struct CudaBackend
 	// diagnostics: the slowest walkers of this launch and the cycles by number of sites
 	void debug_tasks(size_t n, const Counters& ctr)
 	{
+		if (std::getenv("NTB_DEBUG_TASKS")[0] == '2') {
+			return; // timeline only
+		}
 		const TaskResult* results = ws->h_results;
 		const Task* tasks = ws->h_tasks;
 		std::vector<size_t> idx(n);

@@ -1,6 +1,7 @@
 // sm_100a kernels of the ntEdit hot path -- see kernels.cuh for the map to the reference.
 #include "kernels.cuh"
 
+#include <algorithm>
 #include <cstdlib>
 #include <mutex>
 
@@ -1270,6 +1271,28 @@ compact_events_kernel(const Event* in, Event* out, TaskResult* results, uint32_t
 	results[i].last_event = base;
 }
 
+// tasks of a round, fetched from the pinned host buffer by the SMs themselves: a cudaMemcpyAsync would queue on the
+// host-to-device copy engine behind every piece of a text that is still being uploaded
+__global__ void __launch_bounds__(256)
+fetch_host_kernel(uint4* __restrict__ dst, const uint4* __restrict__ src_host, size_t n16)
+{
+	for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x) {
+		dst[i] = src_host[i];
+	}
+}
+
+cudaError_t
+launch_fetch_host(void* dst, const void* src_host, size_t bytes, cudaStream_t stream)
+{
+	const size_t n16 = (bytes + 15) / 16; // (both buffers are allocated in whole 16-byte units)
+	if (n16 == 0) {
+		return cudaSuccess;
+	}
+	const unsigned grid = (unsigned)std::min<size_t>((n16 + 255) / 256, 1184);
+	fetch_host_kernel<<<grid, 256, 0, stream>>>((uint4*)dst, (const uint4*)src_host, n16);
+	return cudaGetLastError();
+}
+
 cudaError_t
 launch_compact_events(const Event* in, Event* out, TaskResult* results, uint32_t n_tasks, Counters* ctr, cudaStream_t stream)
 {
@@ -1325,6 +1348,12 @@ launch_presite_n(const WalkArgs& a, cudaStream_t stream)
 	cudaError_t e = walker_occupancy(presite_kernel<NCAP, COMMON, POW2, SECOND>, cache, smem, WALK_THREADS, &blocks_per_sm);
 	if (e != cudaSuccess) {
 		return e;
+	}
+	if (const char* cap = std::getenv("NTB_WALK_BLOCKS_PER_SM")) { // tuning aid
+		const int c = std::atoi(cap);
+		if (c > 0 && c < blocks_per_sm) {
+			blocks_per_sm = c;
+		}
 	}
 	// persistent grid: the number of items is only known on the device
 	const unsigned grid = (unsigned)(a.sm_count * blocks_per_sm);

@@ -155,6 +155,8 @@ uint32_t presite_launch_count(); // kernels launch_heads + both passes launch
 cudaError_t launch_snv_dense(const WalkArgs& a, uint32_t* visit2, cudaStream_t stream);
 
 // lays every walker's events out contiguously in `out`, in emission order; results[i].last_event becomes the index of the first
+// dst[0, bytes) = pinned host memory src_host[0, bytes), read by a kernel (no copy engine); whole 16-byte units
+cudaError_t launch_fetch_host(void* dst, const void* src_host, size_t bytes, cudaStream_t stream);
 cudaError_t launch_compact_events(const Event* in, Event* out, TaskResult* results, uint32_t n_tasks, Counters* ctr, cudaStream_t stream);
 
 __global__ void insert_kernel(const uint8_t* text, uint64_t total, uint8_t* data, FilterView f, const __grid_constant__ KParams kp);

@@ -4,8 +4,11 @@
 // speculative clean start turned out to be wrong, then replay the accepted events into ropes (replay.hpp).
 //
 // Backend concept:
-//   void  scan_begin(const KParams&);                      -- K1: start building the visit bitmap of the whole batch
-//   void  scan_end();                                      -- ... wait for it
+//   void  scan_begin(const KParams&);                      -- K1: get ready to build the visit bitmap (nothing is scanned yet)
+//   void  scan_until(uint64_t p_end);                      -- ... start scanning every text position below p_end that has not been
+//            started yet (asynchronous; walk() sees the bits of whatever was started before it)
+//   void  scan_prefetch(uint64_t p_end);                   -- ... do the same right behind the next walk()'s own device work
+//   void  scan_end();                                      -- ... wait for everything that was started (timing only)
 //   Task* task_buffer(size_t n);                           -- host buffer (pinned in the CUDA backend) for n tasks
 //   int   walk(const KParams&, size_t n_tasks, bool first_round_of_group, const TaskResult** results, const Event** events,
 //              size_t* n_events);
@@ -170,48 +173,13 @@ polish_run(Backend& be, const KParams& kp_in, const ntb_params& up, char* host_b
 	// first-round walkers may move their segment borders out of runs of flagged positions (engine.h: safe_boundary)
 	kp.boundary_lim = std::getenv("NTB_NO_BORDER_ADJUST") ? 0u : std::min<uint32_t>(512u, seg_len / 2);
 
-	// K1 runs while the host cuts the contigs into segments
-	be.scan_begin(kp);
-
-	// ---- segments
-	std::vector<Segment> segs;
-	std::vector<uint64_t> first_seg(n_contigs + 1, 0);
 	for (uint64_t c = 0; c < n_contigs; c++) {
-		first_seg[c] = segs.size();
-		const uint64_t len64 = offsets[c + 1] - offsets[c] - 1;
-		if (len64 >= 0xFFFFFFFEULL) {
+		if (offsets[c + 1] - offsets[c] - 1 >= 0xFFFFFFFEULL) {
 			err = "contig longer than 2^32-2 bases";
 			return NTB_EINVAL;
 		}
-		const uint32_t len = (uint32_t)len64;
-		if (len < up.min_contig_len || len == 0) {
-			continue; // dropped from all outputs, ntedit.cpp:2242-2245
-		}
-		out.contigs[c].polished = true;
-		out.stats.bases += len;
-		out.stats.contigs++;
-		if (len < kp.k) {
-			continue; // no k-mer: the rope stays the root node
-		}
-		for (uint32_t p = 0; p < len; p += seg_len) {
-			Segment s;
-			s.contig = (uint32_t)c;
-			s.p0 = p;
-			s.p1 = (len - p <= seg_len) ? len : p + seg_len;
-			s.run_start = p;
-			s.arena = -1;
-			std::memset(&s.res, 0, sizeof s.res);
-			segs.push_back(s);
-			if (s.p1 == len) {
-				break;
-			}
-		}
 	}
-	first_seg[n_contigs] = segs.size();
-
-	if (dbg) {
-		std::fprintf(stderr, "[ntb] host: %zu segments built in %.1f ms\n", segs.size(), since(t_begin));
-	}
+	be.scan_begin(kp);
 
 	// host thread pool helper: fn(i) for i in [0, n_items), dynamically scheduled
 	// host threads of this call: NTB_HOST_THREADS, else the cores of the box divided by the ranks that share it (torchrun
@@ -312,13 +280,62 @@ polish_run(Backend& be, const KParams& kp_in, const ntb_params& up, char* host_b
 		}
 		group_first.push_back(n_contigs);
 	}
+	// K1 of the first group runs while the host writes its tasks; the scan of group g+1 is enqueued behind the device work of
+	// group g (scan_prefetch): a text that is still being uploaded arrives beside all of it
+	auto group_end_pos = [&](size_t g) { return n_contigs ? offsets[group_first[g + 1]] : (uint64_t)0; };
+	if (dbg) {
+		std::fprintf(stderr, "[ntb] host: scan prepared at %.1f ms\n", since(t_begin));
+	}
+	be.scan_until(group_end_pos(0));
+	if (dbg) {
+		std::fprintf(stderr, "[ntb] host: first range enqueued at %.1f ms\n", since(t_begin));
+	}
+
+	// ---- segments
+	std::vector<Segment> segs;
+	std::vector<uint64_t> first_seg(n_contigs + 1, 0);
+	for (uint64_t c = 0; c < n_contigs; c++) {
+		first_seg[c] = segs.size();
+		const uint64_t len64 = offsets[c + 1] - offsets[c] - 1;
+		if (len64 >= 0xFFFFFFFEULL) {
+			err = "contig longer than 2^32-2 bases";
+			return NTB_EINVAL;
+		}
+		const uint32_t len = (uint32_t)len64;
+		if (len < up.min_contig_len || len == 0) {
+			continue; // dropped from all outputs, ntedit.cpp:2242-2245
+		}
+		out.contigs[c].polished = true;
+		out.stats.bases += len;
+		out.stats.contigs++;
+		if (len < kp.k) {
+			continue; // no k-mer: the rope stays the root node
+		}
+		for (uint32_t p = 0; p < len; p += seg_len) {
+			Segment s;
+			s.contig = (uint32_t)c;
+			s.p0 = p;
+			s.p1 = (len - p <= seg_len) ? len : p + seg_len;
+			s.run_start = p;
+			s.arena = -1;
+			std::memset(&s.res, 0, sizeof s.res);
+			segs.push_back(s);
+			if (s.p1 == len) {
+				break;
+			}
+		}
+	}
+	first_seg[n_contigs] = segs.size();
+
+	if (dbg) {
+		std::fprintf(stderr, "[ntb] host: %zu segments built in %.1f ms\n", segs.size(), since(t_begin));
+	}
 
 	size_t n_arenas = 0; // rounds walked so far (all groups); a round's events stay where the backend put them
 	double host_ms = 0;  // stitch passes (device phases) + replays, summed over the groups
 	std::mutex host_lock; // guards host_ms / n_edits_total / first_error between the replay thread and this one
 	uint64_t n_edits_total = 0;
 	std::string first_error;
-	bool scan_pending = true; // K1 is still running while the first group's tasks are written
 
 	// ---- device phase of a group: rounds of walkers + stitching
 	auto device_phase = [&](uint64_t c0, uint64_t c1) -> int {
@@ -357,22 +374,14 @@ polish_run(Backend& be, const KParams& kp_in, const ntb_params& up, char* host_b
 					}
 				});
 			}
-			if (scan_pending) {
-				const auto t_scan = clk::now();
-				be.scan_end();
-				scan_pending = false;
-				if (dbg) {
-					std::fprintf(stderr, "[ntb] host: scan returned after %.1f ms\n", since(t_scan));
-				}
-			}
 			const TaskResult* results = nullptr;
 			const Event* round_events = nullptr;
 			size_t n_round_events = 0;
 			const auto t_walk = clk::now();
 			const int rc = be.walk(kp, pending.size(), first_round, &results, &round_events, &n_round_events);
 			if (dbg) {
-				std::fprintf(stderr, "[ntb] host: walk round (%zu tasks, %zu events) returned after %.1f ms\n", pending.size(), n_round_events,
-				             since(t_walk));
+				std::fprintf(stderr, "[ntb] host: walk round (%zu tasks, %zu events) returned after %.1f ms (at %.1f ms)\n", pending.size(),
+				             n_round_events, since(t_walk), since(t_begin));
 			}
 			if (rc != NTB_OK) {
 				err = be.error();
@@ -465,7 +474,8 @@ polish_run(Backend& be, const KParams& kp_in, const ntb_params& up, char* host_b
 				host_ms += std::chrono::duration<double, std::milli>(clk::now() - t0).count();
 			}
 			if (dbg) {
-				std::fprintf(stderr, "[ntb] host:   take-over + stitch pass %.1f ms, %zu to re-run\n", since(t0), pending.size());
+				std::fprintf(stderr, "[ntb] host:   take-over + stitch pass %.1f ms, %zu to re-run (at %.1f ms)\n", since(t0), pending.size(),
+				             since(t_begin));
 			}
 			if (rounds > 64) {
 				err = "stitcher did not converge";
@@ -743,7 +753,8 @@ polish_run(Backend& be, const KParams& kp_in, const ntb_params& up, char* host_b
 		}
 		if (dbg) {
 			std::fprintf(stderr, "[ntb] host:   replay (C) join %.1f ms\n", since(t_c));
-			std::fprintf(stderr, "[ntb] host: replay of contigs [%llu, %llu) %.1f ms\n", (unsigned long long)c0, (unsigned long long)c1, since(t1));
+			std::fprintf(stderr, "[ntb] host: replay of contigs [%llu, %llu) %.1f ms (at %.1f ms)\n", (unsigned long long)c0, (unsigned long long)c1,
+			             since(t1), since(t_begin));
 		}
 		std::lock_guard<std::mutex> guard(host_lock);
 		host_ms += std::chrono::duration<double, std::milli>(clk::now() - t1).count();
@@ -755,6 +766,10 @@ polish_run(Backend& be, const KParams& kp_in, const ntb_params& up, char* host_b
 	int rc_groups = NTB_OK;
 	for (size_t g = 0; g + 1 < group_first.size(); g++) {
 		const uint64_t c0 = group_first[g], c1 = group_first[g + 1];
+		be.scan_until(group_end_pos(g)); // (a group without tasks never reaches the walk() that would have started it)
+		if (g + 2 < group_first.size()) {
+			be.scan_prefetch(group_end_pos(g + 1));
+		}
 		rc_groups = device_phase(c0, c1);
 		if (replay_thread.joinable()) {
 			replay_thread.join();
@@ -772,9 +787,7 @@ polish_run(Backend& be, const KParams& kp_in, const ntb_params& up, char* host_b
 	if (replay_thread.joinable()) {
 		replay_thread.join();
 	}
-	if (scan_pending) {
-		be.scan_end();
-	}
+	be.scan_end();
 	if (rc_groups != NTB_OK) {
 		return rc_groups;
 	}

@@ -43,6 +43,8 @@ struct HostBackend
 
 	// CPU stand-in for the scan kernel K1
 	void scan_end() {}
+	void scan_until(uint64_t) {}    // (scan_begin scans the whole batch at once)
+	void scan_prefetch(uint64_t) {}
 
 	void scan_begin(const KParams& kp)
 	{
