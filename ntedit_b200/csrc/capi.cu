@@ -499,7 +499,12 @@ struct CudaBackend
 			return false; // the filter sits in L2 anyway
 		}
 		const FilterView fv = bloom->view();
-		rl = (uint32_t)env_u64("NTB_BIN_REGION_LOG2", bloom->counting ? 24 : 27); // 16 MB regions: two of them hot at a time
+		// 64 MB regions, ONE of them hot at a time (the probe CTAs move from bucket to bucket in lock step, pace_lag = 1): half
+		// of the L2.  Fewer, larger buckets mean longer runs out of the bin kernel's per-round sort and fewer grid-wide waits
+		// in the probe kernel -- measured per 3 G positions on the 4 GiB filter: 16 MB regions / two hot 71.7 ms (round 1's
+		// choice), 16 MB / one hot 74.1, 32 MB / one hot 68.9, 64 MB / one hot 66.8, 128 MB 122.6; 32 MB / two hot 85.3.  The
+		// 16 GiB filter (256 buckets of 64 MB): two hot 94 ms per 2.5 G positions, one hot 68.6.
+		rl = (uint32_t)env_u64("NTB_BIN_REGION_LOG2", bloom->counting ? 26 : 29);
 		if (rl < 3) {
 			rl = 3;
 		}
@@ -598,8 +603,9 @@ struct CudaBackend
 		binA.bucket_cap = (uint32_t)cap;
 		binA.n_buckets = nb;
 		binA.region_log2 = rl;
+		binA.pace_lag = (uint32_t)std::min<uint64_t>(2, std::max<uint64_t>(1, env_u64("NTB_BIN_PACE_LAG", 1)));
 		bin_ctas = std::max<uint64_t>(1, env_u64("NTB_BIN_CTAS_PER_SM", BIN_CTAS_PER_SM));
-		bin_probe_ctas = (int)env_u64("NTB_BIN_PROBE_CTAS_PER_SM", 3); // measured: 2 -> 81 ms, 3 -> 77, 4 -> 85, 5 -> 93
+		bin_probe_ctas = (int)env_u64("NTB_BIN_PROBE_CTAS_PER_SM", 4); // 64 MB regions, one hot: 3 -> 66.8 ms, 4 -> 66.1, 5 -> 66.5
 		bin_chunk_tiles = chunk_tiles;
 		// A batch whose text is still arriving from the host (ntb_polish_batch) starts with a small chunk and grows from there:
 		// the first kernel then waits for 128 MB instead of a whole chunk's upload, and as long as a chunk is at most 1.25 x its

@@ -664,14 +664,15 @@ probe_bin_kernel(const __grid_constant__ BinArgs A)
 	uint32_t* visit = A.scan.visit;
 	const uint64_t gtid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	const uint64_t gstride = (uint64_t)gridDim.x * blockDim.x;
-	// pacing: the probes only hit L2 while every CTA works on (nearly) the same region, so a CTA may run at most one
-	// bucket ahead of the slowest one -- at most two regions are hot at any time.  A.cursor[BIN_MAX_BUCKETS] counts the
-	// (CTA, bucket) pairs that are done; the grid is launched cooperatively, so every CTA is resident and the wait ends.
+	// pacing: the probes only hit L2 while every CTA works on (nearly) the same region, so a CTA starts bucket b only when
+	// every CTA has finished bucket b - pace_lag: one region hot at a time with pace_lag = 1 (the default: regions of half
+	// the L2), two with pace_lag = 2.  A.cursor[BIN_MAX_BUCKETS] counts the (CTA, bucket) pairs that are done; the grid is
+	// launched cooperatively, so every CTA is resident and the wait ends.
 	unsigned int* done = A.cursor + BIN_MAX_BUCKETS;
 	for (uint32_t b = 0; b < A.n_buckets; b++) {
-		if (b >= 2) {
+		if (b >= A.pace_lag) {
 			if (threadIdx.x == 0) {
-				const unsigned int target = (b - 1) * gridDim.x;
+				const unsigned int target = (b + 1 - A.pace_lag) * gridDim.x;
 				unsigned int seen;
 				do {
 					asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(done) : "memory");

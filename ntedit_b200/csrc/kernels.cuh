@@ -96,6 +96,7 @@ struct BinArgs
 	uint32_t bucket_cap;
 	uint32_t n_buckets;
 	uint32_t region_log2;   // slots per region = 1 << region_log2
+	uint32_t pace_lag;      // probe kernel: a CTA starts bucket b when every CTA has finished bucket b - pace_lag (1 or 2)
 };
 
 // bin_kernel<hash_num, counting> on `grid` persistent CTAs

@@ -622,7 +622,17 @@ polish_run(Backend& be, const KParams& kp_in, const ntb_params& up, char* host_b
 				const Segment& sg = segs[acc[a]];
 				// the backend hands every walker's events over as one contiguous run, first event first
 				const Event* run = sg.res.n_events ? arena_base[(size_t)sg.arena] + sg.res.last_event : nullptr;
+				// a substitution is written into the caller's text at the event's position: a random byte of a multi-GB buffer
+				// per event, so the lines are requested a few events ahead
+				constexpr uint32_t AHEAD = 8;
+				char* const text_c = host_bases ? host_bases + offsets[c] : nullptr;
+				for (uint32_t q = 0; text_c && q < AHEAD && q < sg.res.n_events; q++) {
+					__builtin_prefetch(text_c + run[q].t_pos, 1, 0);
+				}
 				for (uint32_t q = 0; q < sg.res.n_events; q++) {
+					if (text_c && q + AHEAD < sg.res.n_events) {
+						__builtin_prefetch(text_c + run[q + AHEAD].t_pos, 1, 0);
+					}
 					Event ev = run[q];
 					ev.base = resolve(ev.base);
 					for (int x = 0; x < 3; x++) {
