@@ -66,93 +66,23 @@ WORKLOADS = {
 # dram__bytes_read.sum + dram__bytes_write.sum per stage and step from the committed `ncu --set full` capture of this command
 # (profiles/); None = not captured for the current kernels
 NCU_TRAFFIC = {
+    # profiles/r02_final_ncu_full_kernels_summary.csv holds one captured launch per kernel (the first contig group's: 80 % of
+    # the draft); a stage's traffic = captured bytes x (the stage's kernel time per call in the launch list
+    # profiles/r02_final_launches_bench_3Gbp.csv / the captured launch's time)
     "3Gbp_k25_4GiB_m1": {
-        "scan": (int((16.8e9 + 23.2e9) * 88796 / 19982),
-                 "profiles/r02_ncu_full_kernels_summary.csv: (bin_kernel 16.8 GB + probe_bin_kernel 23.2 GB) per "
-                 "19982-tile chunk x 88796/19982 chunks"),
-        "presite": (int(39.4e9 + 0.7e9 + 116.1e9),
-                    "profiles/r02_ncu_full_kernels_summary.csv: presite_dense_kernel round 0 39.4 GB + chain rounds 0.7 GB + "
-                    "presite_kernel (second pass) 116.1 GB; a direct 1-bit probe moves a 128-byte DRAM line"),
-        "walk": (int(22.5e9), "profiles/r02_ncu_full_kernels_summary.csv: walk_kernel 22.5 GB (276 GB in round 1)"),
+        "scan": (int(16.8e9 * 28.1 / 6.29 + 35.5e9 * 40.1 / 8.57),
+                 "profiles/r02_final_ncu_full_kernels_summary.csv: bin_kernel 16.8 GB per 6.29 ms launch x 28.1 ms per call + "
+                 "probe_bin_kernel 35.5 GB per 8.57 ms launch x 40.1 ms per call (16.3 GB of records written once and read once "
+                 "per 675 M positions; the 64 MB filter region is re-fetched 4.6 x per chunk)"),
+        "presite": (int(32.4e9 * 9.47 / 7.47 + 0.4e9 * 2.08 / 0.42 + 93.6e9 * 34.2 / 27.03),
+                    "profiles/r02_final_ncu_full_kernels_summary.csv: presite_dense_kernel round 0 32.4 GB per 7.47 ms x 9.47 ms per "
+                    "call + chain rounds + presite_kernel (second pass) 93.6 GB per 27.03 ms x 34.2 ms per call; a direct 1-bit "
+                    "probe moves a 128-byte DRAM line"),
+        "walk": (int(18.1e9 * 40.7 / 31.61),
+                 "profiles/r02_final_ncu_full_kernels_summary.csv: walk_kernel 18.1 GB per 31.61 ms x 40.7 ms per call (276 GB in "
+                 "round 1)"),
     },
 }
-
-
-def algorithmic_bytes_per_base(w, jump=3):
-    """A = 1 + 32 h L, L = distinct k-mer look-ups per base."""
-    look_ups = 1
-    if w.get("snv"):
-        look_ups = 1 + 3 * (1 + math.ceil(w["k"] / jump))
-    return 1 + 32 * w["h"] * look_ups
-
-
-def contig_lengths(w, rng=None):
-    if w["shape"] == "conifer":
-        # log-normal lengths scaled to the total: N50 / mean = exp(sigma^2 / 2), sigma 1.665 puts N50 at 4x the mean (5 kbp -> 20 kbp)
-        rng = np.random.default_rng(SEED)
-        x = rng.lognormal(0.0, 1.665, w["n_contigs"])
-        lens = np.maximum(200, (x / x.sum() * w["total"]).astype(np.int64))
-        lens[-1] += w["total"] - int(lens.sum())
-        if lens[-1] < 200:
-            lens[-1] = 200
-        return [int(v) for v in lens]
-    small = w["n_small"] * w["small_len"]
-    big_total = w["total"] - small
-    n = w["n_large"]
-    if w["n_small"] == 0:
-        lens = [big_total // n] * n
-    else:
-        weights = np.linspace(50, 250, n)
-        lens = [int(x) for x in weights / weights.sum() * big_total]
-    lens[-1] += big_total - sum(lens)
-    return lens + [w["small_len"]] * w["n_small"]
-
-
-class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md recipe)."""
-
-    def __init__(self, index):
-        super().__init__(daemon=True)
-        self.index = index
-        self.rows = []
-        self.stop_flag = threading.Event()
-        self.proc = None
-
-    def run(self):
-        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-             "clocks_event_reasons.sw_power_cap")
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
-                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE,
-                                         stderr=subprocess.DEVNULL, text=True)
-            for line in self.proc.stdout:
-                self.rows.append([x.strip() for x in line.split(",")])
-                if self.stop_flag.is_set():
-                    break
-        except Exception:
-            pass
-
-    def finish(self):
-        self.stop_flag.set()
-        if self.proc:
-            self.proc.terminate()
-        sm = []
-        smax = 0
-        reasons = set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            try:
-                sm.append(float(r[0]))
-                smax = max(smax, float(r[1]))
-                for nm, v in zip(names, r[3:7]):
-                    if v.lower().startswith("active"):
-                        reasons.add(nm)
-            except Exception:
-                continue
-        busy = [x for x in sm if x > 0]
-        return {"sm_mhz": float(np.median(busy)) if busy else None, "sm_max_mhz": smax or None,
-                "reasons": sorted(reasons), "samples": len(sm)}
 
 
 def gen_sequence(n, g, dev, rank, ci):
