@@ -85,6 +85,83 @@ NCU_TRAFFIC = {
 }
 
 
+def algorithmic_bytes_per_base(w, jump=3):
+    """A = 1 + 32 h L, L = distinct k-mer look-ups per base."""
+    look_ups = 1
+    if w.get("snv"):
+        look_ups = 1 + 3 * (1 + math.ceil(w["k"] / jump))
+    return 1 + 32 * w["h"] * look_ups
+
+
+def contig_lengths(w, rng=None):
+    if w["shape"] == "conifer":
+        # log-normal lengths scaled to the total: N50 / mean = exp(sigma^2 / 2), sigma 1.665 puts N50 at 4x the mean (5 kbp -> 20 kbp)
+        rng = np.random.default_rng(SEED)
+        x = rng.lognormal(0.0, 1.665, w["n_contigs"])
+        lens = np.maximum(200, (x / x.sum() * w["total"]).astype(np.int64))
+        lens[-1] += w["total"] - int(lens.sum())
+        if lens[-1] < 200:
+            lens[-1] = 200
+        return [int(v) for v in lens]
+    small = w["n_small"] * w["small_len"]
+    big_total = w["total"] - small
+    n = w["n_large"]
+    if w["n_small"] == 0:
+        lens = [big_total // n] * n
+    else:
+        weights = np.linspace(50, 250, n)
+        lens = [int(x) for x in weights / weights.sum() * big_total]
+    lens[-1] += big_total - sum(lens)
+    return lens + [w["small_len"]] * w["n_small"]
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.rows = []
+        self.stop_flag = threading.Event()
+        self.proc = None
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                self.rows.append([x.strip() for x in line.split(",")])
+                if self.stop_flag.is_set():
+                    break
+        except Exception:
+            pass
+
+    def finish(self):
+        self.stop_flag.set()
+        if self.proc:
+            self.proc.terminate()
+        sm = []
+        smax = 0
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                smax = max(smax, float(r[1]))
+                for nm, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                continue
+        busy = [x for x in sm if x > 0]
+        return {"sm_mhz": float(np.median(busy)) if busy else None, "sm_max_mhz": smax or None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
 def gen_sequence(n, g, dev, rank, ci):
     """Genome from generator g (rank independent); errors from a rank-specific generator.  Returns (truth, draft) uint8."""
     lut = torch.tensor(list(b"ACGT"), dtype=torch.uint8, device=dev)
