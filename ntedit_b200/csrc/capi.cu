@@ -724,6 +724,8 @@ struct CudaBackend
 		scan_prefetch_p = p_end;
 	}
 
+	bool text_streaming() const { return batch && batch->up_src != nullptr; }
+
 	// the work stream is idle: add up what the ranges took (waits for the text included)
 	void scan_end()
 	{

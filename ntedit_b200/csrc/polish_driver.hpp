@@ -9,6 +9,7 @@
 //            started yet (asynchronous; walk() sees the bits of whatever was started before it)
 //   void  scan_prefetch(uint64_t p_end);                   -- ... do the same right behind the next walk()'s own device work
 //   void  scan_end();                                      -- ... wait for everything that was started (timing only)
+//   bool  text_streaming() const;                          -- the text is still being copied to the device while the call runs
 //   Task* task_buffer(size_t n);                           -- host buffer (pinned in the CUDA backend) for n tasks
 //   int   walk(const KParams&, size_t n_tasks, bool first_round_of_group, const TaskResult** results, const Event** events,
 //              size_t* n_events);
@@ -240,8 +241,14 @@ polish_run(Backend& be, const KParams& kp_in, const ntb_params& up, char* host_b
 	// a fifth of the device time: two groups, the second a quarter of the first (measured at 3 Gbp, 16 threads: 177 ms per
 	// call with 4 equal groups, 174 with 4 at ratio 0.6, 170 with 3 at 0.4, 169 with 2 at 0.3).  With a few threads per GPU
 	// (eight ranks sharing one host) the replay is as long as the device phase: four groups that shrink slowly.
+	// A text that is still arriving from the host, on a host whose ranks share the PCIe uplinks (23 GB/s per GPU with eight
+	// ranks against 55 alone -- barely faster than the device works through it): the device must not sit idle until 40 % of
+	// the text is there, so the groups start small and grow (6, 10, 16, 24, 27, 17 % of the bases): 226 -> ... ms per call
+	// at 8 x 3 Gbp.
 	const bool many_threads = nthreads >= 12;
-	uint64_t n_groups = many_threads ? 2 : 4;
+	const bool grow = !many_threads && be.text_streaming() && !std::getenv("NTB_CONTIG_GROUPS") && !std::getenv("NTB_CONTIG_GROUP_RATIO");
+	static const double grow_cum[] = { 0.06, 0.16, 0.32, 0.56, 0.83 };
+	uint64_t n_groups = grow ? 6 : many_threads ? 2 : 4;
 	if (const char* v = std::getenv("NTB_CONTIG_GROUPS")) {
 		n_groups = std::max<uint64_t>(1, std::strtoull(v, nullptr, 10));
 	}
@@ -271,7 +278,7 @@ polish_run(Backend& be, const KParams& kp_in, const ntb_params& up, char* host_b
 		for (uint64_t g = 1; g < n_groups; g++) {
 			acc += w;
 			w *= ratio;
-			const uint64_t want = (uint64_t)((double)total * (acc / wsum));
+			const uint64_t want = (uint64_t)((double)total * (grow && n_groups == 6 ? grow_cum[g - 1] : acc / wsum));
 			uint64_t c = std::upper_bound(offsets, offsets + n_contigs + 1, want) - offsets; // first contig that starts behind `want`
 			c = std::min<uint64_t>(c, n_contigs);
 			if (c > group_first.back()) {

@@ -45,6 +45,7 @@ struct HostBackend
 	void scan_end() {}
 	void scan_until(uint64_t) {}    // (scan_begin scans the whole batch at once)
 	void scan_prefetch(uint64_t) {}
+	bool text_streaming() const { return false; }
 
 	void scan_begin(const KParams& kp)
 	{
