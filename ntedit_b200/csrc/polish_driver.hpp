@@ -243,8 +243,8 @@ polish_run(Backend& be, const KParams& kp_in, const ntb_params& up, char* host_b
 	// (eight ranks sharing one host) the replay is as long as the device phase: four groups that shrink slowly.
 	// A text that is still arriving from the host, on a host whose ranks share the PCIe uplinks (23 GB/s per GPU with eight
 	// ranks against 55 alone -- barely faster than the device works through it): the device must not sit idle until 40 % of
-	// the text is there, so the groups start small and grow (6, 10, 16, 24, 27, 17 % of the bases): 226 -> ... ms per call
-	// at 8 x 3 Gbp.
+	// the text is there, so the groups start small and grow (6, 10, 16, 24, 27, 17 % of the bases): 226 -> 220 ms per call
+	// at 8 x 3 Gbp, where the upload itself takes 154 ms.
 	const bool many_threads = nthreads >= 12;
 	const bool grow = !many_threads && be.text_streaming() && !std::getenv("NTB_CONTIG_GROUPS") && !std::getenv("NTB_CONTIG_GROUP_RATIO");
 	static const double grow_cum[] = { 0.06, 0.16, 0.32, 0.56, 0.83 };
