@@ -353,6 +353,9 @@ struct WalkerState
 	uint8_t rec_fl;              // ... its EV_TOUCHED flag
 	bool rec_second;             // ... it was completed by the second pre-evaluation pass (diagnostics)
 	uint32_t rec_slot;           // pre-evaluation: slot of the record being written
+	uint32_t rec_skip_T;         // ... the chain's next rec_skip_n sites make no edit and emit nothing (SITE_FL_SKIP): what they
+	uint16_t rec_skip_dist;      //     leave in the stale slots, and the distance to the last of them
+	uint8_t rec_skip_n;
 	bool pre_more;               // pre-evaluation: the chain goes on with the next position
 	// insertion candidates without rolling: hash state after q+1 rolls of an insertion of length L whose inserted chars
 	// contribute nothing (ins_base_*[L-1][sample]); the candidates add their chars' terms from the rotation table
@@ -2211,7 +2214,13 @@ struct Walker
 	// site; the chain goes on from it with everything evaluated in place.
 	NTB_FN void pre_run(uint32_t task_idx, uint32_t pos, bool allow_indels)
 	{
-		for (uint32_t n = 0; n < SITE_CHAIN_MAX; n++) {
+		// The record of the chain's first site learns how many of the sites behind it make no edit and emit nothing
+		// (SITE_FL_SKIP: the walker that commits it goes straight to the last of them); leader-only bookkeeping.
+		const bool skips = !mask_() && !snv_();
+		uint32_t sk_slot = NONE32, sk_pos = 0, sk_n = 0, sk_T = SKIP_IDENTITY;
+		bool sk_open = false;
+		// (first pass: the head and SITE_CHAIN_MAX chain sites, like the dense form's rounds)
+		for (uint32_t n = 0; n < SITE_CHAIN_MAX + (allow_indels ? 0u : 1u); n++) {
 			pre_seed(pos);
 			const uint32_t st = evaluate_site_core(allow_indels);
 			NTB_LEADER_BEGIN
@@ -2247,6 +2256,19 @@ struct Walker
 					}
 				}
 				S.io.table[slot] = r;
+				if (skips && n == 0) {
+					sk_open = dense_skippable(st, r.best_type, r.flags); // (a record that emits an event keeps its fields as they are)
+					sk_slot = slot;
+					sk_pos = pos;
+				} else if (sk_open && dense_skippable(st, r.best_type, r.flags)) {
+					sk_T = dense_skip_compose(sk_T, st, dense_pack_bases(r));
+					sk_n++;
+					SiteRec first = S.io.table[sk_slot];
+					dense_skip_store(first, sk_n, pos - sk_pos, sk_T);
+					S.io.table[sk_slot] = first;
+				} else {
+					sk_open = false;
+				}
 			}
 			// go on behind a site that made no edit
 			S.pre_more = slot != NONE32 && (st == SITE_NONE || (st == SITE_DONE && S.s.best_type == 0));
@@ -2311,6 +2333,11 @@ struct Walker
 		S.use_rec = r.state;
 		S.rec_second = (r.flags & SITE_FL_SECOND) != 0;
 		S.rec_hash = r.state == SITE_DONE && (r.best_type >= 2 || (r.best_type == 1 && !(r.flags & SITE_FL_QUIET)));
+		const bool skip = (r.flags & SITE_FL_SKIP) && (r.state == SITE_NONE || (r.state == SITE_DONE && r.best_type == 0));
+		S.rec_skip_n = skip ? r.indel_len : (uint8_t)0;
+		S.rec_skip_dist = (uint16_t)((uint32_t)(uint8_t)r.indel[4] | ((uint32_t)r.pad_[0] << 8));
+		S.rec_skip_T = (uint32_t)(uint8_t)r.indel[0] | ((uint32_t)(uint8_t)r.indel[1] << 8) | ((uint32_t)(uint8_t)r.indel[2] << 16) |
+		               ((uint32_t)(uint8_t)r.indel[3] << 24);
 		if (r.state != SITE_DONE) {
 			return;
 		}
@@ -2326,9 +2353,10 @@ struct Walker
 		s.altbase1 = (r.altbase[0] & STALE_REF) ? stale[r.altbase[0] & 3] : r.altbase[0];
 		s.altbase2 = (r.altbase[1] & STALE_REF) ? stale[r.altbase[1] & 3] : r.altbase[1];
 		s.altbase3 = (r.altbase[2] & STALE_REF) ? stale[r.altbase[2] & 3] : r.altbase[2];
-		s.indel_len = r.indel_len;
+		// (a no-edit record that carries skip information keeps it where an edit keeps its indel)
+		s.indel_len = skip ? (uint8_t)0 : r.indel_len;
 		for (int i = 0; i < 5; i++) {
-			s.indel[i] = r.indel[i];
+			s.indel[i] = skip ? (char)0 : r.indel[i];
 		}
 		S.draft = r.draft;
 		S.rec_fl = (r.flags & SITE_FL_TOUCHED) ? EV_TOUCHED : 0;
@@ -2689,6 +2717,34 @@ struct Walker
 	}
 
 	// leader: move to the next position after the site test (ntedit.cpp:2118-2138)
+	// leader: the record just committed made no edit, and says the chain's next rec_skip_n flagged positions make none and
+	// emit nothing either (SITE_FL_SKIP): go straight to the last of them -- unless it lies behind this task's end
+	NTB_FN void skip_chain()
+	{
+		const uint32_t last = S.t.pos + S.rec_skip_dist;
+		if (last >= S.t_end || !window_clean()) {
+			return;
+		}
+		S.h.pos += S.rec_skip_dist;
+		S.t.pos = last;
+		S.n_sites += S.rec_skip_n;
+#if defined(NTB_PHASE_PROF) && defined(__CUDA_ARCH__)
+		atomicAdd(&S.io.ctr->n_skipped, (uint32_t)S.rec_skip_n);
+#elif !defined(__CUDA_ARCH__)
+		S.io.ctr->n_skipped += S.rec_skip_n;
+#endif
+		const uint8_t cur[4] = { S.stale_best_sub, S.stale_alt1, S.stale_alt2, S.stale_alt3 };
+		uint8_t nw[4];
+		for (int j = 0; j < 4; j++) {
+			const uint8_t v = (uint8_t)(S.rec_skip_T >> (8 * j));
+			nw[j] = (v & STALE_REF) ? cur[v & 3] : v;
+		}
+		S.stale_best_sub = nw[0];
+		S.stale_alt1 = nw[1];
+		S.stale_alt2 = nw[2];
+		S.stale_alt3 = nw[3];
+	}
+
 	NTB_FN void advance()
 	{
 		const uint32_t k = P.k;
@@ -2979,8 +3035,12 @@ struct Walker
 		if (S.site_now && S.skip_advance) {
 			S.skip_advance = false;
 		} else {
+			if (S.site_now && S.use_rec && S.rec_skip_n) {
+				skip_chain();
+			}
 			advance();
 		}
+		S.rec_skip_n = 0;
 		NTB_LEADER_END
 		NTB_PROF(7);
 		return S.act != ACT_STOP;

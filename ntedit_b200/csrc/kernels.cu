@@ -997,7 +997,6 @@ presite_kernel(const uint8_t* text, const uint32_t* visit, FilterView bloom, Fil
 // loop would stop going on (an edit, or tryIndels pending), exactly the records the strictly sequential chain files; only
 // when all of them let it go on does the chain move to the round after.  SITE_CHAIN_MAX / DENSE_GROUP rounds.
 constexpr int DENSE_THREADS = 128;
-constexpr int DENSE_GROUP = 8;
 constexpr uint32_t DENSE_ROUNDS = 1 + SITE_CHAIN_MAX / DENSE_GROUP;
 
 __global__ void
@@ -1079,6 +1078,29 @@ presite_dense_kernel(const uint8_t* text, const uint32_t* visit, FilterView bloo
 		const bool stops = !active || !dense_continues(st, r);
 		const uint32_t stop_mask = (__ballot_sync(0xFFFFFFFFu, stops) >> gbase) & ((1u << DENSE_GROUP) - 1u);
 		const uint32_t first_stop = stop_mask ? (uint32_t)__ffs((int)stop_mask) - 1u : (uint32_t)DENSE_GROUP;
+		// a no-edit record learns how many of the chain's next sites (the lanes behind it, up to the stop) make no edit and
+		// emit nothing either: the walker jumps over them (SITE_FL_SKIP)
+		if (!kp.mask && !kp.snv) {
+			const uint64_t info = !active ? 0ull : (uint64_t)st | ((uint64_t)r.best_type << 8) | ((uint64_t)r.flags << 16) | ((uint64_t)dense_pack_bases(r) << 32);
+			uint32_t T = SKIP_IDENTITY;
+			uint32_t n_skip = 0, dist = 0;
+			bool run = active && sub < first_stop && dense_skippable(st, r.best_type, r.flags);
+#pragma unroll
+			for (uint32_t d = 1; d < (uint32_t)DENSE_GROUP; d++) {
+				const int src = (int)(gbase + ((sub + d) % DENSE_GROUP));
+				const uint64_t oi = __shfl_sync(0xFFFFFFFFu, info, src);
+				const uint32_t op = __shfl_sync(0xFFFFFFFFu, pos, src);
+				run = run && sub + d < first_stop && dense_skippable((uint32_t)(oi & 0xFF), (uint32_t)((oi >> 8) & 0xFF), (uint32_t)((oi >> 16) & 0xFF));
+				if (run) {
+					T = dense_skip_compose(T, (uint32_t)(oi & 0xFF), (uint32_t)(oi >> 32));
+					n_skip++;
+					dist = op - pos;
+				}
+			}
+			if (n_skip) {
+				dense_skip_store(r, n_skip, dist, T);
+			}
+		}
 		bool ok = true;
 		if (active && sub <= first_stop) {
 			ok = dense_commit(r, st, task.text_off, it.x, pos, table, table_mask, pending, pending_cap, ctr);

@@ -145,8 +145,64 @@ constexpr uint8_t SITE_PENDING = 3; // stopped in front of tryIndels; completed 
 constexpr uint8_t SITE_FL_TOUCHED = 1; // makeEdit's `touched && raw != draft` (EV_TOUCHED of the event)
 constexpr uint8_t SITE_FL_QUIET = 2;   // accepted substitution whose k-1 following windows are no sites: the walker jumps k
 constexpr uint8_t SITE_FL_SECOND = 4;  // completed by the second pass (diagnostics)
+// A record that made no edit may say that the chain's next sites make none either (filed by the first pass's chain rounds,
+// which evaluate DENSE_GROUP consecutive sites of a chain side by side): the walker then goes straight to the last of
+// them.  The fields an edit would use carry it: indel_len = sites to jump over (1 .. DENSE_GROUP - 1), indel[4] |
+// pad_[0] << 8 = distance to the last of them, indel[0..3] = what those sites leave in the four stale slots, each byte a
+// value or STALE_REF | j = "slot j as it is behind THIS record's site".  Only in the plain modes (no -a masking, no -s 1),
+// and only over sites that emit nothing (no SITE_FL_TOUCHED).
+constexpr uint8_t SITE_FL_SKIP = 8;
+constexpr int DENSE_GROUP = 8;         // sites of a chain one round of the first pass evaluates side by side
 constexpr uint32_t SITE_TABLE_PROBES = 64;  // linear probing gives up after this many slots (insert: the record is dropped)
 constexpr uint32_t SITE_CHAIN_MAX = 64;     // flagged positions one pre-evaluation item follows behind a failed site
+
+// ---- skip information of no-edit records (ntb_common.h: SITE_FL_SKIP)
+// may the walker jump over this site?  It makes no edit and emits nothing.
+NTB_HD bool
+dense_skippable(uint32_t st, uint32_t best_type, uint32_t flags)
+{
+	return (st == SITE_NONE || (st == SITE_DONE && best_type == 0)) && !(flags & SITE_FL_TOUCHED);
+}
+
+// T = what the four stale slots hold behind one more site (state st, bytes b = best_sub | altbase1..3 << 8..24), given T
+// before it; both packed one byte per slot, a byte being a value or STALE_REF | j
+constexpr uint32_t SKIP_IDENTITY = (uint32_t)(STALE_REF | 0) | ((uint32_t)(STALE_REF | 1) << 8) | ((uint32_t)(STALE_REF | 2) << 16) |
+                                   ((uint32_t)(STALE_REF | 3) << 24);
+
+NTB_HD uint32_t
+dense_skip_compose(uint32_t T, uint32_t st, uint32_t b)
+{
+	if (st != SITE_DONE) {
+		return T; // no attempt: the slots keep their values
+	}
+	uint32_t n = 0;
+	for (int j = 0; j < 4; j++) {
+		uint32_t v = (b >> (8 * j)) & 0xFFu;
+		if (v & STALE_REF) {
+			v = (T >> (8 * (v & 3u))) & 0xFFu;
+		}
+		n |= v << (8 * j);
+	}
+	return n;
+}
+
+NTB_HD uint32_t
+dense_pack_bases(const SiteRec& r)
+{
+	return (uint32_t)r.best_sub | ((uint32_t)r.altbase[0] << 8) | ((uint32_t)r.altbase[1] << 16) | ((uint32_t)r.altbase[2] << 24);
+}
+
+NTB_HD void
+dense_skip_store(SiteRec& r, uint32_t n, uint32_t dist, uint32_t T)
+{
+	r.flags |= SITE_FL_SKIP;
+	r.indel_len = (uint8_t)n;
+	for (int j = 0; j < 4; j++) {
+		r.indel[j] = (char)((T >> (8 * j)) & 0xFFu);
+	}
+	r.indel[4] = (char)(dist & 0xFFu);
+	r.pad_[0] = (uint8_t)(dist >> 8);
+}
 
 // a site whose pre-evaluation stopped in front of tryIndels
 struct PendingSite
@@ -173,6 +229,8 @@ struct Counters
 	uint32_t n_dropped;  // ... records that found no slot / list entry (the walkers evaluate those sites themselves)
 	uint32_t n_rec_used; // walkers: sites committed from a record (diagnostics)
 	uint32_t n_rec_used2; // ... from a record of the second pass
+	uint32_t n_skipped;  // ... no-edit sites of a chain jumped over (SITE_FL_SKIP); host builds and -DNTB_PHASE_PROF
+	uint32_t pad_;
 	unsigned long long prof[16]; // -DNTB_PHASE_PROF: leader cycles per phase of the walker
 };
 

@@ -569,4 +569,55 @@ dense_step(const DenseCtx& C, const uint8_t* text, uint32_t len, uint64_t goff, 
 	return dense_chain_next(visit, goff, len, pos, C.kp->k - 1);
 }
 
+// One chain round as the device runs it (kernels.cu: presite_dense_kernel<KCAP, true>), for host builds: the next DENSE_GROUP
+// sites of the chain behind `behind` evaluated "side by side", records kept up to the first one at which the chain stops,
+// no-edit records told how far the walker may jump.  Returns the position the next round goes on behind, or NONE32.
+template<int KCAP>
+inline uint32_t
+dense_chain_round_host(const DenseCtx& C, const uint8_t* text, uint32_t len, uint64_t goff, const uint32_t* visit, uint32_t task_idx,
+                       uint32_t behind, SiteRec* table, uint32_t table_mask, PendingSite* pending, uint32_t pending_cap, Counters* ctr)
+{
+	const uint32_t gap = C.kp->k - 1;
+	uint32_t pos[DENSE_GROUP], st[DENSE_GROUP];
+	SiteRec r[DENSE_GROUP];
+	bool active[DENSE_GROUP];
+	uint32_t p = behind, first_stop = DENSE_GROUP;
+	for (int q = 0; q < DENSE_GROUP; q++) {
+		p = p != NONE32 ? dense_chain_next(visit, goff, len, p, gap) : NONE32;
+		pos[q] = p;
+		active[q] = p != NONE32;
+		st[q] = SITE_NONE;
+		if (active[q]) {
+			st[q] = dense_site<KCAP>(C, text, len, p, r[q]);
+		}
+		if (first_stop == (uint32_t)DENSE_GROUP && (!active[q] || !dense_continues(st[q], r[q]))) {
+			first_stop = (uint32_t)q;
+		}
+	}
+	const bool skips = !C.kp->mask && !C.kp->snv;
+	bool ok_last = true;
+	for (uint32_t q = 0; q < (uint32_t)DENSE_GROUP; q++) {
+		if (!active[q] || q > first_stop) {
+			continue;
+		}
+		if (skips && q < first_stop && dense_skippable(st[q], r[q].best_type, r[q].flags)) {
+			uint32_t T = SKIP_IDENTITY;
+			uint32_t n = 0, dist = 0;
+			for (uint32_t j = q + 1; j < first_stop && dense_skippable(st[j], r[j].best_type, r[j].flags); j++) {
+				T = dense_skip_compose(T, st[j], dense_pack_bases(r[j]));
+				n++;
+				dist = pos[j] - pos[q];
+			}
+			if (n) {
+				dense_skip_store(r[q], n, dist, T);
+			}
+		}
+		const bool ok = dense_commit(r[q], st[q], goff, task_idx, pos[q], table, table_mask, pending, pending_cap, ctr);
+		if (q == (uint32_t)DENSE_GROUP - 1) {
+			ok_last = ok;
+		}
+	}
+	return first_stop == (uint32_t)DENSE_GROUP && ok_last ? pos[DENSE_GROUP - 1] : NONE32;
+}
+
 } // namespace ntb

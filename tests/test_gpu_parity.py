@@ -198,6 +198,35 @@ def test_pre_evaluation_is_optional_on_the_device(nb, oracle, monkeypatch, env):
             orep.free()
 
 
+@pytest.mark.parametrize("mode", [0, 1, 2])
+@pytest.mark.parametrize("env", [{}, {"NTB_PRESITE_DENSE": "0"}, {"NTB_NO_BORDER_ADJUST": "1"}], ids=["dense", "warp_first_pass", "nominal_borders"])
+def test_walkers_jump_over_no_edit_chains_on_the_device(nb, oracle, monkeypatch, mode, env):
+    """Novel stretches of the draft (not in the filter, too long for any indel) leave long runs of flagged positions whose
+    sites all end without an edit; the pre-evaluation passes tell the records how far the walker may jump (SITE_FL_SKIP) --
+    the dense chain rounds through shuffles, the second pass and the warp form through the chain's first record -- and the
+    outputs must not notice, stale site locals of the reference included (mode 2 reports them).  With nominal segment
+    borders the jumps also meet task ends and re-run rounds."""
+    from ntedit_b200 import synth
+    for k_, v in env.items():
+        monkeypatch.setenv(k_, v)
+    rng = np.random.default_rng(770 + mode)
+    truth = synth.random_genome(120000, rng)
+    draft = bytearray(synth.mutate(truth, rng, 1.5e-3, 3e-4).tobytes())
+    for start in range(1500, len(draft) - 400, 2500):
+        n = int(rng.integers(8, 160))
+        draft[start:start + n] = bytes(rng.choice(list(b"ACGT"), n).astype(np.uint8))
+    contigs = [(b"c0 novel stretches", bytes(draft[:70000])), (b"c1", bytes(draft[70000:]))]
+    ofilt = oracle.OracleFilter.new(1 << 18, 25, 3, False)
+    ofilt.insert_seq(truth.tobytes())
+    bloom = nb.BloomFilter.create(1 << 18, 25, 3, counting=False, device=0)
+    bloom.insert([(b"t", truth.tobytes())])
+    ofa, otsv, ovcf = oracle.polish(contigs, ofilt, oracle.default_params(25, 3, mode=mode))
+    for seg in (0, 300, 4096):
+        fa, tsv, vcf, st = nb.polish(contigs, bloom, nb.default_params(mode=mode, segment_len=seg))
+        assert fa == ofa and tsv == otsv and vcf == ovcf
+    ofilt.free()
+
+
 def test_contig_groups_pipeline_on_the_device(nb, oracle, monkeypatch):
     """Contig groups (device phase of one beside the host replay of the one before, one site table for all) on the GPU."""
     case = [c for c in tc.CASES if c["name"] == "m1"][0]

@@ -170,3 +170,26 @@ def test_contig_groups_pipeline(oracle, monkeypatch):
         fa, tsv, vcf, st = run_hostsim(inp["contigs"], filt, case["p"], segment_len=400)
         assert fa == ofa and tsv == otsv and vcf == ovcf
     filt.free()
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_walkers_jump_over_no_edit_chains(oracle, mode):
+    """Stretches of the draft that are not in the filter and cannot be fixed (novel sequence, longer than any indel) leave
+    long runs of flagged positions whose sites all end without an edit: the first pass's chain rounds tell the records how
+    far the walker may jump (SITE_FL_SKIP), and the outputs must not notice -- including the reference's stale site locals,
+    which such sites do write (mode 2 reports them)."""
+    rng = np.random.default_rng(77 + mode)
+    truth = synth.random_genome(60000, rng)
+    draft = bytearray(synth.mutate(truth, rng, 1.5e-3, 3e-4).tobytes())
+    for start in range(1500, len(draft) - 400, 2500):
+        n = int(rng.integers(8, 120))
+        draft[start:start + n] = bytes(rng.choice(list(b"ACGT"), n).astype(np.uint8))   # novel sequence
+    contigs = [(b"c0 novel stretches", bytes(draft[:35000])), (b"c1", bytes(draft[35000:]))]
+    filt = oracle.OracleFilter.new(1 << 17, 25, 3, False)
+    filt.insert_seq(truth.tobytes())
+    for seg in (0, 2048):
+        fa, tsv, vcf, st = run_hostsim(contigs, filt, dict(mode=mode), segment_len=seg)
+        ofa, otsv, ovcf = oracle.polish(contigs, filt, oracle.default_params(25, 3, mode=mode))
+        assert fa == ofa and tsv == otsv and vcf == ovcf
+        assert st.pad_ > 200, "no chain site was jumped over"
+    filt.free()
