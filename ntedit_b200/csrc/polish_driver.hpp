@@ -238,8 +238,9 @@ polish_run(Backend& be, const KParams& kp_in, const ntb_params& up, char* host_b
 	// time when eight ranks share the cores) then hides behind the kernels except for the last group's.
 	// How many, and how unequal: every further group costs device time (launch tails, 3 ms per group at 3 Gbp), and the replay
 	// of group g has to fit beside the device phase of group g+1.  With a dozen host threads or more per GPU the replay is
-	// a fifth of the device time: two groups, the second a quarter of the first (measured at 3 Gbp, 16 threads: 177 ms per
-	// call with 4 equal groups, 174 with 4 at ratio 0.6, 170 with 3 at 0.4, 169 with 2 at 0.3).  With a few threads per GPU
+	// a fifth of the device time: two groups, the second an eighth of the first (measured at 3 Gbp, 16 threads: 177 ms per
+	// call with 4 equal groups, 174 with 4 at ratio 0.6, 170 with 3 at 0.4, 169 with 2 at 0.3; later, with everything else in
+	// place, 162.4 / 160.3 / 160.0 ms resident and 169 / 166 / 168 ms end to end with 2 groups at 0.25 / 0.12 / 0.07).  With a few threads per GPU
 	// (eight ranks sharing one host) the replay is as long as the device phase: four groups that shrink slowly.
 	// A text that is still arriving from the host, on a host whose ranks share the PCIe uplinks (23 GB/s per GPU with eight
 	// ranks against 55 alone -- barely faster than the device works through it): the device must not sit idle until 40 % of
@@ -265,7 +266,7 @@ polish_run(Backend& be, const KParams& kp_in, const ntb_params& up, char* host_b
 		// group g+1 holds `ratio` times the bases of group g: the device launches of the large early groups run at their best,
 		// and the replay nothing hides any more -- the last group's -- is small (NTB_CONTIG_GROUP_RATIO; 1 = equal groups)
 		const uint64_t total = n_contigs ? offsets[n_contigs] : 0;
-		double ratio = many_threads ? 0.25 : 0.7;
+		double ratio = many_threads ? 0.12 : 0.7;
 		if (const char* v = std::getenv("NTB_CONTIG_GROUP_RATIO")) {
 			ratio = std::min(1.0, std::max(0.05, std::strtod(v, nullptr)));
 		}
