@@ -222,6 +222,8 @@ struct Workspace
 	int device = 0;
 	cudaStream_t stream = nullptr;
 	cudaStream_t stream2 = nullptr;                      // K1b: the probe kernels run beside the next chunk's bin kernel
+	cudaStream_t stream_d2h = nullptr;                   // a round's events and results go to the host beside the next group's scan
+	cudaEvent_t ev_compact = nullptr;                    // ... once they are grouped by walker
 	cudaEvent_t ev_bin[2] = { nullptr, nullptr };        // K1b: records of buffer i are complete
 	cudaEvent_t ev_probe[2] = { nullptr, nullptr };      // K1b: buffer i has been consumed
 	cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -310,6 +312,12 @@ struct Workspace
 			if (ev_probe[i]) {
 				cudaEventDestroy(ev_probe[i]);
 			}
+		}
+		if (ev_compact) {
+			cudaEventDestroy(ev_compact);
+		}
+		if (stream_d2h) {
+			cudaStreamDestroy(stream_d2h);
 		}
 		if (stream2) {
 			cudaStreamDestroy(stream2);
@@ -1006,16 +1014,26 @@ struct CudaBackend
 			if (round_block(ctr.n_events, &h_round) != NTB_OK) {
 				return rc;
 			}
+			if (!ws->stream_d2h) {
+				NTB_BE(cudaStreamCreateWithFlags(&ws->stream_d2h, cudaStreamNonBlocking));
+				NTB_BE(cudaEventCreateWithFlags(&ws->ev_compact, cudaEventDisableTiming));
+			}
 			NTB_BE(cudaEventRecord(ws->ev0, stream));
 			if (ctr.n_events) {
 				// group the events by walker on the device, then bring them over
 				NTB_BE(launch_compact_events(ws->d_events, ws->d_events_sorted, ws->d_results, (uint32_t)n, ws->d_ctr, stream));
 				launches++;
-				NTB_BE(cudaMemcpyAsync(h_round, ws->d_events_sorted, (size_t)ctr.n_events * sizeof(Event),
-				                       cudaMemcpyDeviceToHost, stream));
 			}
-			NTB_BE(cudaMemcpyAsync(ws->h_results, ws->d_results, n * sizeof(TaskResult), cudaMemcpyDeviceToHost, stream));
-			NTB_BE(cudaEventRecord(ws->ev1, stream));
+			// the copies run on their own stream (100 MB of events per 2.5 Gbp: 2 ms): the work stream goes straight on with the
+			// next group's scan.  Nothing on the work stream touches these buffers before the host has seen the copies land.
+			NTB_BE(cudaEventRecord(ws->ev_compact, stream));
+			NTB_BE(cudaStreamWaitEvent(ws->stream_d2h, ws->ev_compact, 0));
+			if (ctr.n_events) {
+				NTB_BE(cudaMemcpyAsync(h_round, ws->d_events_sorted, (size_t)ctr.n_events * sizeof(Event),
+				                       cudaMemcpyDeviceToHost, ws->stream_d2h));
+			}
+			NTB_BE(cudaMemcpyAsync(ws->h_results, ws->d_results, n * sizeof(TaskResult), cudaMemcpyDeviceToHost, ws->stream_d2h));
+			NTB_BE(cudaEventRecord(ws->ev1, ws->stream_d2h));
 			if (scan_prefetch_p) {
 				// the next contig group's scan goes right behind this round's copies: the device works on it while the host
 				// stitches, and a text that is still being uploaded had the whole group's device phase to arrive
