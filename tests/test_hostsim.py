@@ -193,3 +193,24 @@ def test_walkers_jump_over_no_edit_chains(oracle, mode):
         assert fa == ofa and tsv == otsv and vcf == ovcf
         assert st.pad_ > 200, "no chain site was jumped over"
     filt.free()
+
+
+@pytest.mark.parametrize("threads", ["16", "3"])
+def test_group_rules_for_many_and_few_host_threads(oracle, monkeypatch, threads):
+    """The contig groups of a call are sized by the host threads it may use and by how fragmented the draft is
+    (polish_driver.hpp); every rule must give the same bytes."""
+    monkeypatch.setenv("NTB_HOST_THREADS", threads)
+    monkeypatch.setenv("NTB_CONTIG_GROUP_MIN", "2000")
+    rng = np.random.default_rng(5 + int(threads))
+    truth = synth.random_genome(90000, rng)
+    draft = synth.mutate(truth, rng, 2e-3, 4e-4).tobytes()
+    filt = oracle.OracleFilter.new(1 << 17, 25, 3, False)
+    filt.insert_seq(truth.tobytes())
+    whole = [(b"c%d" % i, draft[i * 30000:(i + 1) * 30000]) for i in range(3)]
+    cuts = sorted(int(x) for x in rng.choice(len(draft), 400, replace=False))
+    frag = [(b"f%d" % i, draft[a:b]) for i, (a, b) in enumerate(zip([0] + cuts, cuts + [len(draft)])) if b - a > 0]
+    for contigs in (whole, frag):
+        fa, tsv, vcf, st = run_hostsim(contigs, filt, dict(mode=1))
+        ofa, otsv, ovcf = oracle.polish(contigs, filt, oracle.default_params(25, 3, mode=1))
+        assert fa == ofa and tsv == otsv and vcf == ovcf
+    filt.free()
