@@ -27,11 +27,18 @@ CASES = [
     (("-m", 0, "-z", 1000), dict(mode=0, min_contig_len=1000), dict(short=True)),
     (("-m", 1, "-i", 1, "-d", 4), dict(mode=1, max_insertions=1, max_deletions=4), {}),
     (("-m", 0, "-i", 0, "-d", 3), dict(mode=0, max_insertions=0, max_deletions=3), {}),
+    # novel stretches (not in the filter, too long for any indel): long chains of sites that end without an edit -- the
+    # records' jump information (SITE_FL_SKIP) and the stale site locals mode 2 reports
+    (("-m", 0), dict(mode=0), dict(novel=True)),
+    (("-m", 1), dict(mode=1), dict(novel=True)),
+    (("-m", 2), dict(mode=2), dict(novel=True)),
+    (("-m", 2, "-i", 0, "-d", 0), dict(mode=2, max_insertions=0, max_deletions=0), dict(novel=True)),
+    (("-m", 1), dict(mode=1), dict(novel=True, fbytes=1 << 14)),
 ]
 
 
 def make_case(seed, n=20000, k=25, h=3, fbytes=1 << 16, counting=False, sub_rate=2e-3, indel_rate=5e-4, ncontigs=2,
-              lower=0.01, nfrac=0.005, iupac=0.0, rep=False, cov=1, short=False):
+              lower=0.01, nfrac=0.005, iupac=0.0, rep=False, cov=1, short=False, novel=False):
     rng = np.random.default_rng(seed)
     contigs = []
     filt = po.OracleFilter.new(fbytes, k, h, counting)
@@ -43,6 +50,12 @@ def make_case(seed, n=20000, k=25, h=3, fbytes=1 << 16, counting=False, sub_rate
         if rep and c == 0:
             repf.insert_seq(truth[: n // 10].tobytes())
         draft = synth.mutate(truth, rng, sub_rate, indel_rate, lower_frac=lower, n_frac=nfrac, iupac_frac=iupac)
+        if novel:
+            d = bytearray(draft.tobytes())
+            for start in range(700, len(d) - 300, 1900):
+                m = int(rng.integers(6, 150))
+                d[start:start + m] = bytes(rng.choice(list(b"ACGT"), m).astype(np.uint8))
+            draft = np.frombuffer(bytes(d), dtype=np.uint8)
         contigs.append((b"ctg%d some comment" % c, draft.tobytes()))
     if short:
         contigs.append((b"tiny", b"ACGTACGTAC" * 30))
@@ -79,7 +92,8 @@ if __name__ == "__main__":
     nseeds = int(sys.argv[1]) if len(sys.argv) > 1 else 2
     seglens = [0, 128, 300]
     bad = 0
-    for ci in range(len(CASES)):
+    first_case = int(sys.argv[2]) if len(sys.argv) > 2 else 0
+    for ci in range(first_case, len(CASES)):
         for seed in range(nseeds):
             for sl in seglens:
                 ok, ref, mine, st, tmp = run_case(ci, seed, sl)
