@@ -214,3 +214,35 @@ def test_group_rules_for_many_and_few_host_threads(oracle, monkeypatch, threads)
         ofa, otsv, ovcf = oracle.polish(contigs, filt, oracle.default_params(25, 3, mode=1))
         assert fa == ofa and tsv == otsv and vcf == ovcf
     filt.free()
+
+
+@pytest.mark.parametrize("mode", [0, 2])
+def test_ragged_and_degenerate_contigs(oracle, mode):
+    """Lengths around k, contigs without a single valid window (all N, an N every k-1 bases), one repeated base, lower case
+    only, IUPAC codes, and an error in the very first / very last window -- next to ordinary contigs in one batch."""
+    rng = np.random.default_rng(4242 + mode)
+    k = 25
+    truth = synth.random_genome(30000, rng)
+    filt = oracle.OracleFilter.new(1 << 17, k, 3, False)
+    filt.insert_seq(truth.tobytes())
+    t = truth.tobytes()
+    body = bytearray(synth.mutate(truth, rng, 2e-3, 4e-4).tobytes())
+    first_last = bytearray(t[5000:9000])
+    first_last[3] = ord("A") if first_last[3] != ord("A") else ord("C")       # inside the first window
+    first_last[-2] = ord("G") if first_last[-2] != ord("G") else ord("T")     # inside the last window
+    no_window = bytearray(t[1000:1600])
+    for i in range(k - 2, len(no_window), k - 1):
+        no_window[i] = ord("N")
+    contigs = [
+        (b"one", t[:1]), (b"kminus1", t[100:100 + k - 1]), (b"k", t[200:200 + k]), (b"kplus1", t[300:300 + k + 1]),
+        (b"twok", t[400:400 + 2 * k]), (b"allN", b"N" * 500), (b"no valid window", bytes(no_window)),
+        (b"polyA", b"A" * 400), (b"lower", t[2000:2600].lower()), (b"iupac", t[3000:3300] + b"RYSWKM" + t[3306:3700]),
+        (b"first and last window", bytes(first_last)), (b"ordinary", bytes(body)),
+    ]
+    for min_len in (1, 100):
+        for seg in (0, 150):
+            params = dict(mode=mode, min_contig_len=min_len)
+            fa, tsv, vcf, st = run_hostsim(contigs, filt, params, segment_len=seg)
+            ofa, otsv, ovcf = oracle.polish(contigs, filt, oracle.default_params(k, 3, mode=mode), min_contig_len=min_len)
+            assert fa == ofa and tsv == otsv and vcf == ovcf
+    filt.free()
