@@ -45,7 +45,8 @@ struct HostBackend
 	void scan_end() {}
 	void scan_until(uint64_t) {}    // (scan_begin scans the whole batch at once)
 	void scan_prefetch(uint64_t) {}
-	bool text_streaming() const { return false; }
+	// (HOSTSIM_STREAMING=1: pretend the text is still being uploaded, which selects the growing contig groups)
+	bool text_streaming() const { return std::getenv("HOSTSIM_STREAMING") != nullptr; }
 
 	void scan_begin(const KParams& kp)
 	{

@@ -195,12 +195,15 @@ def test_walkers_jump_over_no_edit_chains(oracle, mode):
     filt.free()
 
 
+@pytest.mark.parametrize("streaming", [False, True])
 @pytest.mark.parametrize("threads", ["16", "3"])
-def test_group_rules_for_many_and_few_host_threads(oracle, monkeypatch, threads):
+def test_group_rules_for_many_and_few_host_threads(oracle, monkeypatch, threads, streaming):
     """The contig groups of a call are sized by the host threads it may use and by how fragmented the draft is
     (polish_driver.hpp); every rule must give the same bytes."""
     monkeypatch.setenv("NTB_HOST_THREADS", threads)
     monkeypatch.setenv("NTB_CONTIG_GROUP_MIN", "2000")
+    if streaming:
+        monkeypatch.setenv("HOSTSIM_STREAMING", "1")   # with few threads: six groups that start small and grow
     rng = np.random.default_rng(5 + int(threads))
     truth = synth.random_genome(90000, rng)
     draft = synth.mutate(truth, rng, 2e-3, 4e-4).tobytes()
